@@ -1,0 +1,239 @@
+// dmf_abi_rest.cuh -- C ABI entry points for the reverse march, the z-buffer, set cover and the OR combine.
+// Included at the end of dmf_b200.cu (same translation unit, same helpers).
+#pragma once
+
+namespace {
+
+struct RevScratch { unsigned* vis; unsigned* unocc; int* found; };
+
+int fill_rev_args(dmf_ctx* c, RevArgs& a) {
+    if (!c->cam_set) return fail("dmf_set_camera has not been called");
+    if (!c->vol_set) return fail("no volume uploaded");
+    a.vol = c->vol; a.angle = c->angle;
+    a.fx = (double)c->K[0]; a.cx = (double)c->K[2]; a.fy = (double)c->K[4]; a.cy = (double)c->K[5];
+    a.H = c->H; a.W = c->W;
+    a.centroid_hash = c->d_centroid_hash.as<u64>();
+    for (int i = 0; i < 3; i++) { a.ax[i] = c->d_axis[i].as<float>(); a.nax[i] = c->n_axis[i]; }
+    a.vis = nullptr; a.unocc = nullptr; a.vis_words32 = (int)(((c->n_occ + 63) / 64) * 2);
+    a.found_any = nullptr; a.viz = 0;
+    a.view_mark = c->d_view_mark.as<int>(); a.good_bits = c->d_good_bits.as<unsigned>();
+    a.emit_list = nullptr; a.emit_count = nullptr; a.emit_cap = 0; a.zbuf = nullptr;
+    a.counters = c->d_counters.as<u64>();
+    a.step_cap = 1000000;
+    return 0;
+}
+
+// enqueue the reverse march of n_views poses (device) into device outputs
+int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_views, unsigned* d_vis, unsigned* d_unocc, int* d_found,
+                    u64* d_emit_list, unsigned* d_emit_count, unsigned emit_cap, cudaStream_t st) {
+    if (n_views <= 0) return 0;
+    if (n_views > 65535) return fail("at most 65535 views per launch (got %d)", n_views);
+    RevArgs a; DMF_TRY(fill_rev_args(c, a));
+    DMF_TRY(c->d_inv_poses.reserve((size_t)n_views * 48));
+    k_invert_poses<<<(n_views + 127) / 128, 128, 0, st>>>(d_poses, c->d_inv_poses.as<float>(), n_views);
+    c->launches++;
+    DMF_CUDA(cudaGetLastError());
+    const size_t vw = (c->n_occ + 63) / 64;
+    if (d_vis && vw) DMF_CUDA(cudaMemsetAsync(d_vis, 0, (size_t)n_views * vw * 8, st));
+    if (d_unocc && vw) DMF_CUDA(cudaMemsetAsync(d_unocc, 0, (size_t)n_views * vw * 8, st));
+    if (d_found) DMF_CUDA(cudaMemsetAsync(d_found, 0, (size_t)n_views * 4, st));
+    if (d_emit_count) DMF_CUDA(cudaMemsetAsync(d_emit_count, 0, (size_t)n_views * 4, st));
+    a.poses = d_poses; a.inv_poses = c->d_inv_poses.as<float>();
+    a.vis = d_vis; a.unocc = d_unocc; a.found_any = d_found; a.viz = viz;
+    a.emit_list = d_emit_list; a.emit_count = d_emit_count; a.emit_cap = emit_cap;
+    if (fast) {
+        if (!c->n_occ) return 0;
+        dim3 grid((unsigned)((c->n_occ + 127) / 128), n_views);
+        k_reverse<true><<<grid, 128, 0, st>>>(a);
+    } else {
+        size_t total = (size_t)a.nax[0] * a.nax[1] * a.nax[2];
+        if (!total) return 0;
+        size_t gx = (total + 127) / 128;
+        if (gx > 0x7fffffffull) return fail("grid too large for the whole-grid reverse scan");
+        dim3 grid((unsigned)gx, n_views);
+        k_reverse<false><<<grid, 128, 0, st>>>(a);
+    }
+    c->launches++;
+    DMF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmf_reverse_dev(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_views, const dmf_reverse_out* d_out, void* stream) {
+    if (!c || !d_out) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    if (d_out->ids || d_out->ids_offsets) return fail("dmf_reverse_dev does not produce id lists; use dmf_reverse or the visibility bitset");
+    cudaStream_t st = pick_stream(c, stream);
+    DMF_CUDA(cudaEventRecord(c->ev_k0, st));
+    DMF_TRY(enqueue_reverse(c, fast, viz, d_poses, n_views, (unsigned*)d_out->visibility, (unsigned*)d_out->unoccluded, d_out->found_any, nullptr, nullptr, 0, st));
+    DMF_CUDA(cudaEventRecord(c->ev_k1, st));
+    c->timed = true;
+    return 0;
+}
+
+int dmf_reverse(dmf_ctx* c, int fast, int viz, const float* poses, int n_views, const dmf_reverse_out* out) {
+    if (!c || !out || (!poses && n_views > 0)) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    if (!c->vol_set) return fail("no volume uploaded");
+    const size_t vw = (c->n_occ + 63) / 64;
+    const bool want_ids = out->ids_offsets != nullptr;
+    if (want_ids) out->ids_offsets[0] = 0;
+    cudaStream_t st = c->stream;
+    const unsigned emit_cap = (unsigned)std::min<size_t>(2 * c->n_occ + 64, 0x7fffffffu);
+    size_t per_view = 48 + 2 * vw * 8 + 16 + (want_ids ? (fast ? c->n_occ * 4 : (size_t)emit_cap * 16) : 0);
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n_views, (size_t)4096, ((size_t)1 << 30) / per_view}));
+    int64_t ids_total = 0;
+    DMF_CUDA(cudaEventRecord(c->ev_k0, st));
+    for (int v0 = 0; v0 < n_views; v0 += chunk) {
+        const int nv = std::min(chunk, n_views - v0);
+        DevBuf* ob = c->d_out[0];
+        DMF_TRY(c->d_poses[0].reserve((size_t)nv * 48));
+        DMF_CUDA(cudaMemcpyAsync(c->d_poses[0].p, poses + 12 * (size_t)v0, (size_t)nv * 48, cudaMemcpyHostToDevice, st));
+        DMF_TRY(ob[3].reserve(std::max<size_t>(nv * vw * 8, 8))); DMF_TRY(ob[6].reserve(std::max<size_t>(nv * vw * 8, 8))); DMF_TRY(ob[4].reserve((size_t)nv * 4));
+        unsigned* d_vis = ob[3].as<unsigned>(); unsigned* d_unocc = ob[6].as<unsigned>(); int* d_found = ob[4].as<int>();
+        u64* d_emit = nullptr; unsigned* d_emit_count = nullptr;
+        if (want_ids && !fast) {
+            DMF_TRY(c->d_misc[0].reserve((size_t)nv * emit_cap * 16)); DMF_TRY(c->d_misc[1].reserve((size_t)nv * 4));
+            d_emit = c->d_misc[0].as<u64>(); d_emit_count = c->d_misc[1].as<unsigned>();
+        }
+        DMF_TRY(enqueue_reverse(c, fast, viz, c->d_poses[0].as<float>(), nv, d_vis, d_unocc, d_found, d_emit, d_emit_count, emit_cap, st));
+        if (want_ids && fast) {
+            // emission order of reverseRayTraceFast == occupied order: expand each view's bitset in ascending order
+            std::vector<int> n_ids(nv, 0);
+            std::vector<long long> offs(nv + 1, 0);
+            if (c->n_occ) {
+                DMF_TRY(c->d_out_occ.reserve((size_t)nv * c->n_occ * 4)); DMF_TRY(c->d_n_ids.reserve((size_t)nv * 4)); DMF_TRY(c->d_offsets.reserve((size_t)(nv + 1) * 8));
+                k_bits_to_list<<<nv, 256, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_out_occ.as<int>(), c->d_n_ids.as<int>(), (int)c->n_occ);
+                c->launches++;
+                DMF_CUDA(cudaGetLastError());
+                DMF_CUDA(cudaMemcpyAsync(n_ids.data(), c->d_n_ids.p, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+                DMF_CUDA(cudaStreamSynchronize(st));
+            }
+            for (int i = 0; i < nv; i++) offs[i + 1] = offs[i] + n_ids[i];
+            if ((size_t)(ids_total + offs[nv]) > out->ids_capacity || (!out->ids && offs[nv] > 0)) return fail("ids_capacity %zu too small (need >= %lld)", out->ids_capacity, (long long)(ids_total + offs[nv]));
+            if (offs[nv] > 0) {
+                DMF_TRY(c->d_ids.reserve((size_t)offs[nv] * 8));
+                DMF_CUDA(cudaMemcpyAsync(c->d_offsets.p, offs.data(), (size_t)(nv + 1) * 8, cudaMemcpyHostToDevice, st));
+                k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->d_centroid_hash.as<u64>(), c->d_ids.as<u64>(), (int)c->n_occ);
+                c->launches++;
+                DMF_CUDA(cudaGetLastError());
+                DMF_CUDA(cudaMemcpyAsync(out->ids + ids_total, c->d_ids.p, (size_t)offs[nv] * 8, cudaMemcpyDeviceToHost, st));
+            }
+            for (int i = 0; i < nv; i++) out->ids_offsets[v0 + i + 1] = ids_total + offs[i + 1];
+            ids_total += offs[nv];
+        }
+        if (want_ids && !fast) {
+            // whole-grid scan: the kernel appended (scan index, centroid hash) pairs in arbitrary order; the reference's
+            // push_back order is the scan order, so sort each view's (short) list by scan index.
+            std::vector<unsigned> cnt(nv);
+            DMF_CUDA(cudaMemcpyAsync(cnt.data(), d_emit_count, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+            DMF_CUDA(cudaStreamSynchronize(st));
+            for (int i = 0; i < nv; i++) {
+                if (cnt[i] > emit_cap) return fail("reverseRayTrace emitted %u ids for view %d, more than the %u slots reserved", cnt[i], v0 + i, emit_cap);
+                if ((size_t)(ids_total + cnt[i]) > out->ids_capacity || (!out->ids && cnt[i] > 0)) return fail("ids_capacity %zu too small", out->ids_capacity);
+                std::vector<uint64_t> pairs(2 * (size_t)cnt[i]);
+                if (cnt[i]) DMF_CUDA(cudaMemcpy(pairs.data(), d_emit + 2 * (size_t)i * emit_cap, pairs.size() * 8, cudaMemcpyDeviceToHost));
+                std::vector<std::pair<uint64_t, uint64_t>> pv(cnt[i]);
+                for (unsigned j = 0; j < cnt[i]; j++) pv[j] = {pairs[2 * j], pairs[2 * j + 1]};
+                std::sort(pv.begin(), pv.end());
+                for (unsigned j = 0; j < cnt[i]; j++) out->ids[ids_total + j] = pv[j].second;
+                ids_total += cnt[i];
+                out->ids_offsets[v0 + i + 1] = ids_total;
+            }
+        }
+        if (out->visibility && vw) DMF_CUDA(cudaMemcpyAsync(out->visibility + v0 * vw, d_vis, nv * vw * 8, cudaMemcpyDeviceToHost, st));
+        if (out->unoccluded && vw) DMF_CUDA(cudaMemcpyAsync(out->unoccluded + v0 * vw, d_unocc, nv * vw * 8, cudaMemcpyDeviceToHost, st));
+        if (out->found_any) DMF_CUDA(cudaMemcpyAsync(out->found_any + v0, d_found, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+        DMF_CUDA(cudaStreamSynchronize(st));
+    }
+    DMF_CUDA(cudaEventRecord(c->ev_k1, st));
+    c->timed = true;
+    DMF_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int dmf_zbuffer(dmf_ctx* c, const float pose[12], int32_t* depth, int64_t* n_splat) {
+    if (!c || !pose) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    RevArgs a; DMF_TRY(fill_rev_args(c, a));
+    cudaStream_t st = c->stream;
+    const size_t HW = (size_t)c->H * c->W;
+    DMF_TRY(c->d_poses[0].reserve(48)); DMF_TRY(c->d_inv_poses.reserve(48)); DMF_TRY(c->d_misc[2].reserve(HW * 4)); DMF_TRY(c->d_misc[3].reserve(16));
+    DMF_CUDA(cudaMemcpyAsync(c->d_poses[0].p, pose, 48, cudaMemcpyHostToDevice, st));
+    DMF_CUDA(cudaEventRecord(c->ev_k0, st));
+    k_invert_poses<<<1, 32, 0, st>>>(c->d_poses[0].as<float>(), c->d_inv_poses.as<float>(), 1);
+    DMF_TRY(fill_u32(c, st, c->d_misc[2].p, HW, 0x7fffffffu));
+    DMF_CUDA(cudaMemsetAsync(c->d_misc[3].p, 0, 16, st));
+    a.poses = c->d_poses[0].as<float>(); a.inv_poses = c->d_inv_poses.as<float>(); a.zbuf = c->d_misc[2].as<int>();
+    const size_t total = (size_t)a.nax[0] * a.nax[1] * a.nax[2];
+    unsigned long long* cnt = c->d_misc[3].as<unsigned long long>();
+    if (total) {
+        k_zbuffer<0><<<blocks_for(total, 256, 148 * 32), 256, 0, st>>>(a, cnt, cnt + 1);
+        k_zbuffer<1><<<blocks_for(total, 256, 148 * 32), 256, 0, st>>>(a, cnt, cnt + 1);
+    }
+    k_finish_zbuf<<<blocks_for(HW, 256), 256, 0, st>>>(a.zbuf, HW);
+    c->launches += 4;
+    DMF_CUDA(cudaGetLastError());
+    DMF_CUDA(cudaEventRecord(c->ev_k1, st));
+    c->timed = true;
+    unsigned long long h_cnt[2] = {0, 0};
+    DMF_CUDA(cudaMemcpyAsync(h_cnt, cnt, 16, cudaMemcpyDeviceToHost, st));
+    if (depth) DMF_CUDA(cudaMemcpyAsync(depth, a.zbuf, HW * 4, cudaMemcpyDeviceToHost, st));
+    DMF_CUDA(cudaStreamSynchronize(st));
+    if (n_splat) *n_splat = (int64_t)h_cnt[0];
+    return 0;
+}
+
+int dmf_or_reduce_dev(dmf_ctx* c, uint64_t* d_dst, const uint64_t* d_src, int n_src, size_t words, void* stream) {
+    if (!c) return fail("null context");
+    DMF_CUDA(cudaSetDevice(c->device));
+    if (!words || n_src <= 0) return 0;
+    k_or_reduce<<<blocks_for(words, 256, 148 * 8), 256, 0, pick_stream(c, stream)>>>((u64*)d_dst, (const u64*)d_src, n_src, words);
+    c->launches++;
+    DMF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dmf_greedy_set_cover_dev(dmf_ctx* c, const uint64_t* d_bits, int n_sets, size_t words, int32_t* selected, int* n_selected) {
+    if (!c || !selected || !n_selected) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    *n_selected = 0;
+    if (n_sets <= 0 || !words) return 0;
+    cudaStream_t st = c->stream;
+    DevBuf &covered = c->d_misc[0], &taken = c->d_misc[1], &gain = c->d_misc[2], &result = c->d_misc[3];
+    DMF_TRY(covered.reserve(words * 8)); DMF_TRY(taken.reserve((size_t)n_sets * 4)); DMF_TRY(gain.reserve((size_t)n_sets * 4)); DMF_TRY(result.reserve(16));
+    DMF_CUDA(cudaMemsetAsync(covered.p, 0, words * 8, st));
+    DMF_CUDA(cudaMemsetAsync(taken.p, 0, (size_t)n_sets * 4, st));
+    DMF_CUDA(cudaEventRecord(c->ev_k0, st));
+    while (true) {
+        k_cover_gain<<<n_sets, 256, 0, st>>>((const u64*)d_bits, covered.as<u64>(), taken.as<int>(), words, gain.as<unsigned>());
+        k_cover_pick<<<1, 1024, 0, st>>>(gain.as<unsigned>(), n_sets, result.as<int>());
+        k_cover_apply<<<blocks_for(words, 256, 148 * 4), 256, 0, st>>>((const u64*)d_bits, covered.as<u64>(), taken.as<int>(), words, result.as<int>());
+        c->launches += 3;
+        DMF_CUDA(cudaGetLastError());
+        int res[2];
+        DMF_CUDA(cudaMemcpyAsync(res, result.p, 8, cudaMemcpyDeviceToHost, st));
+        DMF_CUDA(cudaStreamSynchronize(st));
+        if (res[0] < 0) break;       // selected == -1  (Algorithms.hpp:71)
+        if (res[1] < 5) break;       // max_points < 5  (Algorithms.hpp:73)
+        selected[(*n_selected)++] = res[0];
+        if (*n_selected >= n_sets) break;
+    }
+    DMF_CUDA(cudaEventRecord(c->ev_k1, st));
+    c->timed = true;
+    return 0;
+}
+
+int dmf_greedy_set_cover(dmf_ctx* c, const uint64_t* bitsets, int n_sets, size_t words, int32_t* selected, int* n_selected) {
+    if (!c || !bitsets) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    if (n_sets <= 0 || !words) { if (n_selected) *n_selected = 0; return 0; }
+    DMF_TRY(c->d_ids.reserve((size_t)n_sets * words * 8));
+    DMF_CUDA(cudaMemcpyAsync(c->d_ids.p, bitsets, (size_t)n_sets * words * 8, cudaMemcpyHostToDevice, c->stream));
+    return dmf_greedy_set_cover_dev(c, c->d_ids.as<uint64_t>(), n_sets, words, selected, n_selected);
+}
+
+}  // extern "C"

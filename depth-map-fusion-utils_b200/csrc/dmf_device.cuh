@@ -1,0 +1,136 @@
+// dmf_device.cuh -- device-side data layout and exact-arithmetic helpers shared by all kernels.
+//
+// Everything here must reproduce the reference's IEEE-754 results bit for bit, so the file is compiled
+// with -fmad=false (no implicit contraction), default -prec-div/-prec-sqrt/-ftz=false, and every op whose
+// rounding matters is spelled with an explicit round-to-nearest intrinsic.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+
+// HBM layout of a VoxelVolume (reference include/Volume.hpp:50-78):
+//   bricks   [nbx][nby][nbz] uint64   occupancy of a 4x4x4 voxel brick, bit = (lx<<4)|(ly<<2)|lz
+//   prefix   [nbx*nby*nbz]   uint32   number of occupied voxels in all earlier bricks (rank directory)
+//   rank2occ [n_occ]         uint32   rank (brick order) -> index into occupied_cells_
+//   bytes    [nx][ny][nz]    uint8    optional byte-per-voxel copy, z fastest (DMF_GRID_BYTE)
+//   noff/normals             CSR of Voxel::normals in occupied order
+struct VolDev {
+    const u64* __restrict__ bricks;
+    const unsigned* __restrict__ prefix;
+    const unsigned* __restrict__ rank2occ;
+    const unsigned char* __restrict__ bytes;
+    const unsigned* __restrict__ noff;
+    const float* __restrict__ normals;
+    const u64* __restrict__ occ_ids;
+    int n_occ;
+    int dim[3];      // xdim_, ydim_, zdim_
+    int nb[3];       // bricks per axis
+    double vmin[3];  // xmin_, ymin_, zmin_
+    double delta[3]; // xdelta_, ydelta_, zdelta_
+    double inv[3];   // RN(1/delta)
+    double c0[3];    // RN(-vmin*inv)
+    double half[3];  // delta/2.0
+    double eps[3];   // |frac| below which the fast quotient cannot be trusted (0 => axis is exact)
+    float lo[3];     // largest float <= vmin   (validPoints: x<=xmin_  <=>  !(x > lo))
+    float hi[3];     // smallest float >= vmax  (validPoints: x>=xmax_  <=>  !(x < hi))
+};
+
+// floor(((double)p - vmin) / delta) exactly as VoxelVolume::getVoxel (Volume.hpp:150-156) computes it.
+// Fast path: q' = fma(p, 1/delta, -vmin/delta) differs from the reference quotient by < eps, so the floors agree
+// unless q' is within eps of an integer; then (and only then) the reference's subtract + IEEE divide is executed.
+// The floor itself uses the 1.5*2^52 shifter so no F2I/I2F conversions are needed.
+__device__ __forceinline__ int voxel_index(float p, double vmin, double delta, double inv, double c0, double eps, unsigned& n_exact) {
+    const double kShift = 6755399441055744.0;  // 1.5 * 2^52
+    double q = fma((double)p, inv, c0);
+    double s = __dadd_rn(q, kShift);
+    int i = __double2loint(s);                 // rint(q)
+    double f = __dsub_rn(q, __dsub_rn(s, kShift));   // q - rint(q), in [-0.5, 0.5]
+    if (fabs(f) < eps) {
+        double qe = __ddiv_rn(__dsub_rn((double)p, vmin), delta);
+        n_exact++;
+        return (int)floor(qe);
+    }
+    return i - (f < 0.0 ? 1 : 0);
+}
+
+__device__ __forceinline__ bool in_bounds(const VolDev& v, float x, float y, float z) {
+    return x > v.lo[0] && x < v.hi[0] && y > v.lo[1] && y < v.hi[1] && z > v.lo[2] && z < v.hi[2];
+}
+
+__device__ __forceinline__ bool coords_valid(const VolDev& v, int x, int y, int z) {
+    return (unsigned)x < (unsigned)v.dim[0] && (unsigned)y < (unsigned)v.dim[1] && (unsigned)z < (unsigned)v.dim[2];
+}
+
+__device__ __forceinline__ size_t brick_index(const VolDev& v, int x, int y, int z) {
+    return ((size_t)(x >> 2) * v.nb[1] + (y >> 2)) * v.nb[2] + (z >> 2);
+}
+__device__ __forceinline__ unsigned brick_bit(int x, int y, int z) { return ((x & 3) << 4) | ((y & 3) << 2) | (z & 3); }
+
+template <int FMT>
+__device__ __forceinline__ bool occupied(const VolDev& v, int x, int y, int z) {
+    if (FMT == 0) {
+        u64 w = __ldg(v.bricks + brick_index(v, x, y, z));
+        return (w >> brick_bit(x, y, z)) & 1ull;
+    } else {
+        return __ldg(v.bytes + ((size_t)x * v.dim[1] + y) * v.dim[2] + z) != 0;
+    }
+}
+
+// index into occupied_cells_ of an occupied voxel
+__device__ __forceinline__ int occupied_ordinal(const VolDev& v, int x, int y, int z) {
+    size_t b = brick_index(v, x, y, z);
+    u64 w = __ldg(v.bricks + b);
+    unsigned bit = brick_bit(x, y, z);
+    unsigned rank = __ldg(v.prefix + b) + __popcll(w & ((1ull << bit) - 1ull));
+    return (int)__ldg(v.rank2occ + rank);
+}
+
+__device__ __forceinline__ u64 voxel_id(int x, int y, int z) {   // getHashId, Volume.hpp:143-148 (non-negative coords)
+    return ((u64)(unsigned)x << 40) ^ (u64)(long long)(y << 20) ^ (u64)(long long)z;
+}
+
+// Eigen 3.3 Affine3f * Vector3f (rule E1 of oracle/dmf_oracle.hpp): ((m0*x + m1*y) + m2*z) + m3, no contraction.
+__device__ __forceinline__ float affine_row(float m0, float m1, float m2, float m3, float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m0, x), __fmul_rn(m1, y)), __fmul_rn(m2, z)), m3);
+}
+// Eigen 3.3 3-element reduction (rule E2): a0 + (a1 + a2)
+__device__ __forceinline__ float sum3(float a0, float a1, float a2) { return __fadd_rn(a0, __fadd_rn(a1, a2)); }
+
+// (camera_center - centroid).normalized() with centroid = point + delta/2 (RayTracingEngine.hpp:345-349), rule E3
+__device__ __forceinline__ void view_direction(const VolDev& v, float px, float py, float pz, float camx, float camy, float camz,
+                                               float& dx, float& dy, float& dz) {
+    float cx = __double2float_rn(__dadd_rn((double)px, v.half[0]));
+    float cy = __double2float_rn(__dadd_rn((double)py, v.half[1]));
+    float cz = __double2float_rn(__dadd_rn((double)pz, v.half[2]));
+    dx = __fsub_rn(camx, cx); dy = __fsub_rn(camy, cy); dz = __fsub_rn(camz, cz);
+    float n2 = sum3(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz));
+    if (n2 > 0.0f) {
+        float s = __fsqrt_rn(n2);
+        dx = __fdiv_rn(dx, s); dy = __fdiv_rn(dy, s); dz = __fdiv_rn(dz, s);
+    }
+}
+
+// Parameters of the "angle in [0,90] degrees" test  degree(acos(n.v)) in [k_AngleMin,k_AngleMax]
+// (RayTracingEngine.hpp:211-212, :362-364, :428-430; CommonUtilities.hpp:17).  The host bisects its own libm's
+// acosf once (dmf_b200_host.cpp): the test is true  <=>  dot_min <= d <= 1.  [band_lo, band_hi) is the range of d
+// where the host libm was observed non-monotonic (empty if band_lo >= band_hi); hits inside it are counted as ties.
+struct AngleTest { float dot_min, band_lo, band_hi; };
+
+// some stored normal of occupied voxel `occ` passes the angle test against direction (dx,dy,dz)
+__device__ __forceinline__ bool any_normal_faces(const VolDev& v, const AngleTest& at, int occ, float dx, float dy, float dz, unsigned& ties) {
+    unsigned b = __ldg(v.noff + occ), e = __ldg(v.noff + occ + 1);
+    for (unsigned j = b; j < e; j++) {
+        float nx = __ldg(v.normals + 3 * (size_t)j), ny = __ldg(v.normals + 3 * (size_t)j + 1), nz = __ldg(v.normals + 3 * (size_t)j + 2);
+        float d = sum3(__fmul_rn(nx, dx), __fmul_rn(ny, dy), __fmul_rn(nz, dz));
+        if (d >= at.band_lo && d < at.band_hi) ties++;
+        if (d >= at.dot_min && d <= 1.0f) return true;
+    }
+    return false;
+}
+
+// x86 cvttsd2si semantics (INT_MIN on NaN / overflow) for the reference's int(round(...)) casts (Camera.hpp:35-36)
+__device__ __forceinline__ int to_int_x86(double v) {
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return (int)0x80000000;
+    return __double2int_rz(v);
+}

@@ -1,0 +1,149 @@
+// dmf_host.cuh -- host-side state behind the C ABI: the context, grow-only device buffers, the host mirror of
+// VoxelVolume used by dmf_volume_from_points, and the libm acosf bisection.
+#pragma once
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "dmf_device.cuh"
+#include "../../include/dmf_b200.h"
+
+namespace dmf {
+
+inline std::string& last_error() { static thread_local std::string e; return e; }
+inline int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    last_error() = buf;
+    return 1;
+}
+#define DMF_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return dmf::fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define DMF_TRY(call) do { int r_ = (call); if (r_) return r_; } while (0)
+
+// grow-only device allocation
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// Host restatement of the data-model half of VoxelVolume (reference include/Volume.hpp:89-128,135-170,199-233);
+// used only to turn a point cloud into (occupied ids, normals CSR) -- the march itself never runs on the host.
+struct HostVolume {
+    double vmin[3], vmax[3], delta[3];
+    int dim[3];
+    std::vector<uint64_t> occupied;                     // occupied_cells_
+    std::vector<std::vector<float>> normals;            // per occupied voxel: flat xyz list
+    std::unordered_map<uint64_t, uint32_t> index;       // id -> ordinal
+
+    void construct(const double b[6], const int dims[3]) {
+        for (int a = 0; a < 3; a++) {
+            vmin[a] = b[2 * a]; vmax[a] = b[2 * a + 1];
+            delta[a] = (vmax[a] - vmin[a]) / dims[a];             // setVolumeSize  :114-116
+            dim[a] = (int)((vmax[a] - vmin[a]) / delta[a]);       // constructVolume :121-123 (truncation)
+        }
+    }
+    bool valid_point(float x, float y, float z) const {           // validPoints :230-233
+        return !(x >= vmax[0] || y >= vmax[1] || z >= vmax[2] || x <= vmin[0] || y <= vmin[1] || z <= vmin[2]);
+    }
+    static uint64_t hash_id(int x, int y, int z) {                // getHashId :143-148
+        uint64_t h = (uint64_t)(long long)x;
+        return (h << 40) ^ (uint64_t)(long long)(y << 20) ^ (uint64_t)(long long)z;
+    }
+    size_t integrate(const float* xyz, const float* nrm, size_t n) {   // integratePointCloud :199-228 (:172-197 if nrm == null)
+        size_t used = 0;
+        for (size_t i = 0; i < n; i++) {
+            float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+            if (!valid_point(px, py, pz)) continue;
+            int c[3] = {(int)std::floor((px - vmin[0]) / delta[0]), (int)std::floor((py - vmin[1]) / delta[1]), (int)std::floor((pz - vmin[2]) / delta[2])};
+            if (c[0] >= dim[0] || c[1] >= dim[1] || c[2] >= dim[2] || c[0] < 0 || c[1] < 0 || c[2] < 0) continue;   // validCoords :211
+            uint64_t h = hash_id(c[0], c[1], c[2]);
+            auto it = index.find(h);
+            uint32_t o;
+            if (it == index.end()) { o = (uint32_t)occupied.size(); index.emplace(h, o); occupied.push_back(h); normals.emplace_back(); }
+            else o = it->second;
+            if (nrm) { normals[o].push_back(nrm[3 * i]); normals[o].push_back(nrm[3 * i + 1]); normals[o].push_back(nrm[3 * i + 2]); }
+            used++;
+        }
+        return used;
+    }
+};
+
+// degree(acos(d)) in [0,90] with the HOST libm's float acos, exactly as the reference evaluates it
+// (CommonUtilities.hpp:17; RayTracingEngine.hpp:211-212): this is a property of the machine the reference would run on.
+inline bool host_angle_ok(float d) {
+    float a = std::acos(d);
+    double deg = ((double)a * 180) / 3.14159;
+    if (!(deg > -2147483649.0 && deg < 2147483648.0)) return false;   // int(NaN) = INT_MIN on x86
+    int angle = (int)deg;
+    return angle >= 0 && angle <= 90;
+}
+inline float next_up(float f) { return std::nextafter(f, INFINITY); }
+inline float next_down(float f) { return std::nextafter(f, -INFINITY); }
+
+// Smallest d with host_angle_ok(d) (bisection over the float order), plus the band where monotonicity fails.
+inline AngleTest bisect_angle_test() {
+    auto ord = [](float f) { int32_t i; std::memcpy(&i, &f, 4); return i < 0 ? (int32_t)0x80000000 - i : i; };
+    auto from = [](int32_t o) { int32_t i = o < 0 ? (int32_t)0x80000000 - o : o; float f; std::memcpy(&f, &i, 4); return f; };
+    int32_t lo = ord(-1.0f), hi = ord(1.0f);      // ok(lo) false, ok(hi) true
+    while (hi - lo > 1) { int32_t mid = lo + (hi - lo) / 2; if (host_angle_ok(from(mid))) hi = mid; else lo = mid; }
+    AngleTest t; t.dot_min = from(hi); t.band_lo = 0.f; t.band_hi = 0.f;
+    // scan a neighbourhood for non-monotonic flips
+    int32_t first_bad = 0, last_bad = 0; bool any = false;
+    for (int32_t o = hi - 4096; o <= hi + 4096; o++) {
+        bool expect = o >= hi, got = host_angle_ok(from(o));
+        if (expect != got) { if (!any) first_bad = o; last_bad = o; any = true; }
+    }
+    if (any) { t.band_lo = from(first_bad); t.band_hi = from(last_bad + 1); }
+    return t;
+}
+
+struct TableKey {
+    float K[9]; int H, W, z0, zdelta, cstride, rstride;
+    bool operator==(const TableKey& o) const { return std::memcmp(this, &o, sizeof *this) == 0; }
+};
+
+}  // namespace dmf
+
+struct dmf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;     // bracket the kernels of the last call
+    cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool timed = false;
+    // camera
+    bool cam_set = false; float K[9]; int H = 0, W = 0;
+    // volume
+    bool vol_set = false;
+    VolDev vol{};
+    double bounds[6]; double voxel_size = 0; size_t n_occ = 0, n_normals = 0;
+    std::vector<uint64_t> h_occ; std::vector<uint32_t> h_noff; std::vector<float> h_normals;
+    dmf::DevBuf d_bricks, d_prefix, d_rank2occ, d_bytes, d_noff, d_normals, d_occ_ids, d_centroid_hash;
+    bool bytes_built = false;
+    dmf::DevBuf d_view_mark, d_good_bits, d_first_view;
+    // reverseRayTrace / rayTraceVolume float-accumulated axes
+    dmf::DevBuf d_axis[3]; int n_axis[3] = {0, 0, 0};
+    // projectPoint tables
+    bool tables_valid = false; dmf::TableKey tkey{};
+    dmf::DevBuf d_xtab, d_ytab, d_ztab; int S = 0, Wc = 0, Hc = 0;
+    // scratch
+    dmf::DevBuf d_poses[2], d_inv_poses, d_out[2][8], d_first_key, d_ray_key, d_ray_occ, d_tmp_a, d_tmp_b, d_out_occ, d_n_ids, d_offsets, d_ids;
+    dmf::DevBuf d_misc[4];
+    dmf::DevBuf d_counters;
+    AngleTest angle{};
+    uint64_t launches = 0;
+};

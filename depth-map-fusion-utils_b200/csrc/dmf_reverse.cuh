@@ -1,0 +1,284 @@
+// dmf_reverse.cuh -- K2: reverse per-voxel visibility march (reverseRayTraceFast / reverseRayTrace,
+// include/RayTracingEngine.hpp:45-226) and K3: the z-buffer splat (rayTraceVolume, :498-564), plus the small
+// volume-preparation kernels.
+#pragma once
+#include "dmf_device.cuh"
+
+// getHash for arbitrary (possibly out-of-range) coordinates: ints sign-extend into the xor (Volume.hpp:135-141)
+__device__ __forceinline__ u64 hash_coords(int x, int y, int z) {
+    u64 h = (u64)(long long)x;
+    return (h << 40) ^ (u64)(long long)(int)((unsigned)y << 20) ^ (u64)(long long)z;
+}
+
+__device__ __forceinline__ u64 hash_point(const VolDev& v, float x, float y, float z, unsigned& n_exact) {
+    int ix = voxel_index(x, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+    int iy = voxel_index(y, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+    int iz = voxel_index(z, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+    return hash_coords(ix, iy, iz);
+}
+
+// centroid of occupied voxel `occ` as reverseRayTraceFast builds it (:148-157):
+//   float x = xid*xdelta_ + xmin_;  centroid = float(x + xdelta_/2.0)
+__device__ __forceinline__ void occ_centroid(const VolDev& v, int occ, int& xid, int& yid, int& zid, float& cx, float& cy, float& cz) {
+    const u64 id = __ldg(v.occ_ids + occ);
+    xid = (int)(id >> 40); yid = (int)((id >> 20) & 0xFFFFFu); zid = (int)(id & 0xFFFFFu);
+    float x = __double2float_rn(__dadd_rn(__dmul_rn((double)xid, v.delta[0]), v.vmin[0]));
+    float y = __double2float_rn(__dadd_rn(__dmul_rn((double)yid, v.delta[1]), v.vmin[1]));
+    float z = __double2float_rn(__dadd_rn(__dmul_rn((double)zid, v.delta[2]), v.vmin[2]));
+    cx = __double2float_rn(__dadd_rn((double)x, v.half[0]));
+    cy = __double2float_rn(__dadd_rn((double)y, v.half[1]));
+    cz = __double2float_rn(__dadd_rn((double)z, v.half[2]));
+}
+
+__global__ void k_centroid_hash(const VolDev v, u64* out) {
+    for (int occ = blockIdx.x * blockDim.x + threadIdx.x; occ < v.n_occ; occ += gridDim.x * blockDim.x) {
+        int xid, yid, zid; float cx, cy, cz; unsigned ne = 0;
+        occ_centroid(v, occ, xid, yid, zid, cx, cy, cz);
+        out[occ] = hash_point(v, cx, cy, cz, ne);
+    }
+}
+
+__global__ void k_expand_bytes(const VolDev v, unsigned char* bytes) {
+    const size_t n = (size_t)v.dim[0] * v.dim[1] * v.dim[2];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int z = (int)(i % v.dim[2]); size_t t = i / v.dim[2];
+        int y = (int)(t % v.dim[1]); int x = (int)(t / v.dim[1]);
+        bytes[i] = occupied<0>(v, x, y, z) ? 1 : 0;
+    }
+}
+
+// Eigen::Affine3f::inverse() (rule E5 of oracle/dmf_oracle.hpp): cofactor inverse * (1/det), translation = -(Linv*t)
+__global__ void k_invert_poses(const float* __restrict__ poses, float* __restrict__ inv, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m[3][4];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) m[r][c] = poses[12 * (size_t)i + 4 * r + c];
+    auto cof = [&](int a, int b) {
+        int a1 = (a + 1) % 3, a2 = (a + 2) % 3, b1 = (b + 1) % 3, b2 = (b + 2) % 3;
+        return __fsub_rn(__fmul_rn(m[a1][b1], m[a2][b2]), __fmul_rn(m[a1][b2], m[a2][b1]));
+    };
+    float c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    float det = sum3(__fmul_rn(c0, m[0][0]), __fmul_rn(c1, m[1][0]), __fmul_rn(c2, m[2][0]));
+    float invdet = __fdiv_rn(1.0f, det);
+    float r[3][4];
+    r[0][0] = __fmul_rn(c0, invdet); r[0][1] = __fmul_rn(c1, invdet); r[0][2] = __fmul_rn(c2, invdet);
+    r[1][0] = __fmul_rn(cof(0, 1), invdet); r[1][1] = __fmul_rn(cof(1, 1), invdet); r[1][2] = __fmul_rn(cof(2, 1), invdet);
+    r[2][0] = __fmul_rn(cof(0, 2), invdet); r[2][1] = __fmul_rn(cof(1, 2), invdet); r[2][2] = __fmul_rn(cof(2, 2), invdet);
+    for (int a = 0; a < 3; a++)
+        r[a][3] = sum3(__fmul_rn(-r[a][0], m[0][3]), __fmul_rn(-r[a][1], m[1][3]), __fmul_rn(-r[a][2], m[2][3]));
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 4; b++) inv[12 * (size_t)i + 4 * a + b] = r[a][b];
+}
+
+struct RevArgs {
+    VolDev vol;
+    AngleTest angle;
+    const float* __restrict__ poses;       // [n_views][12]
+    const float* __restrict__ inv_poses;   // [n_views][12]
+    double fx, cx, fy, cy;
+    int H, W;
+    const u64* __restrict__ centroid_hash; // [n_occ]  (fast)
+    const float* __restrict__ ax[3];       // float-accumulated axes (whole-grid variants)
+    int nax[3];
+    unsigned* vis;                         // emitted
+    unsigned* unocc;                       // not occluded
+    int vis_words32;
+    int* found_any;
+    int viz;
+    int* view_mark;
+    unsigned* good_bits;
+    u64* emit_list;                        // whole-grid variant: [n_views][emit_cap][2] = (scan index, centroid hash)
+    unsigned* emit_count;                  // [n_views]
+    unsigned emit_cap;
+    int* zbuf;                             // [H*W] (z-buffer)
+    u64* counters;
+    int step_cap;
+};
+
+__device__ __forceinline__ void camera_pixel(const RevArgs& a, float xx, float yy, float zz, int& r, int& c) {   // deProjectPoint, Camera.hpp:32-38
+    c = to_int_x86(round(__dadd_rn(__ddiv_rn(__dmul_rn((double)xx, a.fx), (double)zz), a.cx)));
+    r = to_int_x86(round(__dadd_rn(__ddiv_rn(__dmul_rn((double)yy, a.fy), (double)zz), a.cy)));
+}
+
+// The 1 mm march from `centroid` towards (and past) the camera (:81-103, :172-200).  true = occluded.
+template <int FMT>
+__device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float cy, float cz, float vx, float vy, float vz, u64 chash, int d0,
+                                               unsigned& n_samples, unsigned& n_inb, unsigned& n_exact, unsigned& n_runaway) {
+    const VolDev& v = a.vol;
+    for (int depth = d0;; depth++) {
+        if (depth - d0 > a.step_cap) { n_runaway++; return false; }
+        const float s = (float)depth;
+        // centroid + v*double(depth)/1000.0 in float (rule E4)
+        const float px = __fadd_rn(cx, __fdiv_rn(__fmul_rn(vx, s), 1000.0f));
+        const float py = __fadd_rn(cy, __fdiv_rn(__fmul_rn(vy, s), 1000.0f));
+        const float pz = __fadd_rn(cz, __fdiv_rn(__fmul_rn(vz, s), 1000.0f));
+        n_samples++;
+        if (!in_bounds(v, px, py, pz)) return false;
+        n_inb++;
+        const int ix = voxel_index(px, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+        const int iy = voxel_index(py, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+        const int iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+        if (hash_coords(ix, iy, iz) == chash) continue;       // same voxel as the origin
+        if (!coords_valid(v, ix, iy, iz)) return false;        // validCoords == false: break
+        if (occupied<FMT>(v, ix, iy, iz)) return true;
+    }
+}
+
+__device__ __forceinline__ void flush_counters(u64* counters, unsigned n_samples, unsigned n_inb, unsigned n_hits, unsigned n_exact,
+                                               unsigned n_oob, unsigned n_ties, unsigned n_runaway) {
+    unsigned long long c[7] = {n_samples, n_inb, n_hits, n_exact, n_oob, n_ties, n_runaway};
+    const int slot[7] = {0, 1, 2, 3, 4, 5, 7};
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        for (int o = 16; o; o >>= 1) c[j] += __shfl_down_sync(0xffffffffu, c[j], o);
+        if ((threadIdx.x & 31) == 0 && c[j]) atomicAdd(counters + slot[j], c[j]);
+    }
+}
+
+// FAST = true : one thread per occupied voxel (grid.x covers n_occ), reverseRayTraceFast :136-226
+// FAST = false: one thread per visited position of the float-accumulated whole-grid scan, reverseRayTrace :45-134
+template <bool FAST>
+__global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
+    const VolDev& v = a.vol;
+    const int view = blockIdx.y;
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    unsigned n_samples = 0, n_inb = 0, n_hits = 0, n_exact = 0, n_oob = 0, n_ties = 0, n_runaway = 0;
+    const float* T = a.poses + 12 * (size_t)view;
+    const float* I = a.inv_poses + 12 * (size_t)view;
+    bool live = true;
+    int occ = -1; float cx = 0, cy = 0, cz = 0; u64 chash = 0;
+    if (FAST) {
+        live = t < (size_t)v.n_occ;
+        if (live) {
+            int xid, yid, zid;
+            occ = (int)t;
+            occ_centroid(v, occ, xid, yid, zid, cx, cy, cz);
+            chash = __ldg(a.centroid_hash + occ);
+        }
+    } else {
+        const size_t total = (size_t)a.nax[0] * a.nax[1] * a.nax[2];
+        live = t < total;
+        if (live) {
+            const int k = (int)(t % a.nax[2]); const size_t u = t / a.nax[2];
+            const int j = (int)(u % a.nax[1]); const int i = (int)(u / a.nax[1]);
+            const float x = __ldg(a.ax[0] + i), y = __ldg(a.ax[1] + j), z = __ldg(a.ax[2] + k);
+            const int ix = voxel_index(x, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+            const int iy = voxel_index(y, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+            const int iz = voxel_index(z, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+            if (!coords_valid(v, ix, iy, iz)) { n_oob++; live = false; }       // voxels_[xid][yid][zid] out of range (UB)
+            else if (!occupied<0>(v, ix, iy, iz)) live = false;
+            else {
+                occ = occupied_ordinal(v, ix, iy, iz);
+                cx = __double2float_rn(__dadd_rn((double)x, v.half[0]));
+                cy = __double2float_rn(__dadd_rn((double)y, v.half[1]));
+                cz = __double2float_rn(__dadd_rn((double)z, v.half[2]));
+                chash = hash_point(v, cx, cy, cz, n_exact);
+            }
+        }
+    }
+    if (live) {
+        const float xx = affine_row(__ldg(I + 0), __ldg(I + 1), __ldg(I + 2), __ldg(I + 3), cx, cy, cz);
+        const float yy = affine_row(__ldg(I + 4), __ldg(I + 5), __ldg(I + 6), __ldg(I + 7), cx, cy, cz);
+        const float zz = affine_row(__ldg(I + 8), __ldg(I + 9), __ldg(I + 10), __ldg(I + 11), cx, cy, cz);
+        int r, c;
+        camera_pixel(a, xx, yy, zz, r, c);
+        if (r >= 0 && r < a.H && c >= 0 && c < a.W) {                               // validPixel
+            float vx = __fsub_rn(__ldg(T + 3), cx), vy = __fsub_rn(__ldg(T + 7), cy), vz = __fsub_rn(__ldg(T + 11), cz);
+            const float n2 = sum3(__fmul_rn(vx, vx), __fmul_rn(vy, vy), __fmul_rn(vz, vz));
+            if (n2 > 0.0f) { const float s = __fsqrt_rn(n2); vx = __fdiv_rn(vx, s); vy = __fdiv_rn(vy, s); vz = __fdiv_rn(vz, s); }
+            const bool collided = march_collides<0>(a, cx, cy, cz, vx, vy, vz, chash, FAST ? 50 : 1, n_samples, n_inb, n_exact, n_runaway);
+            if (!collided) {
+                n_hits++;
+                if (a.found_any) a.found_any[view] = 1;
+                if (a.unocc) atomicOr(a.unocc + (size_t)view * a.vis_words32 + (occ >> 5), 1u << (occ & 31));
+                if (a.viz) a.view_mark[occ] = 1;                                     // :108, :205
+                bool emit = false;
+                if ((double)zz >= 0.20 && (double)zz <= 1.0) {                       // k_ZMin, k_ZMax (:109, :206)
+                    emit = FAST ? any_normal_faces(v, a.angle, occ, vx, vy, vz, n_ties) : true;
+                }
+                if (emit) {
+                    if (a.viz) atomicOr(a.good_bits + (occ >> 5), 1u << (occ & 31)); // :112, :215
+                    if (a.vis) atomicOr(a.vis + (size_t)view * a.vis_words32 + (occ >> 5), 1u << (occ & 31));
+                    if (!FAST && a.emit_list) {
+                        unsigned slot = atomicAdd(a.emit_count + view, 1u);
+                        if (slot < a.emit_cap) {
+                            a.emit_list[2 * ((size_t)view * a.emit_cap + slot)] = (u64)t;
+                            a.emit_list[2 * ((size_t)view * a.emit_cap + slot) + 1] = chash;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    flush_counters(a.counters, n_samples, n_inb, n_hits, n_exact, n_oob, n_ties, n_runaway);
+}
+
+// visibility bitset -> occupied ordinals in ascending order (= emission order of reverseRayTraceFast), one block per view
+__global__ void __launch_bounds__(256) k_bits_to_list(const unsigned* vis, int vis_words32, int n_occ, int* out_occ, int* n_out, int stride) {
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned s_base;
+    const int view = blockIdx.x;
+    const unsigned* bits = vis + (size_t)view * vis_words32;
+    const int nwords = (n_occ + 31) / 32;
+    const int chunk = (nwords + 255) / 256;
+    const int b = min(nwords, (int)threadIdx.x * chunk), e = min(nwords, b + chunk);
+    unsigned cnt = 0;
+    for (int w = b; w < e; w++) cnt += __popc(bits[w]);
+    // block exclusive scan (256 threads)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned x = cnt;
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned run = 0; for (int i = 0; i < 8; i++) { unsigned tmp = s_warp[i]; s_warp[i] = run; run += tmp; } s_base = run; }
+    __syncthreads();
+    unsigned pos = s_warp[warp] + x - cnt;
+    for (int w = b; w < e; w++) {
+        unsigned m = bits[w];
+        while (m) { int bit = __ffs(m) - 1; m &= m - 1; out_occ[(size_t)view * stride + pos++] = w * 32 + bit; }
+    }
+    if (threadIdx.x == 0) n_out[view] = (int)s_base;
+}
+
+// ---- K3: rayTraceVolume ---------------------------------------------------------------------------------------
+// PASS 0: depth[r][c] = min(depth[r][c], int(round(zz*1000)))  (:528-534; -1 == "unset" is modelled as INT_MAX)
+// PASS 1: voxel->view = 1 where depth[r][c] == d              (:559-562)
+template <int PASS>
+__global__ void __launch_bounds__(256) k_zbuffer(const RevArgs a, unsigned long long* n_splat, unsigned long long* n_minus_one) {
+    const VolDev& v = a.vol;
+    const size_t total = (size_t)a.nax[0] * a.nax[1] * a.nax[2];
+    unsigned n_exact = 0;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t % a.nax[2]); const size_t u = t / a.nax[2];
+        const int j = (int)(u % a.nax[1]); const int i = (int)(u / a.nax[1]);
+        const float x = __ldg(a.ax[0] + i), y = __ldg(a.ax[1] + j), z = __ldg(a.ax[2] + k);
+        const int ix = voxel_index(x, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+        const int iy = voxel_index(y, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+        const int iz = voxel_index(z, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+        if (!coords_valid(v, ix, iy, iz)) continue;
+        if (!occupied<0>(v, ix, iy, iz)) continue;
+        const float cx = __double2float_rn(__dadd_rn((double)x, v.half[0]));
+        const float cy = __double2float_rn(__dadd_rn((double)y, v.half[1]));
+        const float cz = __double2float_rn(__dadd_rn((double)z, v.half[2]));
+        const float* I = a.inv_poses;
+        const float xx = affine_row(__ldg(I + 0), __ldg(I + 1), __ldg(I + 2), __ldg(I + 3), cx, cy, cz);
+        const float yy = affine_row(__ldg(I + 4), __ldg(I + 5), __ldg(I + 6), __ldg(I + 7), cx, cy, cz);
+        const float zz = affine_row(__ldg(I + 8), __ldg(I + 9), __ldg(I + 10), __ldg(I + 11), cx, cy, cz);
+        int r, c;
+        camera_pixel(a, xx, yy, zz, r, c);
+        if (!(r >= 0 && r < a.H && c >= 0 && c < a.W)) continue;
+        const float dm = roundf(__fmul_rn(zz, 1000.0f));
+        const int d = (dm > -2147483904.0f && dm < 2147483648.0f) ? (int)dm : (int)0x80000000;
+        if (PASS == 0) {
+            atomicMin(a.zbuf + (size_t)r * a.W + c, d);
+            atomicAdd(n_splat, 1ull);
+            if (d == -1) atomicAdd(n_minus_one, 1ull);
+        } else if (a.zbuf[(size_t)r * a.W + c] == d) {
+            a.view_mark[occupied_ordinal(v, ix, iy, iz)] = 1;
+        }
+    }
+}
+
+__global__ void k_finish_zbuf(int* zbuf, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (zbuf[i] == 0x7fffffff) zbuf[i] = -1;
+}

@@ -1,0 +1,173 @@
+/* dmf_b200.h -- C ABI of libdmf_b200.so: the RayTracingEngine hot path of REXJJ/depth-map-fusion-utils as
+ * hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI layer: the boundary it exposes is the public C++ surface of three headers
+ * (include/Camera.hpp, include/Volume.hpp, include/RayTracingEngine.hpp).  The drop-in headers in
+ * depth-map-fusion-utils_b200/dropin/ keep those class/method signatures and forward to the entry points
+ * below; each entry point cites the reference interface it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; dmf_last_error() gives the message
+ *     (the reference has no error convention at all: include/RayTracingEngine.hpp prints and continues).
+ *   - poses are row-major 3x4 float camera->world affines, i.e. rows 0..2 of Eigen::Affine3f::matrix().
+ *   - voxel ids are VoxelVolume::getHashId values: (x<<40)^(y<<20)^z  (include/Volume.hpp:143-148).
+ *   - "occupied order" is the order of VoxelVolume::occupied_cells_ (first insertion, Volume.hpp:216).
+ *   - one host thread per context; a context owns one CUDA device, its streams and all device buffers.
+ *   - there is NO CPU fallback: every compute entry point fails if no sm_100 device is usable.
+ */
+#ifndef DMF_B200_H
+#define DMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmf_ctx dmf_ctx;
+
+#define DMF_NO_VOXEL 0xFFFFFFFFFFFFFFFFull
+
+/* forward routines of include/RayTracingEngine.hpp */
+enum {
+    DMF_MODE_POINTS      = 0, /* rayTraceAndGetPoints      :447-494 */
+    DMF_MODE_GOOD_POINTS = 1, /* rayTraceAndGetGoodPoints  :377-445 */
+    DMF_MODE_CLASSIFY    = 2, /* rayTraceAndClassify       :311-375 */
+    DMF_MODE_MARK        = 3, /* rayTrace                  :268-309 */
+    DMF_MODE_MINIMUM     = 4  /* rayTraceAndGetMinimum     :229-264 */
+};
+
+/* occupancy format probed by the march */
+enum {
+    DMF_GRID_BIT  = 0, /* 4x4x4-voxel bricks, one uint64 per brick (1/8 byte per voxel) */
+    DMF_GRID_BYTE = 1  /* one byte per voxel, [x][y][z] z fastest like voxels_[x][y][z] (Volume.hpp:126) */
+};
+
+/* ---- lifetime --------------------------------------------------------------------------------- */
+int  dmf_create(dmf_ctx** out, int device);              /* new: process-global state the by-value RayTracingEngine cannot own */
+void dmf_destroy(dmf_ctx* ctx);
+const char* dmf_last_error(void);
+int  dmf_device_count(void);                             /* CUDA devices visible; 0 => compute calls fail */
+int  dmf_version(void);
+
+/* pinned host memory for the host-buffer entry points (plain malloc'd buffers work too, slower) */
+void* dmf_host_alloc(size_t bytes);
+void  dmf_host_free(void* p);
+
+/* ---- Camera(K, height, width)                                        include/Camera.hpp:23 ---- */
+int dmf_set_camera(dmf_ctx* ctx, const float K[9], int height, int width);
+
+/* ---- VoxelVolume ------------------------------------------------------------------------------ */
+/* Upload a volume that was built on the host by the (drop-in) VoxelVolume: replaces the per-probe
+ * voxels_[x][y][z] reads of RayTracingEngine.hpp (:62,:97,:154,:194,:255,:298,:344,:414,:479,:517).
+ * bounds = xmin,xmax,ymin,ymax,zmin,zmax; delta = xdelta_,ydelta_,zdelta_; dim = xdim_,ydim_,zdim_
+ * (Volume.hpp:55-59).  occupied_ids = occupied_cells_; normal_offsets (n_occ+1) / normals (xyz) are the
+ * per-voxel Voxel::normals lists in occupied order (Volume.hpp:32); both may be NULL (no normals). */
+int dmf_upload_volume(dmf_ctx* ctx, const double bounds[6], const double delta[3], const int dim[3],
+                      const uint64_t* occupied_ids, size_t n_occ,
+                      const uint32_t* normal_offsets, const float* normals);
+
+/* Build the volume inside the library from a point cloud: setDimensions + setVolumeSize + constructVolume
+ * + integratePointCloud(cloud, normals) (Volume.hpp:89-128,199-228), then upload.  normals may be NULL
+ * (the xyz-only overload, Volume.hpp:172-197). */
+int dmf_volume_from_points(dmf_ctx* ctx, const double bounds[6], const int dims[3],
+                           const float* xyz, const float* normals, size_t n_points);
+
+/* dims[3], deltas[3], n_occ, n_normals of the uploaded volume (any pointer may be NULL) */
+int dmf_volume_info(dmf_ctx* ctx, int dims[3], double deltas[3], double* voxel_size, size_t* n_occ, size_t* n_normals);
+int dmf_volume_get_occupied(dmf_ctx* ctx, uint64_t* ids /* n_occ */);
+/* CSR of the per-voxel normal lists in occupied order: offsets[n_occ+1], normals[3*n_normals] */
+int dmf_volume_get_normals(dmf_ctx* ctx, uint32_t* offsets, float* normals);
+
+/* Voxel::view / Voxel::good (Volume.hpp:33-34) live on the device between calls. */
+int dmf_clear_marks(dmf_ctx* ctx);
+int dmf_download_marks(dmf_ctx* ctx, int32_t* view /* n_occ */, uint8_t* good /* n_occ */);
+
+/* ---- forward per-pixel march ------------------------------------------------------------------ */
+typedef struct {
+    int mode;        /* DMF_MODE_*                                                                    */
+    int zdelta;      /* z-plane stride in mm (reference defaults: 10; 1 for MINIMUM)                   */
+    int sparse;      /* pixel stride 5 (10 for MINIMUM) instead of 1                                   */
+    int view_id0;    /* CLASSIFY: `view` argument of pose 0; pose i uses view_id0 + i                  */
+    int grid_format; /* DMF_GRID_*                                                                     */
+} dmf_forward_params;
+
+/* Per-view outputs; any pointer may be NULL.  For the *_dev entry point these are device pointers. */
+typedef struct {
+    int32_t*  depth_mm;    /* [n_views][H][W]    z_depth (mm) of each pixel's first occupied sample, -1 = none/not cast */
+    float*    points;      /* [n_views][H][W][3] world-space sample point of that first hit (simulated depth cloud), 0 if none */
+    uint64_t* hit_voxel;   /* [n_views][H][W]    voxel id of the first hit, DMF_NO_VOXEL if none           */
+    uint64_t* visibility;  /* [n_views][vis_words] bit i <=> occupied_cells_[i] is in the view's returned id list */
+    int32_t*  found_any;   /* [n_views]          .first of the returned pair (any pixel hit)               */
+    int32_t*  min_depth;   /* [n_views]          rayTraceAndGetMinimum result (-1 = none); MINIMUM mode    */
+    uint64_t* ids;         /* returned id lists, discovery order (z_depth, r, c), views concatenated       */
+    int64_t*  ids_offsets; /* [n_views+1]        view v owns ids[ids_offsets[v] .. ids_offsets[v+1])       */
+    size_t    ids_capacity;/* entries available in ids; fails (no partial write) if too small             */
+} dmf_forward_out;
+
+size_t dmf_visibility_words(dmf_ctx* ctx);   /* ceil(n_occ/64) */
+
+/* Host-buffer call: copies poses H2D, casts all views, copies the requested outputs D2H, synchronises.
+ * Replaces n_views consecutive calls of one forward routine (RayTracingEngine.hpp:229,268,311,377,447). */
+int dmf_forward(dmf_ctx* ctx, const dmf_forward_params* p, const float* poses, int n_views, const dmf_forward_out* out);
+
+/* Device-buffer call: poses and outputs already in HBM (ids / ids_offsets not supported here); enqueues on
+ * `stream` (a cudaStream_t, NULL = the context's stream) and returns without synchronising. */
+int dmf_forward_dev(dmf_ctx* ctx, const dmf_forward_params* p, const float* d_poses, int n_views,
+                    const dmf_forward_out* d_out, void* stream);
+
+/* ---- reverse per-voxel march ------------------------------------------------------------------ */
+typedef struct {
+    uint64_t* visibility;  /* [n_views][vis_words] bit i <=> occupied_cells_[i] emitted (good_points)      */
+    uint64_t* unoccluded;  /* [n_views][vis_words] bit i <=> occupied_cells_[i] not occluded (view=1 when viz) */
+    int32_t*  found_any;   /* [n_views]                                                                   */
+    uint64_t* ids;         /* emitted centroid hashes in emission order, views concatenated               */
+    int64_t*  ids_offsets; /* [n_views+1]                                                                 */
+    size_t    ids_capacity;
+} dmf_reverse_out;
+
+/* fast = 1: reverseRayTraceFast (:136-226); fast = 0: reverseRayTrace (:45-134).  viz != 0 also updates
+ * Voxel::view / Voxel::good on the device (dmf_download_marks). */
+int dmf_reverse(dmf_ctx* ctx, int fast, int viz, const float* poses, int n_views, const dmf_reverse_out* out);
+int dmf_reverse_dev(dmf_ctx* ctx, int fast, int viz, const float* d_poses, int n_views, const dmf_reverse_out* d_out, void* stream);
+
+/* ---- z-buffer splat: rayTraceVolume (:498-564) ------------------------------------------------ */
+/* depth receives the H*W z-buffer (mm, -1 = empty; not returned by the reference, exposed for parity);
+ * Voxel::view is set to 1 on the device for voxels whose depth equals the buffer. */
+int dmf_zbuffer(dmf_ctx* ctx, const float pose[12], int32_t* depth /* H*W or NULL */, int64_t* n_splat /* or NULL */);
+
+/* ---- greedy set cover over visibility bitsets: Algorithms::greedySetCover (Algorithms.hpp:38-86) */
+/* bitsets: [n_sets][words] host buffer (bit i = element i).  selected receives the chosen set indices in
+ * selection order (capacity n_sets); *n_selected their count. */
+int dmf_greedy_set_cover(dmf_ctx* ctx, const uint64_t* bitsets, int n_sets, size_t words, int32_t* selected, int* n_selected);
+int dmf_greedy_set_cover_dev(dmf_ctx* ctx, const uint64_t* d_bitsets, int n_sets, size_t words, int32_t* selected, int* n_selected);
+
+/* ---- bitwise OR of per-rank bitsets (the "seen" map combine step of a sharded sweep) ------------ */
+/* d_dst[w] |= OR over r of d_src[r*words + w];  device pointers, enqueued on stream */
+int dmf_or_reduce_dev(dmf_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int n_src, size_t words, void* stream);
+
+/* ---- counters ---------------------------------------------------------------------------------- */
+enum {
+    DMF_CNT_SAMPLES = 0,   /* probes evaluated (pixel,z_depth) / (voxel,step)                              */
+    DMF_CNT_INBOUNDS = 1,  /* probes that passed validPoints, up to and including the first hit           */
+    DMF_CNT_HITS = 2,      /* forward: rays that hit; reverse: unoccluded voxels                          */
+    DMF_CNT_EXACT_DIV = 3, /* probes whose voxel index needed the exact-division path (quotient near an integer) */
+    DMF_CNT_OOB = 4,       /* reads the reference would perform out of bounds (treated as empty)          */
+    DMF_CNT_ACOS_TIES = 5, /* good-point tests whose dot product fell in the host-libm acosf ambiguity band */
+    DMF_CNT_LAUNCHES = 6,  /* kernels launched by this context                                           */
+    DMF_CNT_RUNAWAY = 7,   /* reverse marches stopped by the step cap                                     */
+    DMF_CNT_COUNT = 8
+};
+int dmf_counters(dmf_ctx* ctx, uint64_t out[DMF_CNT_COUNT]);  /* cumulative; synchronises */
+int dmf_reset_counters(dmf_ctx* ctx);
+
+/* duration in ms of the kernels of the most recent *_dev/host call on this context, measured with CUDA
+ * events on the launching stream (synchronises) */
+int dmf_last_kernel_ms(dmf_ctx* ctx, float* ms);
+int dmf_synchronize(dmf_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMF_B200_H */

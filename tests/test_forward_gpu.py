@@ -1,0 +1,180 @@
+"""GPU parity: forward per-pixel march (K1) through the C ABI vs the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): voxel hit sets, occupancy counts and visibility bitsets bit-exact; simulated
+depths / points within 1e-5 relative (they are in fact compared bit-exact; the tolerance is stated for the record).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+K_H, K_W = 480, 640
+DEPTH_RTOL = 1e-5
+
+
+def _scene_pair(dmf, oracle, ctx, name):
+    sc = dmf.scenes.scene(name)
+    ov = oracle.volume_from_scene(sc, flat=True)
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds)
+    gv.setVolumeSize(*sc.dims)
+    gv.constructVolume()
+    gv.integratePointCloud(sc.points, sc.normals)
+    return sc, ov, gv
+
+
+def _poses(dmf, sc, n_sphere=3):
+    L = float(sc.bounds[1])
+    ps = [dmf.scenes.pose_p1(L)[0]]
+    ps += list(dmf.scenes.poses_sphere_lookat(L, 200)[:: max(1, 200 // n_sphere)][:n_sphere])
+    ps += list(dmf.scenes.poses_position_camera(L, 40)[[7, 23]])
+    return np.stack(ps)
+
+
+def _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, mode, zdelta, sparse, grid_format=0, H=K_H, W=K_W, K=None):
+    K = dmf.scenes.REFERENCE_K if K is None else K
+    eng = dmf.RayTracingEngine(dmf.Camera(K, H, W), ctx, grid_format)
+    ctx.reset_counters()
+    g = eng.forward_views(gv, poses, mode, zdelta, sparse)
+    cnt = ctx.counters()
+    occ = gv.occupied_cells_
+    assert np.array_equal(occ, ov.occupied()), "occupied_cells_ differ"
+    tot = dict(samples=0, inbounds=0, hits=0)
+    for i, pose in enumerate(poses):
+        o = oracle.forward(ov, K, H, W, pose, mode, zdelta, sparse)
+        assert bool(g["found_any"][i]) == o["found_any"], f"view {i}: found_any"
+        assert np.array_equal(g["depth"][i], o["depth"]), f"view {i}: first-hit depth image differs in {(g['depth'][i] != o['depth']).sum()} px"
+        hit = o["depth"] >= 0
+        assert np.array_equal(g["voxel"][i][hit], o["voxel"][hit]), f"view {i}: hit voxel ids differ"
+        assert np.all(g["voxel"][i][~hit] == dmf.NO_VOXEL)
+        # simulated depth cloud: stated tolerance 1e-5 relative; observed: bit-exact
+        np.testing.assert_allclose(g["points"][i][hit], o["points"][hit], rtol=DEPTH_RTOL, atol=0)
+        assert np.array_equal(g["points"][i][hit], o["points"][hit]), f"view {i}: points not bit-exact"
+        # returned id list: exact, in the reference's discovery order
+        assert np.array_equal(g["ids"][i], o["ids"]), f"view {i}: id list differs (gpu {len(g['ids'][i])}, oracle {len(o['ids'])})"
+        # visibility bitset == set of returned ids
+        vis_idx = dmf.bits_to_indices(g["visibility"][i])
+        assert np.array_equal(np.sort(occ[vis_idx]), np.sort(o["ids"])), f"view {i}: visibility bitset != id set"
+        for k in tot:
+            tot[k] += o["counters"][k]
+    assert cnt["samples"] == tot["samples"] and cnt["inbounds"] == tot["inbounds"] and cnt["hits"] == tot["hits"], (cnt, tot)
+    return cnt
+
+
+@pytest.mark.parametrize("name", ["S64", "S128", "S128-odd", "S128-clutter"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_points_and_good_points_dense(dmf, oracle, ctx, name, mode):
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, name)
+    _check_forward(dmf, oracle, ctx, sc, ov, gv, _poses(dmf, sc), mode, sc.zdelta, False)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sparse_default_arguments(dmf, oracle, ctx, mode):
+    """reference defaults: zdelta=10, sparse=true (pixel stride 5)"""
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S128")
+    _check_forward(dmf, oracle, ctx, sc, ov, gv, _poses(dmf, sc), mode, 10, True)
+
+
+def test_byte_grid_matches(dmf, oracle, ctx):
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S128")
+    _check_forward(dmf, oracle, ctx, sc, ov, gv, _poses(dmf, sc, 2), 0, sc.zdelta, False, grid_format=dmf.GRID_BYTE)
+
+
+def test_ragged_image_and_odd_zdelta(dmf, oracle, ctx):
+    """image size not a multiple of the tile, z stride that does not divide the range"""
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S64")
+    K = dmf.scenes.REFERENCE_K.copy()
+    K[[0, 2, 4, 5]] *= 0.25
+    for sparse in (False, True):
+        _check_forward(dmf, oracle, ctx, sc, ov, gv, _poses(dmf, sc, 2), 0, 7, sparse, H=123, W=157, K=K)
+
+
+def test_empty_volume_and_camera_outside(dmf, oracle, ctx):
+    sc = dmf.scenes.scene("S64")
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume()
+    gv.integratePointCloud(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    eng = dmf.RayTracingEngine(dmf.Camera(dmf.scenes.REFERENCE_K), ctx)
+    found, ids = eng.rayTraceAndGetPoints(gv, dmf.scenes.pose_p1(1.024)[0], 8, False)
+    assert not found and len(ids) == 0
+    # camera far outside the volume looking away: nothing in bounds
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S64")
+    away = dmf.scenes.look_at([5.0, 5.0, 5.0], [9.0, 9.0, 9.0])
+    _check_forward(dmf, oracle, ctx, sc, ov, gv, away[None], 0, 8, False)
+
+
+def test_classify_and_mark(dmf, oracle, ctx):
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S128")
+    poses = _poses(dmf, sc)
+    K = dmf.scenes.REFERENCE_K
+    eng = dmf.RayTracingEngine(dmf.Camera(K), ctx)
+    # sequential rayTraceAndClassify calls with increasing view ids == one batched call
+    gv._commit(ctx); gv.clear_marks(); ov.clear_marks()
+    eng.forward_views(gv, poses, dmf.MODE_CLASSIFY, sc.zdelta, False, view_id0=3, want=())
+    for i, p in enumerate(poses):
+        oracle.forward(ov, K, K_H, K_W, p, oracle.MODE_CLASSIFY, sc.zdelta, False, view=3 + i, want_pixels=False)
+    gview, ggood = gv.marks()
+    oview, ogood = ov.marks()
+    assert np.array_equal(gview, oview), f"Voxel::view differs on {(gview != oview).sum()} voxels"
+    assert np.array_equal(ggood, ogood), f"Voxel::good differs on {(ggood != ogood).sum()} voxels"
+    assert gview.max() > 3 and ggood.sum() > 0
+    # a second classify pass must not overwrite existing view ids
+    eng.rayTraceAndClassify(gv, poses[1], sc.zdelta, 99, False)
+    oracle.forward(ov, K, K_H, K_W, poses[1], oracle.MODE_CLASSIFY, sc.zdelta, False, view=99, want_pixels=False)
+    assert np.array_equal(gv.marks()[0], ov.marks()[0])
+    # rayTrace: view = 1 on every first-hit voxel
+    gv.clear_marks(); ov.clear_marks()
+    eng.rayTrace(gv, poses[2], sc.zdelta, True)
+    oracle.forward(ov, K, K_H, K_W, poses[2], oracle.MODE_MARK, sc.zdelta, True, want_pixels=False)
+    assert np.array_equal(gv.marks()[0], ov.marks()[0]) and gv.marks()[0].sum() > 0
+
+
+@pytest.mark.parametrize("sparse,zdelta", [(True, 1), (False, 1), (True, 3)])
+def test_minimum(dmf, oracle, ctx, sparse, zdelta):
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S128")
+    K = dmf.scenes.REFERENCE_K
+    eng = dmf.RayTracingEngine(dmf.Camera(K), ctx)
+    poses = _poses(dmf, sc)
+    g = eng.forward_views(gv, poses, dmf.MODE_MINIMUM, zdelta, sparse, want=())["min_depth"]
+    for i, p in enumerate(poses):
+        o = oracle.forward(ov, K, K_H, K_W, p, oracle.MODE_MINIMUM, zdelta, sparse, want_pixels=False)
+        assert int(g[i]) == o["min_depth"], (i, int(g[i]), o["min_depth"])
+    assert eng.rayTraceAndGetMinimum(gv, dmf.scenes.look_at([5, 5, 5], [9, 9, 9]), 1, True) == -1
+
+
+def test_config1_512_dyadic_single_view(dmf, oracle, ctx):
+    """BASELINE.json configs[1]: one 640x480 view into the 512^3 grid (dyadic bounds => op-order independent)."""
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S512")
+    poses = np.stack([dmf.scenes.pose_p1(1.0)[0], dmf.scenes.poses_sphere_lookat(1.0, 64)[37]])
+    cnt = _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, 0, sc.zdelta, False)
+    assert cnt["exact_div"] == 0   # power-of-two voxel size: reciprocal multiply is exact
+
+
+def test_full_size_properties_512(dmf, ctx):
+    """Size-independent properties at full size (no oracle): byte grid == bit grid, batched == one-by-one,
+    sparse lattice is a sub-sampling of dense, visibility popcount == unique hit voxels, idempotence."""
+    sc = dmf.scenes.scene("S512")
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+    K = dmf.scenes.REFERENCE_K
+    poses = dmf.scenes.poses_sphere_lookat(1.0, 256)[::32]
+    e_bit = dmf.RayTracingEngine(dmf.Camera(K), ctx, dmf.GRID_BIT)
+    e_byte = dmf.RayTracingEngine(dmf.Camera(K), ctx, dmf.GRID_BYTE)
+    a = e_bit.forward_views(gv, poses, 0, sc.zdelta, False)
+    b = e_byte.forward_views(gv, poses, 0, sc.zdelta, False)
+    for k in ("depth", "voxel", "points", "visibility"):
+        assert np.array_equal(a[k], b[k]), k
+    one = e_bit.forward_views(gv, poses[3:4], 0, sc.zdelta, False)
+    assert np.array_equal(one["depth"][0], a["depth"][3]) and np.array_equal(one["ids"][0], a["ids"][3])
+    again = e_bit.forward_views(gv, poses, 0, sc.zdelta, False)
+    assert np.array_equal(again["depth"], a["depth"])
+    sp = e_bit.forward_views(gv, poses, 0, sc.zdelta, True)
+    assert np.array_equal(sp["depth"][:, ::5, ::5], a["depth"][:, ::5, ::5])
+    mask = np.ones(sp["depth"].shape[1:], bool); mask[::5, ::5] = False
+    assert np.all(sp["depth"][:, mask] == -1)
+    for i in range(len(poses)):
+        hit = a["depth"][i] >= 0
+        uniq = np.unique(a["voxel"][i][hit])
+        assert len(uniq) == len(a["ids"][i]) == int(np.unpackbits(a["visibility"][i].view(np.uint8)).sum())
+        assert np.array_equal(np.sort(a["ids"][i]), uniq)
+        assert np.isin(uniq, gv.occupied_cells_).all()
