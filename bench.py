@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s and voxel-updates/s of the RayTracingEngine forward march (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--views V] [--impl reference]
+
+A step = one pass of the hot path over one batch of V synthetic views per GPU: 640x480 camera, 512^3
+box-shell grid (scene S512 of SURVEY 8d), zdelta = 2 mm, sparse = false, rayTraceAndGetPoints semantics
+(first-hit depth image + simulated point cloud + hit voxel ids + per-view visibility bitset).
+    value  : whole-job rays/s with poses and outputs resident in HBM (dmf_forward_dev), CUDA-event timed.
+    e2e    : the same through the host-buffer C-ABI call dmf_forward (pinned host buffers; H2D of the poses
+             and D2H of depth + points + visibility inside the timed region).
+    N > 1  : one process per GPU (torchrun), views sharded by rank, grid replicated, per-view visibility
+             bitsets all-gathered over NCCL every step (the exchange the set-cover consumer needs).
+--impl reference times the CPU oracle port of the reference (the reference itself cannot be built here:
+no Eigen/PCL) on the host cores, same workload, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "depth-map-fusion-utils_b200"))
+
+H, W = 480, 640
+SCENE = "S512"
+WORKLOAD = "S512 box shell (512^3 grid, 1 m cube), 640x480 camera, zdelta=2mm dense, sphere look-at sweep (P1024)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--views", type=int, default=128, help="views per step per GPU (128 x 8 GPUs = the 1024-view sweep)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", default="bit", choices=["bit", "byte"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hot = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(hot)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per k_forward launch from the committed ncu capture, if any (profiles/*_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "forward_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def oracle_volume(O, scenes, flat: bool):
+    sc = scenes.scene(SCENE)
+    return sc, O.volume_from_scene(sc, flat=flat)
+
+
+def cpu_baseline(scenes, n_views_serial=2, with_all_cores=True) -> dict:
+    """The oracle port (kind 'port') timed on this box's host cores: the reference's own single-threaded path on its
+    own pointer grid, then the same code with views spread over all cores.  Bounded sample, stated."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    sc, vol = oracle_volume(O, scenes, flat=False)
+    poses = scenes.bench_poses(float(sc.bounds[1]), 64)
+    K = scenes.REFERENCE_K
+    sec, _ = O.time_views(vol, K, H, W, poses[:n_views_serial], O.MODE_POINTS, sc.zdelta, False, threads=1)
+    out = {"value": n_views_serial * H * W / sec, "unit": "rays/s", "cores": 1, "kind": "port",
+           "sample": f"{n_views_serial} views of the same workload, 1 thread, reference vector<vector<vector<Voxel*>>> grid; the reference hot path is single-threaded",
+           "sec_per_view": sec / n_views_serial}
+    if with_all_cores:
+        nt = O.max_threads()
+        nv = max(nt, 2)
+        sec2, _ = O.time_views(vol, K, H, W, poses[:nv], O.MODE_POINTS, sc.zdelta, False, threads=nt)
+        out["all_cores"] = {"value": nv * H * W / sec2, "cores": nt, "sample": f"{nv} views over {nt} OpenMP threads"}
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dmf_b200 import scenes
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    sc, vol = oracle_volume(O, scenes, flat=False)
+    K = scenes.REFERENCE_K
+    nt = O.max_threads()
+    nv = max(nt, 1)                      # one view per host thread per step: a bounded sample of the V-view batch
+    poses = scenes.bench_poses(float(sc.bounds[1]), 1024)
+    cnt = O.forward(vol, K, H, W, poses[0], O.MODE_POINTS, sc.zdelta, False, want_pixels=False)["counters"]
+    steps, warm = max(1, min(args.steps, 6)), max(0, min(args.warmup, 1))   # ~5 s per step: keep the run to a few minutes
+    for i in range(warm):
+        O.time_views(vol, K, H, W, poses[i * nv:(i + 1) * nv], O.MODE_POINTS, sc.zdelta, False, threads=nt)
+    total = 0.0
+    for i in range(steps):
+        s, _ = O.time_views(vol, K, H, W, poses[(warm + i) * nv:(warm + i + 1) * nv], O.MODE_POINTS, sc.zdelta, False, threads=nt)
+        total += s
+    val = steps * nv * H * W / total
+    line = {
+        "impl": "reference", "metric": "rays/s", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "views_per_step": nv, "note": "CPU oracle port of the reference (reference needs Eigen/PCL, not buildable here); "
+                   "each step is a bounded sample of the batch: one view per host thread"},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": nt, "kind": "port", "sample": f"{nv} views per step over {nt} OpenMP threads, reference pointer grid"},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "voxel_updates_per_s": val / (H * W) * cnt["inbounds"], "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import dmf_b200 as D
+    from dmf_b200._lib import ForwardOut, ForwardParams, check
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    V = args.views
+    ctx = D.Context(local)
+    sc = D.scenes.scene(SCENE)
+    vol = D.VoxelVolume(ctx)
+    vol.setDimensions(*sc.bounds); vol.setVolumeSize(*sc.dims); vol.constructVolume(); vol.integratePointCloud(sc.points, sc.normals)
+    fmt = D.GRID_BIT if args.grid == "bit" else D.GRID_BYTE
+    eng = D.RayTracingEngine(D.Camera(D.scenes.REFERENCE_K, H, W), ctx, fmt)
+    eng._prepare(vol)
+    n_occ = len(vol.occupied_cells_)
+    vw = (n_occ + 63) // 64
+    all_poses = D.scenes.bench_poses(float(sc.bounds[1]), V * world)
+    poses = np.ascontiguousarray(all_poses[rank * V:(rank + 1) * V])      # this rank's shard of the sweep
+    dev = torch.device("cuda", local)
+
+    # device-resident buffers for `value`
+    d_poses = torch.from_numpy(poses).to(dev)
+    d_depth = torch.empty((V, H, W), dtype=torch.int32, device=dev)
+    d_points = torch.empty((V, H, W, 3), dtype=torch.float32, device=dev)
+    d_voxel = torch.empty((V, H, W), dtype=torch.int64, device=dev)
+    d_vis = torch.zeros((V, vw), dtype=torch.int64, device=dev)
+    d_found = torch.zeros((V,), dtype=torch.int32, device=dev)
+    d_vis_all = torch.zeros((world * V, vw), dtype=torch.int64, device=dev) if world > 1 else None
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    params = ForwardParams(D.MODE_POINTS, sc.zdelta, 0, 1, fmt)
+    o = ForwardOut()
+    o.depth_mm, o.points, o.hit_voxel = d_depth.data_ptr(), d_points.data_ptr(), d_voxel.data_ptr()
+    o.visibility, o.found_any = d_vis.data_ptr(), d_found.data_ptr()
+
+    def step_dev():
+        st = torch.cuda.current_stream().cuda_stream
+        check(ctx.lib.dmf_forward_dev(ctx.h, C.byref(params), C.c_void_p(d_poses.data_ptr()), V, C.byref(o), C.c_void_p(st)))
+        if world > 1:
+            dist.all_gather_into_tensor(d_vis_all, d_vis)
+
+    # ---- value: device-resident, CUDA events on torch's current stream --------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    torch.cuda.synchronize()
+    ctx.reset_counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    hot_ms = []
+    barrier(); torch.cuda.synchronize()
+    t_wall = time.perf_counter()
+    for a, b in evs:
+        if flush is not None:
+            flush.fill_(1)                      # evict the L2 between timed iterations (not timed)
+        a.record()
+        step_dev()
+        b.record()
+        if rank == 0 and len(hot_ms) < 4:
+            hot_ms.append(ctx.last_hot_kernel_ms())   # synchronises; cheap, outside the event pair's GPU time
+    torch.cuda.synchronize(); barrier()
+    wall = time.perf_counter() - t_wall
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+    cnt = ctx.counters()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    rays_total = args.steps * V * H * W * world
+    value = rays_total / (dev_ms * 1e-3)
+    inb = torch.tensor([cnt["inbounds"], cnt["samples"], cnt["launches"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(inb)
+    inbounds_total, samples_total, launches_total = (float(x) for x in inb.tolist())
+
+    # ---- e2e: host-buffer C-ABI call, pinned host memory, H2D + D2H inside the timed region ---------------------
+    def pinned(shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = ctx.lib.dmf_host_alloc(max(n, 8))
+        if not p:
+            raise SystemExit("dmf_host_alloc failed")
+        return np.frombuffer((C.c_char * n).from_address(p), dtype=dtype).reshape(shape), p
+
+    h_poses, p0 = pinned((V, 12), np.float32)
+    h_poses[:] = poses
+    h_depth, p1 = pinned((V, H, W), np.int32)
+    h_points, p2 = pinned((V, H, W, 3), np.float32)
+    h_vis, p3 = pinned((V, max(vw, 1)), np.uint64)
+    h_found, p4 = pinned((V,), np.int32)
+    oh = ForwardOut()
+    oh.depth_mm, oh.points, oh.visibility, oh.found_any = h_depth.ctypes.data, h_points.ctypes.data, h_vis.ctypes.data, h_found.ctypes.data
+    fp = h_poses.ctypes.data_as(C.POINTER(C.c_float))
+
+    def step_host():
+        check(ctx.lib.dmf_forward(ctx.h, C.byref(params), fp, V, C.byref(oh)))
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_host()
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize(); barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = e2e_steps * V * H * W * world / e2e_s
+    same = bool(np.array_equal(h_depth, d_depth.cpu().numpy()))
+    h2d = V * 48
+    d2h = V * (H * W * 4 + H * W * 12 + vw * 8 + 4)
+    for p in (p0, p1, p2, p3, p4):
+        ctx.lib.dmf_host_free(p)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        # algorithmic bytes of one k_forward launch: 1/8 B (bit grid) or 1 B (byte grid) per in-bounds sample,
+        # + 24 B per cast ray (int32 depth, float3 point, uint64 hit id), + n_occ/8 B visibility and 48 B pose per view
+        per_launch_inb = cnt["inbounds"] / args.steps
+        grid_b = 0.125 if fmt == D.GRID_BIT else 1.0
+        alg_bytes = per_launch_inb * grid_b + V * H * W * 24 + V * (vw * 8 + 48)
+        hot = float(np.mean(hot_ms)) if hot_ms else dev_ms / args.steps
+        achieved = alg_bytes / (hot * 1e-3) / 1e9
+        traffic = ncu_traffic()
+        line = {
+            "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "views_per_step_per_gpu": V, "mode": "rayTraceAndGetPoints", "grid_format": args.grid,
+                       "outputs": "depth_mm+points+hit_voxel+visibility", "n_occupied": n_occ,
+                       "l2": "flushed between timed iterations (256 MiB fill, untimed)" if flush is not None else "not flushed",
+                       "parallelism": f"views sharded over {world} GPU(s), grid replicated" + (", visibility all-gather (NCCL) per step" if world > 1 else "")},
+            "voxel_updates_per_s": inbounds_total / (dev_ms * 1e-3),
+            "samples_per_s": samples_total / (dev_ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
+                         "peak_source": peak_src, "kernel": "k_forward", "kernel_ms": hot, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "issue-bound by design: ~60 exact-IEEE instructions per probe, grid is L2-resident; see DESIGN.md"},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_run": same},
+            "gpu_launches": int(launches_total),
+            "clocks": clocks,
+            "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(D.scenes)
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,7 @@ int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_v
     a.poses = d_poses; a.inv_poses = c->d_inv_poses.as<float>();
     a.vis = d_vis; a.unocc = d_unocc; a.found_any = d_found; a.viz = viz;
     a.emit_list = d_emit_list; a.emit_count = d_emit_count; a.emit_cap = emit_cap;
+    DMF_CUDA(cudaEventRecord(c->ev_h0, st));
     if (fast) {
         if (!c->n_occ) return 0;
         dim3 grid((unsigned)((c->n_occ + 127) / 128), n_views);
@@ -53,6 +54,8 @@ int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_v
         dim3 grid((unsigned)gx, n_views);
         k_reverse<false><<<grid, 128, 0, st>>>(a);
     }
+    DMF_CUDA(cudaEventRecord(c->ev_h1, st));
+    c->hot_timed = true;
     c->launches++;
     DMF_CUDA(cudaGetLastError());
     return 0;

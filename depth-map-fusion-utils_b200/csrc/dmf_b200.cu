@@ -210,6 +210,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     a.first_view = c->d_first_view.as<int>(); a.good_bits = c->d_good_bits.as<unsigned>(); a.view_mark = c->d_view_mark.as<int>();
     a.counters = c->d_counters.as<u64>();
     dim3 grid((c->Wc + FWD_TILE_W - 1) / FWD_TILE_W, (c->Hc + FWD_TILE_H - 1) / FWD_TILE_H, n_views);
+    DMF_CUDA(cudaEventRecord(c->ev_h0, st));
     switch (p->mode) {
         case 0: launch_forward_fmt<0>(a, p->grid_format, grid, st); break;
         case 1: launch_forward_fmt<1>(a, p->grid_format, grid, st); break;
@@ -217,6 +218,8 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
         case 3: launch_forward_fmt<3>(a, p->grid_format, grid, st); break;
         default: launch_forward_fmt<4>(a, p->grid_format, grid, st); break;
     }
+    DMF_CUDA(cudaEventRecord(c->ev_h1, st));
+    c->hot_timed = true;
     c->launches++;
     DMF_CUDA(cudaGetLastError());
     if (p->mode == DMF_MODE_CLASSIFY && c->n_occ) {
@@ -238,6 +241,13 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
 extern "C" {
 
 int dmf_version(void) { return 100; }
+
+int dmf_host_angle_test(float out[3]) {
+    if (!out) return fail("null argument");
+    AngleTest t = bisect_angle_test();
+    out[0] = t.dot_min; out[1] = t.band_lo; out[2] = t.band_hi;
+    return 0;
+}
 const char* dmf_last_error(void) { return last_error().c_str(); }
 
 int dmf_device_count(void) {
@@ -269,6 +279,7 @@ int dmf_create(dmf_ctx** out, int device) {
     DMF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DMF_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     DMF_CUDA(cudaEventCreate(&c->ev_k0)); DMF_CUDA(cudaEventCreate(&c->ev_k1));
+    DMF_CUDA(cudaEventCreate(&c->ev_h0)); DMF_CUDA(cudaEventCreate(&c->ev_h1));
     for (int i = 0; i < 2; i++) {
         DMF_CUDA(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
         DMF_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
@@ -292,6 +303,8 @@ void dmf_destroy(dmf_ctx* c) {
     for (auto* b : bufs) b->release();
     for (int i = 0; i < 2; i++) for (int j = 0; j < 8; j++) c->d_out[i][j].release();
     for (int i = 0; i < 2; i++) { if (c->ev_compute[i]) cudaEventDestroy(c->ev_compute[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
+    if (c->ev_h0) cudaEventDestroy(c->ev_h0);
+    if (c->ev_h1) cudaEventDestroy(c->ev_h1);
     if (c->ev_k0) cudaEventDestroy(c->ev_k0);
     if (c->ev_k1) cudaEventDestroy(c->ev_k1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -404,6 +417,7 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
     size_t per_view = 48 + (out->depth_mm ? HW * 4 : 0) + (out->points ? HW * 12 : 0) + (out->hit_voxel ? HW * 8 : 0) +
                       (out->visibility ? vw * 8 : 0) + 8 + (want_ids ? c->n_occ * 4 + R * 20 : 0);
     int chunk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n_views, (size_t)4096, ((size_t)1 << 30) / per_view}));
+    if (!want_ids && n_views >= 8) chunk = std::min(chunk, (n_views + 3) / 4);   // >= 4 chunks: D2H of one overlaps the march of the next
     cudaStream_t st = c->stream, cs = c->copy_stream;
     DMF_CUDA(cudaEventRecord(c->ev_k0, st));
     int64_t ids_total = 0;
@@ -420,7 +434,7 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
         if (out->points) { DMF_TRY(ob[1].reserve(nv * HW * 12)); d.points = ob[1].as<float>(); }
         if (out->hit_voxel) { DMF_TRY(ob[2].reserve(nv * HW * 8)); d.hit_voxel = ob[2].as<uint64_t>(); }
         if (out->visibility && vw) { DMF_TRY(ob[3].reserve(nv * vw * 8)); d.visibility = ob[3].as<uint64_t>(); }
-        if (out->found_any || true) { DMF_TRY(ob[4].reserve((size_t)nv * 4)); d.found_any = ob[4].as<int32_t>(); }
+        DMF_TRY(ob[4].reserve((size_t)nv * 4)); d.found_any = ob[4].as<int32_t>();
         if (p->mode == DMF_MODE_MINIMUM) { DMF_TRY(ob[5].reserve((size_t)nv * 4)); d.min_depth = ob[5].as<int32_t>(); }
         unsigned *fk = nullptr, *rk = nullptr; int* ro = nullptr;
         if (want_ids) {
@@ -492,6 +506,14 @@ int dmf_last_kernel_ms(dmf_ctx* c, float* ms) {
     DMF_CUDA(cudaSetDevice(c->device));
     DMF_CUDA(cudaEventSynchronize(c->ev_k1));
     DMF_CUDA(cudaEventElapsedTime(ms, c->ev_k0, c->ev_k1));
+    return 0;
+}
+int dmf_last_hot_kernel_ms(dmf_ctx* c, float* ms) {
+    if (!c || !ms) return fail("null argument");
+    if (!c->hot_timed) return fail("no march launched yet");
+    DMF_CUDA(cudaSetDevice(c->device));
+    DMF_CUDA(cudaEventSynchronize(c->ev_h1));
+    DMF_CUDA(cudaEventElapsedTime(ms, c->ev_h0, c->ev_h1));
     return 0;
 }
 int dmf_synchronize(dmf_ctx* c) {

@@ -124,7 +124,8 @@ struct dmf_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;     // bracket the kernels of the last call
     cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-    bool timed = false;
+    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;     // bracket the dominant march kernel of the last call
+    bool timed = false, hot_timed = false;
     // camera
     bool cam_set = false; float K[9]; int H = 0, W = 0;
     // volume

@@ -63,9 +63,11 @@ SYMBOLS = {
     "dmf_greedy_set_cover": (C.c_int, [vp, u64p, C.c_int, C.c_size_t, i32p, ip]),
     "dmf_greedy_set_cover_dev": (C.c_int, [vp, vp, C.c_int, C.c_size_t, i32p, ip]),
     "dmf_or_reduce_dev": (C.c_int, [vp, vp, vp, C.c_int, C.c_size_t, vp]),
+    "dmf_host_angle_test": (C.c_int, [fp]),
     "dmf_counters": (C.c_int, [vp, u64p]),
     "dmf_reset_counters": (C.c_int, [vp]),
     "dmf_last_kernel_ms": (C.c_int, [vp, fp]),
+    "dmf_last_hot_kernel_ms": (C.c_int, [vp, fp]),
     "dmf_synchronize": (C.c_int, [vp]),
 }
 

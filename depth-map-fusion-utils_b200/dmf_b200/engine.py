@@ -79,6 +79,11 @@ class Context:
         check(self.lib.dmf_last_kernel_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def last_hot_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(self.lib.dmf_last_hot_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def synchronize(self):
         check(self.lib.dmf_synchronize(self.h))
 

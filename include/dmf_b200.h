@@ -147,6 +147,12 @@ int dmf_greedy_set_cover_dev(dmf_ctx* ctx, const uint64_t* d_bitsets, int n_sets
 /* d_dst[w] |= OR over r of d_src[r*words + w];  device pointers, enqueued on stream */
 int dmf_or_reduce_dev(dmf_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int n_src, size_t words, void* stream);
 
+/* ---- host utility (no GPU needed) ------------------------------------------------------------- */
+/* The reference's good-point test  degree(acos(n.v)) in [0,90]  (CommonUtilities.hpp:17, RayTracingEngine.hpp:211-212)
+ * depends on the HOST libm's float acos.  The library bisects it once; the kernels then test dot_min <= d <= 1.
+ * out[0] = dot_min, out[1..2] = [band_lo, band_hi) where the host acosf was seen non-monotonic (empty if lo >= hi). */
+int dmf_host_angle_test(float out[3]);
+
 /* ---- counters ---------------------------------------------------------------------------------- */
 enum {
     DMF_CNT_SAMPLES = 0,   /* probes evaluated (pixel,z_depth) / (voxel,step)                              */
@@ -165,6 +171,8 @@ int dmf_reset_counters(dmf_ctx* ctx);
 /* duration in ms of the kernels of the most recent *_dev/host call on this context, measured with CUDA
  * events on the launching stream (synchronises) */
 int dmf_last_kernel_ms(dmf_ctx* ctx, float* ms);
+/* same, for the dominant march kernel alone (k_forward / k_reverse of the last chunk launched) */
+int dmf_last_hot_kernel_ms(dmf_ctx* ctx, float* ms);
 int dmf_synchronize(dmf_ctx* ctx);
 
 #ifdef __cplusplus
