@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--grid", default="bit", choices=["bit", "byte"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-skip", action="store_true", help="evaluate every probe (brute-force kernel)")
     return ap.parse_args()
 
 
@@ -213,13 +214,19 @@ def run_b200(args):
     d_found = torch.zeros((V,), dtype=torch.int32, device=dev)
     d_vis_all = torch.zeros((world * V, vw), dtype=torch.int64, device=dev) if world > 1 else None
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    params = ForwardParams(D.MODE_POINTS, sc.zdelta, 0, 1, fmt)
+    params = ForwardParams(D.MODE_POINTS, sc.zdelta, 0, 1, fmt, 1 if args.no_skip else 0)
     o = ForwardOut()
     o.depth_mm, o.points, o.hit_voxel = d_depth.data_ptr(), d_points.data_ptr(), d_voxel.data_ptr()
     o.visibility, o.found_any = d_vis.data_ptr(), d_found.data_ptr()
 
+    # a dedicated non-default stream: the C ABI treats a NULL stream as "the context's own stream", and torch.cuda.Event
+    # only sees work on torch's current stream
+    bench_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(bench_stream)
+
     def step_dev():
         st = torch.cuda.current_stream().cuda_stream
+        assert st != 0
         check(ctx.lib.dmf_forward_dev(ctx.h, C.byref(params), C.c_void_p(d_poses.data_ptr()), V, C.byref(o), C.c_void_p(st)))
         if world > 1:
             dist.all_gather_into_tensor(d_vis_all, d_vis)

@@ -38,46 +38,108 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
     VolDev& v = c->vol;
     std::memcpy(c->bounds, bounds, sizeof c->bounds);
     c->voxel_size = delta[0] * delta[1] * delta[2];
+    if ((double)(dim[0] + 1) * (dim[1] + 1) * (dim[2] + 1) >= 4294967296.0) return fail("volume %dx%dx%d too large for the 32-bit linear voxel index", dim[0], dim[1], dim[2]);
     for (int a = 0; a < 3; a++) {
-        v.dim[a] = dim[a]; v.nb[a] = (dim[a] + 3) / 4;
-        v.vmin[a] = bounds[2 * a]; v.delta[a] = delta[a];
+        const double vmin = bounds[2 * a], vmax = bounds[2 * a + 1];
+        v.dim[a] = dim[a]; v.pdim[a] = dim[a] + 1; v.mdim[a] = (dim[a] + 1 + 7) / 8;
+        v.vmin[a] = vmin; v.delta[a] = delta[a];
         v.inv[a] = 1.0 / delta[a];
-        v.c0[a] = -bounds[2 * a] * v.inv[a];
+        v.c0[a] = -vmin * v.inv[a];
         v.half[a] = delta[a] / 2.0;
-        int e; double mant = std::frexp(delta[a], &e);
-        if (mant == 0.5) v.eps[a] = 0.0;            // power-of-two delta: reciprocal multiply is exact
+        int e; const double mant = std::frexp(delta[a], &e);
+        const bool pow2 = (mant == 0.5);
+        if (pow2) v.eps[a] = 0.0;            // power-of-two delta: the double reciprocal multiply is exact
         else {
-            double bound = std::ldexp((double)dim[a] + 2.0, -51) + std::ldexp(std::fabs(bounds[2 * a]) * v.inv[a], -53);
+            double bound = std::ldexp((double)dim[a] + 2.0, -51) + std::ldexp(std::fabs(vmin) * v.inv[a], -53);
             v.eps[a] = std::max(4.0 * bound, std::ldexp(1.0, -30));
             if (v.eps[a] > 0.25) v.eps[a] = 1.0;    // hopeless conditioning: always take the exact path
         }
-        float lo = (float)bounds[2 * a]; if ((double)lo > bounds[2 * a]) lo = next_down(lo);
-        float hi = (float)bounds[2 * a + 1]; if ((double)hi < bounds[2 * a + 1]) hi = next_up(hi);
+        // float filter: q32 = fmaf(p, inv32, c32).  |q32 - q_ref| <= 2^-24 * (|p|max/delta + |vmin|/delta + dim + 1) (+ double-level
+        // terms); x2 safety.  Exact (err 0) when delta is a power of two and vmin == 0: then q32 == p/delta exactly.
+        v.inv32[a] = (float)v.inv[a]; v.c32[a] = (float)v.c0[a];
+        if (pow2 && vmin == 0.0) v.err32[a] = 0.0f;
+        else {
+            double pmax = std::max(std::fabs(vmin), std::fabs(vmax));
+            double e32 = 2.0 * std::ldexp(pmax * v.inv[a] * 2.0 + std::fabs(vmin) * v.inv[a] * 2.0 + dim[a] + 2.0, -24) + v.eps[a];
+            v.err32[a] = (float)std::min(e32 * (1.0 + 1e-6), 1.0);   // >= 0.5 means "always use the double path"
+            if (!(e32 == e32)) v.err32[a] = 1.0f;
+        }
+        float lo = (float)vmin; if ((double)lo > vmin) lo = next_down(lo);
+        float hi = (float)vmax; if ((double)hi < vmax) hi = next_up(hi);
         v.lo[a] = lo; v.hi[a] = hi;
     }
-    const size_t nbricks = (size_t)v.nb[0] * v.nb[1] * v.nb[2];
-    std::vector<uint64_t> bricks(nbricks, 0);
-    std::vector<uint32_t> prefix(nbricks, 0);
-    auto locate = [&](uint64_t id, size_t& b, unsigned& bit) -> bool {
+    const size_t nbits = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
+    const size_t nwords = ((nbits + 31) / 32 + 7) / 8 * 8;           // whole 8-word (256-bit) rank blocks
+    const size_t nmacro = (size_t)v.mdim[0] * v.mdim[1] * v.mdim[2];
+    std::vector<uint32_t> words(nwords, 0), prefix(nwords / 8, 0), macro((nmacro + 31) / 32, 0);
+    auto locate = [&](uint64_t id, size_t& idx) -> bool {
         const uint64_t mask = (1u << 20) - 1;
         long long x = (long long)(id >> 40), y = (long long)((id >> 20) & mask), z = (long long)(id & mask);   // getVoxelCoords :158-165
         if (x >= dim[0] || y >= dim[1] || z >= dim[2]) return false;
-        b = ((size_t)(x >> 2) * v.nb[1] + (size_t)(y >> 2)) * v.nb[2] + (size_t)(z >> 2);
-        bit = (unsigned)(((x & 3) << 4) | ((y & 3) << 2) | (z & 3));
+        idx = ((size_t)x * v.pdim[1] + (size_t)y) * v.pdim[2] + (size_t)z;
+        size_t m = ((size_t)(x >> 3) * v.mdim[1] + (size_t)(y >> 3)) * v.mdim[2] + (size_t)(z >> 3);
+        macro[m >> 5] |= 1u << (m & 31);
         return true;
     };
     for (size_t i = 0; i < n_occ; i++) {
-        size_t b; unsigned bit;
-        if (!locate(ids[i], b, bit)) return fail("occupied id %llu (#%zu) outside the %dx%dx%d grid", (unsigned long long)ids[i], i, dim[0], dim[1], dim[2]);
-        if ((bricks[b] >> bit) & 1ull) return fail("duplicate occupied id %llu (#%zu)", (unsigned long long)ids[i], i);
-        bricks[b] |= 1ull << bit;
+        size_t idx;
+        if (!locate(ids[i], idx)) return fail("occupied id %llu (#%zu) outside the %dx%dx%d grid", (unsigned long long)ids[i], i, dim[0], dim[1], dim[2]);
+        if ((words[idx >> 5] >> (idx & 31)) & 1u) return fail("duplicate occupied id %llu (#%zu)", (unsigned long long)ids[i], i);
+        words[idx >> 5] |= 1u << (idx & 31);
     }
+    std::vector<uint32_t> word_rank(nwords);
     uint32_t run = 0;
-    for (size_t b = 0; b < nbricks; b++) { prefix[b] = run; run += (uint32_t)__builtin_popcountll(bricks[b]); }
+    for (size_t w = 0; w < nwords; w++) { if ((w & 7) == 0) prefix[w >> 3] = run; word_rank[w] = run; run += (uint32_t)__builtin_popcount(words[w]); }
     std::vector<uint32_t> rank2occ(std::max<size_t>(n_occ, 1));
     for (size_t i = 0; i < n_occ; i++) {
-        size_t b; unsigned bit; locate(ids[i], b, bit);
-        rank2occ[prefix[b] + __builtin_popcountll(bricks[b] & ((1ull << bit) - 1ull))] = (uint32_t)i;
+        size_t idx; locate(ids[i], idx);
+        rank2occ[word_rank[idx >> 5] + __builtin_popcount(words[idx >> 5] & ((1u << (idx & 31)) - 1u))] = (uint32_t)i;
+    }
+    std::vector<uint32_t>().swap(word_rank);
+    // Chebyshev distance (in macro cells) from every macro cell to the nearest "blocked" cell: one that holds an occupied
+    // voxel, is not entirely inside [0,dim) on every axis, or lies outside the grid.  Box dilation is separable, so each
+    // radius step is three 1-D passes.  clearance = 8*(D-1) - 0.25 voxels for D >= 2, else 0 (see k_forward_skip).
+    std::vector<float> clearance(nmacro, 0.0f);
+    {
+        const int mx = v.mdim[0], my = v.mdim[1], mz = v.mdim[2];
+        const int ex = mx + 2, ey = my + 2, ez = mz + 2;                      // one blocked border cell on every side
+        auto at = [&](int x, int y, int z) { return ((size_t)x * ey + y) * ez + z; };
+        std::vector<uint8_t> cur((size_t)ex * ey * ez, 1), tmp(cur.size());
+        std::vector<uint8_t> dist(nmacro, 0);
+        for (int x = 0; x < mx; x++) for (int y = 0; y < my; y++) for (int z = 0; z < mz; z++) {
+            size_t m = ((size_t)x * my + y) * mz + z;
+            bool blocked = ((macro[m >> 5] >> (m & 31)) & 1u) || 8 * (x + 1) > dim[0] || 8 * (y + 1) > dim[1] || 8 * (z + 1) > dim[2];
+            cur[at(x + 1, y + 1, z + 1)] = blocked ? 1 : 0;
+        }
+        const int kMaxD = 40;
+        for (int r = 1; r <= kMaxD; r++) {
+            // dilate by one cell along z, then y, then x
+            for (int pass = 0; pass < 3; pass++) {
+                const size_t stride = pass == 0 ? 1 : (pass == 1 ? (size_t)ez : (size_t)ey * ez);
+                for (size_t i = 0; i < cur.size(); i++) {
+                    uint8_t c = cur[i];
+                    if (!c) { if (i >= stride && cur[i - stride]) c = 1; else if (i + stride < cur.size() && cur[i + stride]) c = 1; }
+                    tmp[i] = c;
+                }
+                // the flat +-stride neighbours wrap across rows only into border cells, which are blocked anyway
+                cur.swap(tmp);
+            }
+            size_t fresh = 0;
+            for (int x = 0; x < mx; x++) for (int y = 0; y < my; y++) for (int z = 0; z < mz; z++) {
+                size_t m = ((size_t)x * my + y) * mz + z;
+                if (cur[at(x + 1, y + 1, z + 1)] && dist[m] == 0) {
+                    bool blocked0 = ((macro[m >> 5] >> (m & 31)) & 1u) || 8 * (x + 1) > dim[0] || 8 * (y + 1) > dim[1] || 8 * (z + 1) > dim[2];
+                    if (!blocked0) { dist[m] = (uint8_t)r; fresh++; }
+                }
+            }
+            if (!fresh) break;
+        }
+        for (size_t m = 0; m < nmacro; m++) {
+            size_t xm = m / ((size_t)my * mz), ym = (m / mz) % my, zm = m % mz;
+            bool blocked0 = ((macro[m >> 5] >> (m & 31)) & 1u) || 8 * ((int)xm + 1) > dim[0] || 8 * ((int)ym + 1) > dim[1] || 8 * ((int)zm + 1) > dim[2];
+            int D = blocked0 ? 0 : (dist[m] ? dist[m] : kMaxD + 1);           // never reached: farther than kMaxD
+            clearance[m] = D >= 2 ? 8.0f * (float)(D - 1) - 0.25f : 0.0f;
+        }
     }
     c->n_occ = n_occ;
     c->h_occ.assign(ids, ids + n_occ);
@@ -87,14 +149,16 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
     c->h_normals.assign(3 * c->n_normals, 0.f);
     if (normals && c->n_normals) c->h_normals.assign(normals, normals + 3 * c->n_normals);
 
-    DMF_TRY(c->d_bricks.reserve(nbricks * 8)); DMF_TRY(c->d_prefix.reserve(nbricks * 4));
+    DMF_TRY(c->d_bricks.reserve(nwords * 4)); DMF_TRY(c->d_prefix.reserve(prefix.size() * 4)); DMF_TRY(c->d_macro.reserve(macro.size() * 4)); DMF_TRY(c->d_clearance.reserve(clearance.size() * 4));
     DMF_TRY(c->d_rank2occ.reserve(rank2occ.size() * 4)); DMF_TRY(c->d_occ_ids.reserve(std::max<size_t>(n_occ, 1) * 8));
     DMF_TRY(c->d_noff.reserve((n_occ + 1) * 4)); DMF_TRY(c->d_normals.reserve(std::max<size_t>(c->h_normals.size(), 1) * 4));
     DMF_TRY(c->d_view_mark.reserve(std::max<size_t>(n_occ, 1) * 4)); DMF_TRY(c->d_first_view.reserve(std::max<size_t>(n_occ, 1) * 4));
     DMF_TRY(c->d_good_bits.reserve(((n_occ + 63) / 64 + 1) * 8));
     cudaStream_t st = c->stream;
-    DMF_CUDA(cudaMemcpyAsync(c->d_bricks.p, bricks.data(), nbricks * 8, cudaMemcpyHostToDevice, st));
-    DMF_CUDA(cudaMemcpyAsync(c->d_prefix.p, prefix.data(), nbricks * 4, cudaMemcpyHostToDevice, st));
+    DMF_CUDA(cudaMemcpyAsync(c->d_bricks.p, words.data(), nwords * 4, cudaMemcpyHostToDevice, st));
+    DMF_CUDA(cudaMemcpyAsync(c->d_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, st));
+    DMF_CUDA(cudaMemcpyAsync(c->d_macro.p, macro.data(), macro.size() * 4, cudaMemcpyHostToDevice, st));
+    DMF_CUDA(cudaMemcpyAsync(c->d_clearance.p, clearance.data(), clearance.size() * 4, cudaMemcpyHostToDevice, st));
     DMF_CUDA(cudaMemcpyAsync(c->d_rank2occ.p, rank2occ.data(), rank2occ.size() * 4, cudaMemcpyHostToDevice, st));
     if (n_occ) DMF_CUDA(cudaMemcpyAsync(c->d_occ_ids.p, c->h_occ.data(), n_occ * 8, cudaMemcpyHostToDevice, st));
     DMF_CUDA(cudaMemcpyAsync(c->d_noff.p, c->h_noff.data(), (n_occ + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -103,7 +167,7 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
     DMF_CUDA(cudaMemsetAsync(c->d_good_bits.p, 0, ((n_occ + 63) / 64 + 1) * 8, st));
     DMF_TRY(fill_u32(c, st, c->d_first_view.p, std::max<size_t>(n_occ, 1), 0x7fffffffu));
     DMF_CUDA(cudaStreamSynchronize(st));   // host staging vectors die here
-    v.bricks = c->d_bricks.as<u64>(); v.prefix = c->d_prefix.as<unsigned>(); v.rank2occ = c->d_rank2occ.as<unsigned>();
+    v.bits = c->d_bricks.as<unsigned>(); v.prefix = c->d_prefix.as<unsigned>(); v.rank2occ = c->d_rank2occ.as<unsigned>(); v.macro = c->d_macro.as<unsigned>();
     v.noff = c->d_noff.as<unsigned>(); v.normals = c->d_normals.as<float>(); v.occ_ids = c->d_occ_ids.as<u64>();
     v.bytes = nullptr; v.n_occ = (int)n_occ;
     c->bytes_built = false;
@@ -131,7 +195,7 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
 int ensure_bytes(dmf_ctx* c, cudaStream_t st) {
     if (c->bytes_built) return 0;
     VolDev& v = c->vol;
-    size_t n = (size_t)v.dim[0] * v.dim[1] * v.dim[2];
+    size_t n = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
     DMF_TRY(c->d_bytes.reserve(n));
     k_expand_bytes<<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(v, c->d_bytes.as<unsigned char>());
     c->launches++;
@@ -149,20 +213,31 @@ int ensure_tables(dmf_ctx* c, int z0, int zdelta, int cstride, int rstride, cuda
     int S = (1000 - z0 + zdelta - 1) / zdelta;
     int Wc = (c->W + cstride - 1) / cstride, Hc = (c->H + rstride - 1) / rstride;
     DMF_TRY(c->d_xtab.reserve((size_t)S * Wc * 4)); DMF_TRY(c->d_ytab.reserve((size_t)S * Hc * 4)); DMF_TRY(c->d_ztab.reserve((size_t)S * 4));
+    DMF_TRY(c->d_dcx.reserve((size_t)Wc * 4)); DMF_TRY(c->d_dcy.reserve((size_t)Hc * 4));
     // the tables may still be in use by work queued on another stream of this context
     DMF_CUDA(cudaDeviceSynchronize());
-    k_build_tables<<<blocks_for((size_t)S * (Wc + Hc + 1), 256), 256, 0, st>>>(c->d_xtab.as<float>(), c->d_ytab.as<float>(), c->d_ztab.as<float>(),
+    k_build_tables<<<blocks_for((size_t)S * (Wc + Hc + 1), 256), 256, 0, st>>>(c->d_xtab.as<float>(), c->d_ytab.as<float>(), c->d_ztab.as<float>(), c->d_dcx.as<float>(), c->d_dcy.as<float>(),
         S, Wc, Hc, cstride, rstride, z0, zdelta, (double)c->K[0], (double)c->K[2], (double)c->K[4], (double)c->K[5]);
     c->launches++;
     DMF_CUDA(cudaGetLastError());
+    {
+        const double fx = c->K[0], cx = c->K[2], fy = c->K[4], cy = c->K[5];
+        c->dcx_max = (float)(std::max(std::fabs(0.0 - cx), std::fabs((double)(c->W - 1) - cx)) / std::fabs(fx) * 1.0001);
+        c->dcy_max = (float)(std::max(std::fabs(0.0 - cy), std::fabs((double)(c->H - 1) - cy)) / std::fabs(fy) * 1.0001);
+    }
     c->S = S; c->Wc = Wc; c->Hc = Hc; c->tkey = k; c->tables_valid = true;
     return 0;
 }
 
 template <int MODE>
-void launch_forward_fmt(const FwdArgs& a, int fmt, dim3 grid, cudaStream_t st) {
-    if (fmt == DMF_GRID_BYTE) k_forward<MODE, 1><<<grid, FWD_THREADS, 0, st>>>(a);
-    else k_forward<MODE, 0><<<grid, FWD_THREADS, 0, st>>>(a);
+void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, dim3 grid, cudaStream_t st) {
+    if (skip) {
+        if (fmt == DMF_GRID_BYTE) k_forward_skip<MODE, 1><<<grid, FWD_THREADS, 0, st>>>(a);
+        else k_forward_skip<MODE, 0><<<grid, FWD_THREADS, 0, st>>>(a);
+    } else {
+        if (fmt == DMF_GRID_BYTE) k_forward<MODE, 1><<<grid, FWD_THREADS, 0, st>>>(a);
+        else k_forward<MODE, 0><<<grid, FWD_THREADS, 0, st>>>(a);
+    }
 }
 
 struct FwdPlan { int z0, cstride, rstride; };
@@ -209,14 +284,17 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     a.first_key = first_key; a.ray_key = ray_key; a.ray_occ = ray_occ;
     a.first_view = c->d_first_view.as<int>(); a.good_bits = c->d_good_bits.as<unsigned>(); a.view_mark = c->d_view_mark.as<int>();
     a.counters = c->d_counters.as<u64>();
+    a.dcx = c->d_dcx.as<float>(); a.dcy = c->d_dcy.as<float>(); a.clearance = c->d_clearance.as<float>();
+    a.dcx_max = c->dcx_max; a.dcy_max = c->dcy_max;
+    const bool skip = !(p->flags & DMF_FWD_NO_SKIP);
     dim3 grid((c->Wc + FWD_TILE_W - 1) / FWD_TILE_W, (c->Hc + FWD_TILE_H - 1) / FWD_TILE_H, n_views);
     DMF_CUDA(cudaEventRecord(c->ev_h0, st));
     switch (p->mode) {
-        case 0: launch_forward_fmt<0>(a, p->grid_format, grid, st); break;
-        case 1: launch_forward_fmt<1>(a, p->grid_format, grid, st); break;
-        case 2: launch_forward_fmt<2>(a, p->grid_format, grid, st); break;
-        case 3: launch_forward_fmt<3>(a, p->grid_format, grid, st); break;
-        default: launch_forward_fmt<4>(a, p->grid_format, grid, st); break;
+        case 0: launch_forward_fmt<0>(a, p->grid_format, skip, grid, st); break;
+        case 1: launch_forward_fmt<1>(a, p->grid_format, skip, grid, st); break;
+        case 2: launch_forward_fmt<2>(a, p->grid_format, skip, grid, st); break;
+        case 3: launch_forward_fmt<3>(a, p->grid_format, skip, grid, st); break;
+        default: launch_forward_fmt<4>(a, p->grid_format, skip, grid, st); break;
     }
     DMF_CUDA(cudaEventRecord(c->ev_h1, st));
     c->hot_timed = true;
@@ -296,7 +374,7 @@ void dmf_destroy(dmf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&c->d_bricks, &c->d_prefix, &c->d_rank2occ, &c->d_bytes, &c->d_noff, &c->d_normals, &c->d_occ_ids, &c->d_centroid_hash,
+    DevBuf* bufs[] = {&c->d_bricks, &c->d_macro, &c->d_clearance, &c->d_dcx, &c->d_dcy, &c->d_prefix, &c->d_rank2occ, &c->d_bytes, &c->d_noff, &c->d_normals, &c->d_occ_ids, &c->d_centroid_hash,
                       &c->d_view_mark, &c->d_good_bits, &c->d_first_view, &c->d_axis[0], &c->d_axis[1], &c->d_axis[2], &c->d_xtab, &c->d_ytab, &c->d_ztab,
                       &c->d_poses[0], &c->d_poses[1], &c->d_inv_poses, &c->d_first_key, &c->d_ray_key, &c->d_ray_occ, &c->d_tmp_a, &c->d_tmp_b,
                       &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters};

@@ -10,35 +10,44 @@
 typedef unsigned long long u64;
 
 // HBM layout of a VoxelVolume (reference include/Volume.hpp:50-78):
-//   bricks   [nbx][nby][nbz] uint64   occupancy of a 4x4x4 voxel brick, bit = (lx<<4)|(ly<<2)|lz
-//   prefix   [nbx*nby*nbz]   uint32   number of occupied voxels in all earlier bricks (rank directory)
-//   rank2occ [n_occ]         uint32   rank (brick order) -> index into occupied_cells_
-//   bytes    [nx][ny][nz]    uint8    optional byte-per-voxel copy, z fastest (DMF_GRID_BYTE)
-//   noff/normals             CSR of Voxel::normals in occupied order
+//   bits     uint32 words of a linear bit grid over the PADDED index space [0,dim_x] x [0,dim_y] x [0,dim_z]
+//            (pdim = dim + 1 per axis, z fastest like voxels_[x][y][z]); bit index = (x*pdim_y + y)*pdim_z + z.
+//            The padding plane is always empty: a probe whose quotient rounds up to exactly `dim` (the reference
+//            reads out of bounds there) lands on it, so the forward march needs no index range check.
+//   prefix   uint32 per 8 words (256 bits): number of occupied voxels before that block (rank directory)
+//   rank2occ [n_occ] rank (linear order) -> index into occupied_cells_
+//   bytes    optional byte-per-voxel copy over the same padded index space (DMF_GRID_BYTE)
+//   macro    1 bit per 8x8x8-voxel macro cell: "contains an occupied voxel" (empty-space skipping)
+//   noff/normals  CSR of Voxel::normals in occupied order
 struct VolDev {
-    const u64* __restrict__ bricks;
+    const unsigned* __restrict__ bits;
     const unsigned* __restrict__ prefix;
     const unsigned* __restrict__ rank2occ;
     const unsigned char* __restrict__ bytes;
+    const unsigned* __restrict__ macro;
     const unsigned* __restrict__ noff;
     const float* __restrict__ normals;
     const u64* __restrict__ occ_ids;
     int n_occ;
     int dim[3];      // xdim_, ydim_, zdim_
-    int nb[3];       // bricks per axis
+    int pdim[3];     // dim + 1
+    int mdim[3];     // macro cells per axis = ceil(pdim / 8)
     double vmin[3];  // xmin_, ymin_, zmin_
     double delta[3]; // xdelta_, ydelta_, zdelta_
     double inv[3];   // RN(1/delta)
     double c0[3];    // RN(-vmin*inv)
     double half[3];  // delta/2.0
-    double eps[3];   // |frac| below which the fast quotient cannot be trusted (0 => axis is exact)
+    double eps[3];   // |frac| below which the double fast quotient cannot be trusted (0 => axis is exact)
+    float inv32[3];  // (float)inv
+    float c32[3];    // (float)c0
+    float err32[3];  // bound on |fmaf(p,inv32,c32) - reference quotient|  (0 => the float quotient is exact)
     float lo[3];     // largest float <= vmin   (validPoints: x<=xmin_  <=>  !(x > lo))
     float hi[3];     // smallest float >= vmax  (validPoints: x>=xmax_  <=>  !(x < hi))
 };
 
-// floor(((double)p - vmin) / delta) exactly as VoxelVolume::getVoxel (Volume.hpp:150-156) computes it.
-// Fast path: q' = fma(p, 1/delta, -vmin/delta) differs from the reference quotient by < eps, so the floors agree
-// unless q' is within eps of an integer; then (and only then) the reference's subtract + IEEE divide is executed.
+// floor(((double)p - vmin) / delta) exactly as VoxelVolume::getVoxel (Volume.hpp:150-156) computes it, in double.
+// q' = fma(p, 1/delta, -vmin/delta) differs from the reference quotient by < eps, so the floors agree unless q' is
+// within eps of an integer; then (and only then) the reference's subtract + IEEE divide is executed.
 // The floor itself uses the 1.5*2^52 shifter so no F2I/I2F conversions are needed.
 __device__ __forceinline__ int voxel_index(float p, double vmin, double delta, double inv, double c0, double eps, unsigned& n_exact) {
     const double kShift = 6755399441055744.0;  // 1.5 * 2^52
@@ -54,6 +63,18 @@ __device__ __forceinline__ int voxel_index(float p, double vmin, double delta, d
     return i - (f < 0.0 ? 1 : 0);
 }
 
+// Float filter for the same index: q32 = fmaf(p, inv32, c32) is within err of the reference quotient (bound derived
+// in DESIGN.md "voxel index filter", computed on the host per axis), so floor(q32) is the reference index whenever q32
+// is at least err away from every integer.  Otherwise `unsafe` is raised and the caller redoes the probe in double.
+__device__ __forceinline__ int voxel_index_f32(float p, float inv, float c, float err, bool& unsafe) {
+    const float kShift = 12582912.0f;          // 1.5 * 2^23
+    const float q = fmaf(p, inv, c);
+    const float s = __fadd_rn(q, kShift);
+    const float f = __fsub_rn(q, __fsub_rn(s, kShift));   // q - rint(q)
+    unsafe = unsafe || (fabsf(f) < err);
+    return (__float_as_int(s) - 0x4B400000) - (f < 0.0f ? 1 : 0);
+}
+
 __device__ __forceinline__ bool in_bounds(const VolDev& v, float x, float y, float z) {
     return x > v.lo[0] && x < v.hi[0] && y > v.lo[1] && y < v.hi[1] && z > v.lo[2] && z < v.hi[2];
 }
@@ -61,28 +82,30 @@ __device__ __forceinline__ bool in_bounds(const VolDev& v, float x, float y, flo
 __device__ __forceinline__ bool coords_valid(const VolDev& v, int x, int y, int z) {
     return (unsigned)x < (unsigned)v.dim[0] && (unsigned)y < (unsigned)v.dim[1] && (unsigned)z < (unsigned)v.dim[2];
 }
-
-__device__ __forceinline__ size_t brick_index(const VolDev& v, int x, int y, int z) {
-    return ((size_t)(x >> 2) * v.nb[1] + (y >> 2)) * v.nb[2] + (z >> 2);
+// inside the padded index space (what the grids can be addressed with)
+__device__ __forceinline__ bool coords_padded(const VolDev& v, int x, int y, int z) {
+    return (unsigned)x < (unsigned)v.pdim[0] && (unsigned)y < (unsigned)v.pdim[1] && (unsigned)z < (unsigned)v.pdim[2];
 }
-__device__ __forceinline__ unsigned brick_bit(int x, int y, int z) { return ((x & 3) << 4) | ((y & 3) << 2) | (z & 3); }
 
+__device__ __forceinline__ unsigned linear_index(const VolDev& v, int x, int y, int z) {   // < 2^31 for dims <= 1024
+    return ((unsigned)x * (unsigned)v.pdim[1] + (unsigned)y) * (unsigned)v.pdim[2] + (unsigned)z;
+}
+
+// FMT 0: bit grid, 1: byte grid.  (x,y,z) must be inside the padded index space.
 template <int FMT>
 __device__ __forceinline__ bool occupied(const VolDev& v, int x, int y, int z) {
-    if (FMT == 0) {
-        u64 w = __ldg(v.bricks + brick_index(v, x, y, z));
-        return (w >> brick_bit(x, y, z)) & 1ull;
-    } else {
-        return __ldg(v.bytes + ((size_t)x * v.dim[1] + y) * v.dim[2] + z) != 0;
-    }
+    const unsigned idx = linear_index(v, x, y, z);
+    if (FMT == 0) return (__ldg(v.bits + (idx >> 5)) >> (idx & 31)) & 1u;
+    return __ldg(v.bytes + idx) != 0;
 }
 
 // index into occupied_cells_ of an occupied voxel
 __device__ __forceinline__ int occupied_ordinal(const VolDev& v, int x, int y, int z) {
-    size_t b = brick_index(v, x, y, z);
-    u64 w = __ldg(v.bricks + b);
-    unsigned bit = brick_bit(x, y, z);
-    unsigned rank = __ldg(v.prefix + b) + __popcll(w & ((1ull << bit) - 1ull));
+    const unsigned idx = linear_index(v, x, y, z);
+    const unsigned w = idx >> 5;
+    unsigned rank = __ldg(v.prefix + (w >> 3));
+    for (unsigned j = w & ~7u; j < w; j++) rank += __popc(__ldg(v.bits + j));
+    rank += __popc(__ldg(v.bits + w) & ((1u << (idx & 31)) - 1u));
     return (int)__ldg(v.rank2occ + rank);
 }
 
@@ -113,7 +136,7 @@ __device__ __forceinline__ void view_direction(const VolDev& v, float px, float 
 
 // Parameters of the "angle in [0,90] degrees" test  degree(acos(n.v)) in [k_AngleMin,k_AngleMax]
 // (RayTracingEngine.hpp:211-212, :362-364, :428-430; CommonUtilities.hpp:17).  The host bisects its own libm's
-// acosf once (dmf_b200_host.cpp): the test is true  <=>  dot_min <= d <= 1.  [band_lo, band_hi) is the range of d
+// acosf once (dmf_host.cuh): the test is true  <=>  dot_min <= d <= 1.  [band_lo, band_hi) is the range of d
 // where the host libm was observed non-monotonic (empty if band_lo >= band_hi); hits inside it are counted as ties.
 struct AngleTest { float dot_min, band_lo, band_hi; };
 

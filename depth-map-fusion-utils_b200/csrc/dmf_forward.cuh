@@ -18,6 +18,12 @@ struct FwdArgs {
     const float* __restrict__ ytab;    // [S][Hc]  (float)(z_k*((double)r-cy)/fy)
     const float* __restrict__ ztab;    // [S]      (float)z_k,  z_k = (z0 + k*zdelta)*0.001
     int S, Wc, Hc, W, H, cstride, rstride, z0, zdelta;
+    // empty-space skipping (k_forward_skip): approximate ray slopes and the macro-cell clearance field
+    const float* __restrict__ dcx;     // [Wc] (float)((c-cx)/fx)   -- approximate, only steers the skipping
+    const float* __restrict__ dcy;     // [Hc] (float)((r-cy)/fy)
+    const float* __restrict__ clearance; // [mdim_x][mdim_y][mdim_z] voxels that can be crossed (L-inf) from anywhere in the cell
+                                       //  while provably staying in empty, in-bounds macro cells (0 = evaluate exactly)
+    float dcx_max, dcy_max;            // max |dcx|, |dcy| (for the per-view error bound)
     // outputs (may be null)
     int* depth;                        // [n_views][H][W]
     float* points;                     // [n_views][H][W][3]
@@ -38,9 +44,13 @@ struct FwdArgs {
 };
 
 // xtab/ytab/ztab: exact IEEE double mul/div then round to float, as the tuple<float,float,float> return does.
-__global__ void k_build_tables(float* xtab, float* ytab, float* ztab, int S, int Wc, int Hc, int cstride, int rstride,
+__global__ void k_build_tables(float* xtab, float* ytab, float* ztab, float* dcx, float* dcy, int S, int Wc, int Hc, int cstride, int rstride,
                                int z0, int zdelta, double fx, double cx, double fy, double cy) {
     int per = Wc + Hc + 1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < Wc + Hc; j += gridDim.x * blockDim.x) {
+        if (j < Wc) dcx[j] = (float)(((double)(j * cstride) - cx) / fx);
+        else dcy[j - Wc] = (float)(((double)((j - Wc) * rstride) - cy) / fy);
+    }
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)S * per; i += (long long)gridDim.x * blockDim.x) {
         int k = (int)(i / per), j = (int)(i % per);
         double z = __dmul_rn((double)(z0 + k * zdelta), 0.001);
@@ -57,84 +67,13 @@ __global__ void k_build_tables(float* xtab, float* ytab, float* ztab, int S, int
     }
 }
 
-constexpr int FWD_THREADS = 256;      // 8 warps: 4 across x 2 down, each warp an 8x4 pixel tile
-constexpr int FWD_TILE_W = 32, FWD_TILE_H = 8;
-constexpr int FWD_CHUNK = 32;         // z-steps staged in shared memory per round
-
-// MODE: DMF_MODE_*, FMT: DMF_GRID_*
-template <int MODE, int FMT>
-__global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
-    __shared__ float sx[FWD_CHUNK][FWD_TILE_W];
-    __shared__ float sy[FWD_CHUNK][FWD_TILE_H];
-    __shared__ float sz[FWD_CHUNK][4];   // m02*z, m12*z, m22*z
-    __shared__ unsigned long long s_cnt[4];
-
-    const int view = blockIdx.z;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lc = (warp & 3) * 8 + (lane & 7);   // column within the tile
-    const int lr = (warp >> 2) * 4 + (lane >> 3); // row within the tile
-    const int ci = blockIdx.x * FWD_TILE_W + lc;  // lattice column
-    const int ri = blockIdx.y * FWD_TILE_H + lr;  // lattice row
-    const bool active = ci < a.Wc && ri < a.Hc;
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
-
-    const float* P = a.poses + 12 * (size_t)view;
-    const float m00 = __ldg(P + 0), m01 = __ldg(P + 1), m02 = __ldg(P + 2), m03 = __ldg(P + 3);
-    const float m10 = __ldg(P + 4), m11 = __ldg(P + 5), m12 = __ldg(P + 6), m13 = __ldg(P + 7);
-    const float m20 = __ldg(P + 8), m21 = __ldg(P + 9), m22 = __ldg(P + 10), m23 = __ldg(P + 11);
+// Per-ray epilogue shared by k_forward and k_forward_skip: outputs, visibility, marks, discovery keys, counters.
+template <int MODE>
+__device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long long* s_cnt, int view, int ci, int ri, bool active, int hit_k,
+                                                 int hx, int hy, int hz, float hpx, float hpy, float hpz, float m03, float m13, float m23,
+                                                 unsigned n_samples, unsigned n_inb, unsigned n_exact, unsigned n_f64, unsigned n_skip) {
     const VolDev& v = a.vol;
-
-    bool done = !active;
-    int hit_k = -1, hx = 0, hy = 0, hz = 0;
-    float hpx = 0.f, hpy = 0.f, hpz = 0.f;
-    unsigned n_samples = 0, n_inb = 0, n_exact = 0;
-
-    for (int k0 = 0; k0 < a.S; k0 += FWD_CHUNK) {
-        bool stop = done;
-        if (MODE == 4) {   // rayTraceAndGetMinimum returns at the first hit plane: later planes cannot matter
-            int cur = *((volatile int*)(a.min_depth + view));
-            stop = stop || (a.z0 + k0 * a.zdelta > cur);
-        }
-        if (__syncthreads_and(stop)) break;   // also fences the previous round's shared-memory reads
-        const int nk = min(FWD_CHUNK, a.S - k0);
-        for (int i = threadIdx.x; i < FWD_CHUNK * FWD_TILE_W; i += FWD_THREADS) {
-            int kk = i / FWD_TILE_W, cc = i % FWD_TILE_W, col = blockIdx.x * FWD_TILE_W + cc;
-            sx[kk][cc] = (kk < nk && col < a.Wc) ? __ldg(a.xtab + (size_t)(k0 + kk) * a.Wc + col) : 0.f;
-        }
-        {
-            int i = threadIdx.x;   // FWD_CHUNK*FWD_TILE_H == FWD_THREADS
-            int kk = i / FWD_TILE_H, rr = i % FWD_TILE_H, row = blockIdx.y * FWD_TILE_H + rr;
-            sy[kk][rr] = (kk < nk && row < a.Hc) ? __ldg(a.ytab + (size_t)(k0 + kk) * a.Hc + row) : 0.f;
-        }
-        if (threadIdx.x < FWD_CHUNK) {
-            float z = (threadIdx.x < nk) ? __ldg(a.ztab + k0 + threadIdx.x) : 0.f;
-            sz[threadIdx.x][0] = __fmul_rn(m02, z); sz[threadIdx.x][1] = __fmul_rn(m12, z); sz[threadIdx.x][2] = __fmul_rn(m22, z);
-        }
-        __syncthreads();
-        if (!done) {
-            for (int kk = 0; kk < nk; kk++) {
-                const float xf = sx[kk][lc], yf = sy[kk][lr];
-                // transformPoints (Camera.hpp:39-45), rule E1
-                const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, xf), __fmul_rn(m01, yf)), sz[kk][0]), m03);
-                const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, xf), __fmul_rn(m11, yf)), sz[kk][1]), m13);
-                const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, xf), __fmul_rn(m21, yf)), sz[kk][2]), m23);
-                n_samples++;
-                if (!in_bounds(v, px, py, pz)) continue;          // validPoints: skip, do not terminate
-                n_inb++;
-                const int ix = voxel_index(px, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
-                const int iy = voxel_index(py, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
-                const int iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
-                if (!coords_valid(v, ix, iy, iz)) continue;       // the reference reads out of bounds here (UB): empty
-                if (occupied<FMT>(v, ix, iy, iz)) {
-                    hit_k = k0 + kk; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz;
-                    done = true;
-                    break;
-                }
-            }
-        }
-    }
-
-    // ---- per-ray epilogue ------------------------------------------------------------------------------
+    const int lane = threadIdx.x & 31;
     const bool hit = hit_k >= 0;
     const int z_depth = a.z0 + hit_k * a.zdelta;
     if (active) {
@@ -187,18 +126,243 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
     }
 
     // ---- counters: warp reduce -> shared -> 4 global atomics per block ------------------------------
-    unsigned long long c0 = n_samples, c1 = n_inb, c2 = hit ? 1u : 0u, c3 = n_exact, c5 = ties;
+    unsigned long long c0 = n_samples, c1 = n_inb, c2 = hit ? 1u : 0u, c3 = n_exact, c5 = ties, c8 = n_f64, c9 = n_skip;
     for (int o = 16; o; o >>= 1) {
         c0 += __shfl_down_sync(0xffffffffu, c0, o); c1 += __shfl_down_sync(0xffffffffu, c1, o);
         c2 += __shfl_down_sync(0xffffffffu, c2, o); c3 += __shfl_down_sync(0xffffffffu, c3, o);
-        c5 += __shfl_down_sync(0xffffffffu, c5, o);
+        c5 += __shfl_down_sync(0xffffffffu, c5, o); c8 += __shfl_down_sync(0xffffffffu, c8, o); c9 += __shfl_down_sync(0xffffffffu, c9, o);
     }
     if (lane == 0) {
         atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); atomicAdd(&s_cnt[2], c2); atomicAdd(&s_cnt[3], c3);
         if (c5) atomicAdd(a.counters + 5, c5);
+        if (c8) atomicAdd(a.counters + 8, c8);
+        if (c9) atomicAdd(a.counters + 9, c9);
     }
     __syncthreads();
     if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(a.counters + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+
+constexpr int FWD_THREADS = 256;      // 8 warps: 4 across x 2 down, each warp an 8x4 pixel tile
+constexpr int FWD_TILE_W = 32, FWD_TILE_H = 8;
+constexpr int FWD_CHUNK = 32;         // z-steps staged in shared memory per round
+
+// MODE: DMF_MODE_*, FMT: DMF_GRID_*
+template <int MODE, int FMT>
+__global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
+    __shared__ float sx[FWD_CHUNK][FWD_TILE_W];
+    __shared__ float sy[FWD_CHUNK][FWD_TILE_H];
+    __shared__ __align__(16) float sz[FWD_CHUNK][4];   // m02*z, m12*z, m22*z
+    __shared__ unsigned long long s_cnt[4];
+
+    const int view = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lc = (warp & 3) * 8 + (lane & 7);   // column within the tile
+    const int lr = (warp >> 2) * 4 + (lane >> 3); // row within the tile
+    const int ci = blockIdx.x * FWD_TILE_W + lc;  // lattice column
+    const int ri = blockIdx.y * FWD_TILE_H + lr;  // lattice row
+    const bool active = ci < a.Wc && ri < a.Hc;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
+
+    const float* P = a.poses + 12 * (size_t)view;
+    const float m00 = __ldg(P + 0), m01 = __ldg(P + 1), m02 = __ldg(P + 2), m03 = __ldg(P + 3);
+    const float m10 = __ldg(P + 4), m11 = __ldg(P + 5), m12 = __ldg(P + 6), m13 = __ldg(P + 7);
+    const float m20 = __ldg(P + 8), m21 = __ldg(P + 9), m22 = __ldg(P + 10), m23 = __ldg(P + 11);
+    const VolDev& v = a.vol;
+
+    // loop-invariant copies of the per-axis constants (kept in registers / uniform registers by the compiler)
+    const float lo0 = v.lo[0], lo1 = v.lo[1], lo2 = v.lo[2], hi0 = v.hi[0], hi1 = v.hi[1], hi2 = v.hi[2];
+    const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2], cc0 = v.c32[0], cc1 = v.c32[1], cc2 = v.c32[2];
+    const float er0 = v.err32[0], er1 = v.err32[1], er2 = v.err32[2];
+    const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
+    const unsigned* __restrict__ gbits = v.bits;
+    const unsigned char* __restrict__ gbytes = v.bytes;
+
+    bool done = !active;
+    int hit_k = -1, hx = 0, hy = 0, hz = 0;
+    float hpx = 0.f, hpy = 0.f, hpz = 0.f;
+    unsigned n_samples = 0, n_inb = 0, n_exact = 0, n_f64 = 0;
+
+    for (int k0 = 0; k0 < a.S; k0 += FWD_CHUNK) {
+        bool stop = done;
+        if (MODE == 4) {   // rayTraceAndGetMinimum returns at the first hit plane: later planes cannot matter
+            int cur = *((volatile int*)(a.min_depth + view));
+            stop = stop || (a.z0 + k0 * a.zdelta > cur);
+        }
+        if (__syncthreads_and(stop)) break;   // also fences the previous round's shared-memory reads
+        const int nk = min(FWD_CHUNK, a.S - k0);
+        for (int i = threadIdx.x; i < FWD_CHUNK * FWD_TILE_W; i += FWD_THREADS) {
+            int kk = i / FWD_TILE_W, cc = i % FWD_TILE_W, col = blockIdx.x * FWD_TILE_W + cc;
+            sx[kk][cc] = (kk < nk && col < a.Wc) ? __ldg(a.xtab + (size_t)(k0 + kk) * a.Wc + col) : 0.f;
+        }
+        {
+            int i = threadIdx.x;   // FWD_CHUNK*FWD_TILE_H == FWD_THREADS
+            int kk = i / FWD_TILE_H, rr = i % FWD_TILE_H, row = blockIdx.y * FWD_TILE_H + rr;
+            sy[kk][rr] = (kk < nk && row < a.Hc) ? __ldg(a.ytab + (size_t)(k0 + kk) * a.Hc + row) : 0.f;
+        }
+        if (threadIdx.x < FWD_CHUNK) {
+            float z = (threadIdx.x < nk) ? __ldg(a.ztab + k0 + threadIdx.x) : 0.f;
+            sz[threadIdx.x][0] = __fmul_rn(m02, z); sz[threadIdx.x][1] = __fmul_rn(m12, z); sz[threadIdx.x][2] = __fmul_rn(m22, z);
+        }
+        __syncthreads();
+        if (!done) {
+            const float* psx = &sx[0][lc];
+            const float* psy = &sy[0][lr];
+            const float4* psz = reinterpret_cast<const float4*>(&sz[0][0]);
+            int kk = 0;
+#pragma unroll 1
+            for (; kk < nk; kk++, psx += FWD_TILE_W, psy += FWD_TILE_H, psz++) {
+                const float xf = *psx, yf = *psy;
+                const float4 zt = *psz;
+                // transformPoints (Camera.hpp:39-45), rule E1: ((m0*x + m1*y) + m2*z) + m3 with separate roundings
+                const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, xf), __fmul_rn(m01, yf)), zt.x), m03);
+                const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, xf), __fmul_rn(m11, yf)), zt.y), m13);
+                const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, xf), __fmul_rn(m21, yf)), zt.z), m23);
+                // validPoints (Volume.hpp:230-233): outside => skip this sample, the ray goes on
+                if (!(px > lo0 && px < hi0 && py > lo1 && py < hi1 && pz > lo2 && pz < hi2)) continue;
+                n_inb++;
+                // getVoxel (Volume.hpp:150-156): float filter, exact double path only near an integer quotient
+                bool unsafe = false;
+                int ix = voxel_index_f32(px, in0, cc0, er0, unsafe);
+                int iy = voxel_index_f32(py, in1, cc1, er1, unsafe);
+                int iz = voxel_index_f32(pz, in2, cc2, er2, unsafe);
+                if (unsafe) {
+                    n_f64++;
+                    ix = voxel_index(px, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+                    iy = voxel_index(py, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+                    iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+                }
+                // voxels_[xid][yid][zid] != nullptr: indices are in [0,dim] here, the padded grid covers index == dim
+                const unsigned idx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+                const bool occ_here = FMT == 0 ? ((__ldg(gbits + (idx >> 5)) >> (idx & 31)) & 1u) != 0u : __ldg(gbytes + idx) != 0;
+                if (occ_here) {
+                    hit_k = k0 + kk; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz;
+                    done = true;
+                    kk++;
+                    break;
+                }
+            }
+            n_samples += (unsigned)kk;
+        }
+    }
+
+    forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23, n_samples, n_inb, n_exact, n_f64, 0u);
+}
+
+// ---- K1 with empty-space skipping -----------------------------------------------------------------------------
+// Same results as k_forward, probe for probe.  Each ray's sample positions lie within eps_q (voxel units, bounded
+// below) of the straight line  Q(k) = QA + k*QB  (voxel units), so:
+//   * vol.clearance[cell] = C > 0 means: from ANY point of that 8^3-voxel macro cell one can move C voxels (L-inf) and
+//     still be in macro cells that are empty and entirely inside the volume (Chebyshev distance field, built at upload,
+//     0.25 voxel already subtracted).  Hence the n = floor(C / max|QB|) next samples, and the current one, are
+//     in-bounds misses: they are counted (n_inb) and skipped without being evaluated.
+//   * wherever the clearance is 0 (next to an occupied macro cell, next to the volume boundary, outside it) the
+//     sample is evaluated exactly as in k_forward.
+// Error budget: |float sample - line| <= eps_p = 16*2^-24 * (|m0|X + |m1|Y + |m2|Z + |m3|) per axis (5 roundings of the
+// reference evaluation + <= 8 of the line's own float evaluation, doubled), eps_q = eps_p/delta.  A view whose eps_q
+// exceeds 0.1 voxel on any axis does not skip at all (skip_ok = false).  2*eps_q <= 0.2 < the 0.25 voxel margin.
+template <int MODE, int FMT>
+__global__ void __launch_bounds__(FWD_THREADS) k_forward_skip(const FwdArgs a) {
+    __shared__ unsigned long long s_cnt[4];
+    const int view = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * FWD_TILE_W + (warp & 3) * 8 + (lane & 7);
+    const int ri = blockIdx.y * FWD_TILE_H + (warp >> 2) * 4 + (lane >> 3);
+    const bool active = ci < a.Wc && ri < a.Hc;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    const float* P = a.poses + 12 * (size_t)view;
+    const float m00 = __ldg(P + 0), m01 = __ldg(P + 1), m02 = __ldg(P + 2), m03 = __ldg(P + 3);
+    const float m10 = __ldg(P + 4), m11 = __ldg(P + 5), m12 = __ldg(P + 6), m13 = __ldg(P + 7);
+    const float m20 = __ldg(P + 8), m21 = __ldg(P + 9), m22 = __ldg(P + 10), m23 = __ldg(P + 11);
+    const VolDev& v = a.vol;
+    const float lo0 = v.lo[0], lo1 = v.lo[1], lo2 = v.lo[2], hi0 = v.hi[0], hi1 = v.hi[1], hi2 = v.hi[2];
+    const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2], cc0 = v.c32[0], cc1 = v.c32[1], cc2 = v.c32[2];
+    const float er0 = v.err32[0], er1 = v.err32[1], er2 = v.err32[2];
+    const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
+    const unsigned mdx = (unsigned)v.mdim[0], mdy = (unsigned)v.mdim[1], mdz = (unsigned)v.mdim[2];
+    const unsigned* __restrict__ gbits = v.bits;
+    const unsigned char* __restrict__ gbytes = v.bytes;
+    const float* __restrict__ clr = a.clearance;
+
+    // the ray as a line in voxel units (approximate; only steers skipping)
+    const int cic = active ? ci : 0, ric = active ? ri : 0;
+    const float dcx = __ldg(a.dcx + cic), dcy = __ldg(a.dcy + ric);
+    const float g0 = fmaf(m00, dcx, fmaf(m01, dcy, m02)), g1 = fmaf(m10, dcx, fmaf(m11, dcy, m12)), g2 = fmaf(m20, dcx, fmaf(m21, dcy, m22));
+    const float z0m = (float)a.z0 * 0.001f, zdm = (float)a.zdelta * 0.001f;
+    const float qa0 = fmaf(fmaf(z0m, g0, m03), in0, cc0), qa1 = fmaf(fmaf(z0m, g1, m13), in1, cc1), qa2 = fmaf(fmaf(z0m, g2, m23), in2, cc2);
+    const float qb0 = zdm * g0 * in0, qb1 = zdm * g1 * in1, qb2 = zdm * g2 * in2;
+    const float qbmax = fmaxf(fabsf(qb0), fmaxf(fabsf(qb1), fabsf(qb2)));
+    const float rq = 1.0f / fmaxf(qbmax, 1e-6f);
+    // per-view error bound in voxel units (uniform over the block)
+    const float kEps = 9.5367431640625e-07f;   // 16 * 2^-24
+    const float e0 = kEps * (fabsf(m00) * a.dcx_max + fabsf(m01) * a.dcy_max + fabsf(m02) + fabsf(m03) + fabsf((float)v.vmin[0])) * fabsf(in0);
+    const float e1 = kEps * (fabsf(m10) * a.dcx_max + fabsf(m11) * a.dcy_max + fabsf(m12) + fabsf(m13) + fabsf((float)v.vmin[1])) * fabsf(in1);
+    const float e2 = kEps * (fabsf(m20) * a.dcx_max + fabsf(m21) * a.dcy_max + fabsf(m22) + fabsf(m23) + fabsf((float)v.vmin[2])) * fabsf(in2);
+    const bool skip_ok = clr != nullptr && fmaxf(e0, fmaxf(e1, e2)) <= 0.1f;   // NaN poses compare false: no skipping
+
+    int hit_k = -1, hx = 0, hy = 0, hz = 0;
+    float hpx = 0.f, hpy = 0.f, hpz = 0.f;
+    unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
+    int k = 0;
+    float kf = 0.0f;
+    const int S = a.S;
+    const float* __restrict__ xt = a.xtab + cic;
+    const float* __restrict__ yt = a.ytab + ric;
+    const float* __restrict__ zt = a.ztab;
+    const float kM = 12582912.0f;
+    unsigned iter = 0;
+    if (active) {
+        while (k < S) {
+            if (MODE == 4 && (iter++ & 15u) == 0u) {   // rayTraceAndGetMinimum: planes behind the current minimum cannot matter
+                const int cur = *((volatile int*)(a.min_depth + view));
+                if (a.z0 + k * a.zdelta > cur) break;
+            }
+            if (skip_ok) {
+                // macro cell of the line point (floor(q/8) through the round-down shifter; no F2I)
+                const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
+                const unsigned mx = (unsigned)(__float_as_int(__fadd_rd(q0 * 0.125f, kM)) - 0x4B400000);
+                const unsigned my = (unsigned)(__float_as_int(__fadd_rd(q1 * 0.125f, kM)) - 0x4B400000);
+                const unsigned mz = (unsigned)(__float_as_int(__fadd_rd(q2 * 0.125f, kM)) - 0x4B400000);
+                if (mx < mdx && my < mdy && mz < mdz) {
+                    const float c = __ldg(clr + ((mx * mdy + my) * mdz + mz));
+                    if (c > 0.0f) {
+                        int n = min(__float2int_rz(c * rq), S - k - 1);   // samples k .. k+n are provably in-bounds misses
+                        n_skip += (unsigned)(n + 1); n_inb += (unsigned)(n + 1);
+                        k += n + 1; kf += (float)(n + 1);
+                        continue;
+                    }
+                }
+            }
+            // ---- exact evaluation of sample k (identical to k_forward) ----
+            const float xf = __ldg(xt + (size_t)k * a.Wc), yf = __ldg(yt + (size_t)k * a.Hc), zf = __ldg(zt + k);
+            const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, xf), __fmul_rn(m01, yf)), __fmul_rn(m02, zf)), m03);
+            const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, xf), __fmul_rn(m11, yf)), __fmul_rn(m12, zf)), m13);
+            const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, xf), __fmul_rn(m21, yf)), __fmul_rn(m22, zf)), m23);
+            k++; kf += 1.0f;
+            if (!(px > lo0 && px < hi0 && py > lo1 && py < hi1 && pz > lo2 && pz < hi2)) continue;
+            n_inb++;
+            bool unsafe = false;
+            int ix = voxel_index_f32(px, in0, cc0, er0, unsafe);
+            int iy = voxel_index_f32(py, in1, cc1, er1, unsafe);
+            int iz = voxel_index_f32(pz, in2, cc2, er2, unsafe);
+            if (unsafe) {
+                n_f64++;
+                ix = voxel_index(px, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+                iy = voxel_index(py, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+                iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+            }
+            const unsigned idx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+            const bool occ_here = FMT == 0 ? ((__ldg(gbits + (idx >> 5)) >> (idx & 31)) & 1u) != 0u : __ldg(gbytes + idx) != 0;
+            if (occ_here) {
+                hit_k = k - 1; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz;
+                break;
+            }
+        }
+    }
+    const unsigned n_samples = active ? (unsigned)min(k, S) : 0u;
+    forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23, n_samples, n_inb, n_exact, n_f64, n_skip);
 }
 
 // CLASSIFY: `if(voxel->view==0) voxel->view=view` over a batch of views in call order (:354-355)

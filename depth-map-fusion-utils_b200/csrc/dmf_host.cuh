@@ -133,14 +133,14 @@ struct dmf_ctx {
     VolDev vol{};
     double bounds[6]; double voxel_size = 0; size_t n_occ = 0, n_normals = 0;
     std::vector<uint64_t> h_occ; std::vector<uint32_t> h_noff; std::vector<float> h_normals;
-    dmf::DevBuf d_bricks, d_prefix, d_rank2occ, d_bytes, d_noff, d_normals, d_occ_ids, d_centroid_hash;
+    dmf::DevBuf d_bricks /* bit grid words */, d_macro, d_prefix, d_rank2occ, d_bytes, d_noff, d_normals, d_occ_ids, d_centroid_hash;
     bool bytes_built = false;
     dmf::DevBuf d_view_mark, d_good_bits, d_first_view;
     // reverseRayTrace / rayTraceVolume float-accumulated axes
     dmf::DevBuf d_axis[3]; int n_axis[3] = {0, 0, 0};
     // projectPoint tables
     bool tables_valid = false; dmf::TableKey tkey{};
-    dmf::DevBuf d_xtab, d_ytab, d_ztab; int S = 0, Wc = 0, Hc = 0;
+    dmf::DevBuf d_xtab, d_ytab, d_ztab, d_dcx, d_dcy, d_clearance; int S = 0, Wc = 0, Hc = 0; float dcx_max = 0, dcy_max = 0;
     // scratch
     dmf::DevBuf d_poses[2], d_inv_poses, d_out[2][8], d_first_key, d_ray_key, d_ray_occ, d_tmp_a, d_tmp_b, d_out_occ, d_n_ids, d_offsets, d_ids;
     dmf::DevBuf d_misc[4];

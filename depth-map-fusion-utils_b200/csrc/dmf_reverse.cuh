@@ -39,12 +39,9 @@ __global__ void k_centroid_hash(const VolDev v, u64* out) {
 }
 
 __global__ void k_expand_bytes(const VolDev v, unsigned char* bytes) {
-    const size_t n = (size_t)v.dim[0] * v.dim[1] * v.dim[2];
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        int z = (int)(i % v.dim[2]); size_t t = i / v.dim[2];
-        int y = (int)(t % v.dim[1]); int x = (int)(t / v.dim[1]);
-        bytes[i] = occupied<0>(v, x, y, z) ? 1 : 0;
-    }
+    const size_t n = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];   // same padded linear index space as the bit grid
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        bytes[i] = (unsigned char)((__ldg(v.bits + (i >> 5)) >> (i & 31)) & 1u);
 }
 
 // Eigen::Affine3f::inverse() (rule E5 of oracle/dmf_oracle.hpp): cofactor inverse * (1/det), translation = -(Linv*t)

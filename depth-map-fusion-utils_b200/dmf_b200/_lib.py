@@ -17,7 +17,7 @@ class DmfError(RuntimeError):
 
 
 class ForwardParams(C.Structure):
-    _fields_ = [("mode", C.c_int), ("zdelta", C.c_int), ("sparse", C.c_int), ("view_id0", C.c_int), ("grid_format", C.c_int)]
+    _fields_ = [("mode", C.c_int), ("zdelta", C.c_int), ("sparse", C.c_int), ("view_id0", C.c_int), ("grid_format", C.c_int), ("flags", C.c_int)]
 
 
 class ForwardOut(C.Structure):
@@ -71,7 +71,7 @@ SYMBOLS = {
     "dmf_synchronize": (C.c_int, [vp]),
 }
 
-COUNTER_NAMES = ("samples", "inbounds", "hits", "exact_div", "oob", "acos_ties", "launches", "runaway")
+COUNTER_NAMES = ("samples", "inbounds", "hits", "exact_div", "oob", "acos_ties", "launches", "runaway", "f64_path", "skipped", "rsv10", "rsv11")
 
 _lib = None
 

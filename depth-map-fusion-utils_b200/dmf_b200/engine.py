@@ -67,7 +67,7 @@ class Context:
             pass
 
     def counters(self) -> dict:
-        out = np.zeros(8, np.uint64)
+        out = np.zeros(len(_lib.COUNTER_NAMES), np.uint64)
         check(self.lib.dmf_counters(self.h, _ptr(out, C.c_uint64)))
         return dict(zip(_lib.COUNTER_NAMES, (int(x) for x in out)))
 
@@ -209,10 +209,11 @@ def _poses12(T) -> np.ndarray:
 class RayTracingEngine:
     """RayTracingEngine(cam) -- include/RayTracingEngine.hpp:27-42.  Public member cam_ as in the reference."""
 
-    def __init__(self, cam: Camera, ctx: Optional[Context] = None, grid_format: int = GRID_BIT):
+    def __init__(self, cam: Camera, ctx: Optional[Context] = None, grid_format: int = GRID_BIT, skip_empty: bool = True):
         self.cam_ = cam
         self.ctx = ctx or Context.default()
         self.grid_format = grid_format
+        self.skip_empty = skip_empty   # False: DMF_FWD_NO_SKIP (evaluate every probe)
 
     def _prepare(self, volume: VoxelVolume):
         volume._commit(self.ctx)
@@ -244,7 +245,7 @@ class RayTracingEngine:
             cap = n * min(len(volume.occupied_cells_), H * W) + 1
             ids, offs = np.zeros(cap, np.uint64), np.zeros(n + 1, np.int64)
             o.ids, o.ids_offsets, o.ids_capacity = _vptr(ids), _vptr(offs), cap
-        p = ForwardParams(mode, int(zdelta), int(bool(sparse)), int(view_id0), self.grid_format)
+        p = ForwardParams(mode, int(zdelta), int(bool(sparse)), int(view_id0), self.grid_format, 0 if self.skip_empty else 1)
         check(self.ctx.lib.dmf_forward(self.ctx.h, C.byref(p), _ptr(poses, C.c_float), n, C.byref(o)))
         if ids is not None:
             res["ids"] = [ids[offs[i]:offs[i + 1]].copy() for i in range(n)]

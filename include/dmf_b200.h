@@ -40,7 +40,7 @@ enum {
 
 /* occupancy format probed by the march */
 enum {
-    DMF_GRID_BIT  = 0, /* 4x4x4-voxel bricks, one uint64 per brick (1/8 byte per voxel) */
+    DMF_GRID_BIT  = 0, /* linear bit grid, [x][y][z] z fastest, uint32 words (1/8 byte per voxel)  */
     DMF_GRID_BYTE = 1  /* one byte per voxel, [x][y][z] z fastest like voxels_[x][y][z] (Volume.hpp:126) */
 };
 
@@ -91,7 +91,13 @@ typedef struct {
     int sparse;      /* pixel stride 5 (10 for MINIMUM) instead of 1                                   */
     int view_id0;    /* CLASSIFY: `view` argument of pose 0; pose i uses view_id0 + i                  */
     int grid_format; /* DMF_GRID_*                                                                     */
+    int flags;       /* DMF_FWD_*                                                                      */
 } dmf_forward_params;
+
+/* By default the march skips probes that a macro-cell distance field proves to be in-bounds misses (results, id
+ * lists and the samples/inbounds counters are identical either way; DMF_CNT_SKIPPED says how many were skipped).
+ * DMF_FWD_NO_SKIP evaluates every probe (the brute-force kernel; used to validate the skipping one). */
+#define DMF_FWD_NO_SKIP 1
 
 /* Per-view outputs; any pointer may be NULL.  For the *_dev entry point these are device pointers. */
 typedef struct {
@@ -163,7 +169,9 @@ enum {
     DMF_CNT_ACOS_TIES = 5, /* good-point tests whose dot product fell in the host-libm acosf ambiguity band */
     DMF_CNT_LAUNCHES = 6,  /* kernels launched by this context                                           */
     DMF_CNT_RUNAWAY = 7,   /* reverse marches stopped by the step cap                                     */
-    DMF_CNT_COUNT = 8
+    DMF_CNT_F64_PATH = 8,  /* probes whose float index filter was inconclusive and were redone in double           */
+    DMF_CNT_SKIPPED = 9,   /* probes proven empty by the macro-cell traversal without being evaluated              */
+    DMF_CNT_COUNT = 12
 };
 int dmf_counters(dmf_ctx* ctx, uint64_t out[DMF_CNT_COUNT]);  /* cumulative; synchronises */
 int dmf_reset_counters(dmf_ctx* ctx);

@@ -32,8 +32,17 @@ def _poses(dmf, sc, n_sphere=3):
 
 
 def _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, mode, zdelta, sparse, grid_format=0, H=K_H, W=K_W, K=None):
+    """both kernels -- empty-space skipping (default) and brute force (DMF_FWD_NO_SKIP) -- against the oracle"""
+    cache = {}
+    a = _check_forward_one(dmf, oracle, ctx, sc, ov, gv, poses, mode, zdelta, sparse, grid_format, H, W, K, True, cache)
+    b = _check_forward_one(dmf, oracle, ctx, sc, ov, gv, poses, mode, zdelta, sparse, grid_format, H, W, K, False, cache)
+    assert b["skipped"] == 0
+    return a
+
+
+def _check_forward_one(dmf, oracle, ctx, sc, ov, gv, poses, mode, zdelta, sparse, grid_format, H, W, K, skip_empty, cache):
     K = dmf.scenes.REFERENCE_K if K is None else K
-    eng = dmf.RayTracingEngine(dmf.Camera(K, H, W), ctx, grid_format)
+    eng = dmf.RayTracingEngine(dmf.Camera(K, H, W), ctx, grid_format, skip_empty=skip_empty)
     ctx.reset_counters()
     g = eng.forward_views(gv, poses, mode, zdelta, sparse)
     cnt = ctx.counters()
@@ -41,7 +50,9 @@ def _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, mode, zdelta, sparse, gr
     assert np.array_equal(occ, ov.occupied()), "occupied_cells_ differ"
     tot = dict(samples=0, inbounds=0, hits=0)
     for i, pose in enumerate(poses):
-        o = oracle.forward(ov, K, H, W, pose, mode, zdelta, sparse)
+        if i not in cache:
+            cache[i] = oracle.forward(ov, K, H, W, pose, mode, zdelta, sparse)
+        o = cache[i]
         assert bool(g["found_any"][i]) == o["found_any"], f"view {i}: found_any"
         assert np.array_equal(g["depth"][i], o["depth"]), f"view {i}: first-hit depth image differs in {(g['depth'][i] != o['depth']).sum()} px"
         hit = o["depth"] >= 0
@@ -147,7 +158,8 @@ def test_config1_512_dyadic_single_view(dmf, oracle, ctx):
     sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S512")
     poses = np.stack([dmf.scenes.pose_p1(1.0)[0], dmf.scenes.poses_sphere_lookat(1.0, 64)[37]])
     cnt = _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, 0, sc.zdelta, False)
-    assert cnt["exact_div"] == 0   # power-of-two voxel size: reciprocal multiply is exact
+    assert cnt["exact_div"] == 0 and cnt["f64_path"] == 0   # power-of-two voxel size, vmin = 0: the float quotient is exact
+    assert cnt["skipped"] > 0.5 * cnt["inbounds"]            # most of the box scene is empty space
 
 
 def test_full_size_properties_512(dmf, ctx):
@@ -160,10 +172,20 @@ def test_full_size_properties_512(dmf, ctx):
     poses = dmf.scenes.poses_sphere_lookat(1.0, 256)[::32]
     e_bit = dmf.RayTracingEngine(dmf.Camera(K), ctx, dmf.GRID_BIT)
     e_byte = dmf.RayTracingEngine(dmf.Camera(K), ctx, dmf.GRID_BYTE)
+    e_brute = dmf.RayTracingEngine(dmf.Camera(K), ctx, dmf.GRID_BIT, skip_empty=False)
+    ctx.reset_counters()
     a = e_bit.forward_views(gv, poses, 0, sc.zdelta, False)
+    ca = ctx.counters(); ctx.reset_counters()
     b = e_byte.forward_views(gv, poses, 0, sc.zdelta, False)
+    ctx.reset_counters()
+    c = e_brute.forward_views(gv, poses, 0, sc.zdelta, False)
+    cc = ctx.counters()
     for k in ("depth", "voxel", "points", "visibility"):
         assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], c[k]), k
+    # skipping changes neither the probes that count nor the in-bounds tally
+    assert (ca["samples"], ca["inbounds"], ca["hits"]) == (cc["samples"], cc["inbounds"], cc["hits"])
+    assert ca["skipped"] > 0 and cc["skipped"] == 0
     one = e_bit.forward_views(gv, poses[3:4], 0, sc.zdelta, False)
     assert np.array_equal(one["depth"][0], a["depth"][3]) and np.array_equal(one["ids"][0], a["ids"][3])
     again = e_bit.forward_views(gv, poses, 0, sc.zdelta, False)
