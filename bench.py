@@ -201,8 +201,10 @@ def run_b200(args):
     eng._prepare(vol)
     n_occ = len(vol.occupied_cells_)
     vw = (n_occ + 63) // 64
+    from dmf_b200.sweep import shard_range
     all_poses = D.scenes.bench_poses(float(sc.bounds[1]), V * world)
-    poses = np.ascontiguousarray(all_poses[rank * V:(rank + 1) * V])      # this rank's shard of the sweep
+    lo, hi = shard_range(V * world, rank, world)
+    poses = np.ascontiguousarray(all_poses[lo:hi])                        # this rank's contiguous shard of the sweep
     dev = torch.device("cuda", local)
 
     # device-resident buffers for `value`
@@ -262,10 +264,10 @@ def run_b200(args):
     dev_ms = float(t.item())
     rays_total = args.steps * V * H * W * world
     value = rays_total / (dev_ms * 1e-3)
-    inb = torch.tensor([cnt["inbounds"], cnt["samples"], cnt["launches"]], dtype=torch.float64, device=dev)
+    inb = torch.tensor([cnt["inbounds"], cnt["samples"], cnt["launches"], cnt["skipped"], cnt["f64_path"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(inb)
-    inbounds_total, samples_total, launches_total = (float(x) for x in inb.tolist())
+    inbounds_total, samples_total, launches_total, skipped_total, f64_total = (float(x) for x in inb.tolist())
 
     # ---- e2e: host-buffer C-ABI call, pinned host memory, H2D + D2H inside the timed region ---------------------
     def pinned(shape, dtype):
@@ -281,30 +283,36 @@ def run_b200(args):
     h_points, p2 = pinned((V, H, W, 3), np.float32)
     h_vis, p3 = pinned((V, max(vw, 1)), np.uint64)
     h_found, p4 = pinned((V,), np.int32)
-    oh = ForwardOut()
-    oh.depth_mm, oh.points, oh.visibility, oh.found_any = h_depth.ctypes.data, h_points.ctypes.data, h_vis.ctypes.data, h_found.ctypes.data
     fp = h_poses.ctypes.data_as(C.POINTER(C.c_float))
 
-    def step_host():
-        check(ctx.lib.dmf_forward(ctx.h, C.byref(params), fp, V, C.byref(oh)))
+    def time_host(with_points: bool):
+        oh = ForwardOut()
+        oh.depth_mm, oh.visibility, oh.found_any = h_depth.ctypes.data, h_vis.ctypes.data, h_found.ctypes.data
+        if with_points:
+            oh.points = h_points.ctypes.data
+        n = max(3, min(args.steps, 10))
+        for _ in range(2):
+            check(ctx.lib.dmf_forward(ctx.h, C.byref(params), fp, V, C.byref(oh)))
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            check(ctx.lib.dmf_forward(ctx.h, C.byref(params), fp, V, C.byref(oh)))
+        torch.cuda.synchronize(); barrier()
+        sec = time.perf_counter() - t0
+        t = torch.tensor([sec], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), n
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        step_host()
-    barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    torch.cuda.synchronize(); barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    # headline e2e: the step's result = first-hit depth image + visibility bitset + found flag per view
+    e2e_s, e2e_steps = time_host(False)
     e2e_value = e2e_steps * V * H * W * world / e2e_s
-    same = bool(np.array_equal(h_depth, d_depth.cpu().numpy()))
+    same = bool(np.array_equal(h_depth, d_depth.cpu().numpy()) and np.array_equal(h_vis.view(np.int64)[:, :vw], d_vis.cpu().numpy()))
     h2d = V * 48
-    d2h = V * (H * W * 4 + H * W * 12 + vw * 8 + 4)
+    d2h = V * (H * W * 4 + vw * 8 + 4)
+    # the same with the float3 simulated point cloud copied back as well (PCIe-bound: 12 more bytes per pixel)
+    e2e_pts_s, e2e_pts_steps = time_host(True)
+    e2e_pts_value = e2e_pts_steps * V * H * W * world / e2e_pts_s
     for p in (p0, p1, p2, p3, p4):
         ctx.lib.dmf_host_free(p)
 
@@ -330,11 +338,14 @@ def run_b200(args):
             "samples_per_s": samples_total / (dev_ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
-                         "peak_source": peak_src, "kernel": "k_forward", "kernel_ms": hot, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "issue-bound by design: ~60 exact-IEEE instructions per probe, grid is L2-resident; see DESIGN.md"},
+                         "peak_source": peak_src, "kernel": "k_forward" if args.no_skip else "k_forward_skip", "kernel_ms": hot, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "algorithmic bytes are the reference-equivalent ones (every in-bounds probe reads the grid once); the skipping kernel proves most of them empty without touching memory, so measured DRAM traffic is far lower; instruction-issue bound, see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_run": same},
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_run": same, "result": "depth_mm + visibility + found_any per view",
+                    "with_points": {"value": e2e_pts_value, "d2h_bytes_per_step": d2h + V * H * W * 12, "ms_per_step": 1e3 * e2e_pts_s / e2e_pts_steps}},
             "gpu_launches": int(launches_total),
+            "probes": {"reference_equivalent_per_step": samples_total / args.steps, "in_bounds_per_step": inbounds_total / args.steps,
+                       "skipped_as_provably_empty_per_step": skipped_total / args.steps, "redone_in_f64_per_step": f64_total / args.steps},
             "clocks": clocks,
             "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
         }

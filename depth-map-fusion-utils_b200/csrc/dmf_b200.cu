@@ -463,6 +463,19 @@ int dmf_download_marks(dmf_ctx* c, int32_t* view, uint8_t* good) {
     return 0;
 }
 
+int dmf_upload_marks(dmf_ctx* c, const int32_t* view, const uint8_t* good) {
+    if (!c || !c->vol_set) return fail("no volume uploaded");
+    if (!view || !good) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    DMF_CUDA(cudaStreamSynchronize(c->stream));
+    if (!c->n_occ) return 0;
+    std::vector<uint32_t> bits((c->n_occ + 63) / 64 * 2 + 2, 0);
+    for (size_t i = 0; i < c->n_occ; i++) if (good[i]) bits[i >> 5] |= 1u << (i & 31);
+    DMF_CUDA(cudaMemcpy(c->d_view_mark.p, view, c->n_occ * 4, cudaMemcpyHostToDevice));
+    DMF_CUDA(cudaMemcpy(c->d_good_bits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 size_t dmf_visibility_words(dmf_ctx* c) { return c && c->vol_set ? (c->n_occ + 63) / 64 : 0; }
 
 int dmf_forward_dev(dmf_ctx* c, const dmf_forward_params* p, const float* d_poses, int n_views, const dmf_forward_out* d_out, void* stream) {

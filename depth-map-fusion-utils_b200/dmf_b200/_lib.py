@@ -54,6 +54,7 @@ SYMBOLS = {
     "dmf_volume_get_normals": (C.c_int, [vp, u32p, fp]),
     "dmf_clear_marks": (C.c_int, [vp]),
     "dmf_download_marks": (C.c_int, [vp, i32p, u8p]),
+    "dmf_upload_marks": (C.c_int, [vp, i32p, u8p]),
     "dmf_visibility_words": (C.c_size_t, [vp]),
     "dmf_forward": (C.c_int, [vp, C.POINTER(ForwardParams), fp, C.c_int, C.POINTER(ForwardOut)]),
     "dmf_forward_dev": (C.c_int, [vp, C.POINTER(ForwardParams), vp, C.c_int, C.POINTER(ForwardOut), vp]),

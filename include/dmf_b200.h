@@ -83,6 +83,7 @@ int dmf_volume_get_normals(dmf_ctx* ctx, uint32_t* offsets, float* normals);
 /* Voxel::view / Voxel::good (Volume.hpp:33-34) live on the device between calls. */
 int dmf_clear_marks(dmf_ctx* ctx);
 int dmf_download_marks(dmf_ctx* ctx, int32_t* view /* n_occ */, uint8_t* good /* n_occ */);
+int dmf_upload_marks(dmf_ctx* ctx, const int32_t* view /* n_occ */, const uint8_t* good /* n_occ */);
 
 /* ---- forward per-pixel march ------------------------------------------------------------------ */
 typedef struct {
