@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--views", type=int, default=128, help="views per step per GPU (128 x 8 GPUs = the 1024-view sweep)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--grid", default="bit", choices=["bit", "byte"])
+    ap.add_argument("--grid", default="byte", choices=["bit", "byte"], help="byte = per-voxel Chebyshev distance bytes (default), bit = packed bits + macro-cell clearance")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-skip", action="store_true", help="evaluate every probe (brute-force kernel)")

@@ -4,6 +4,7 @@
 #include "dmf_host.cuh"
 #include "dmf_forward.cuh"
 #include "dmf_reverse.cuh"
+#include "dmf_distance.cuh"
 #include "dmf_setcover.cuh"
 #include <algorithm>
 #include <climits>
@@ -67,6 +68,7 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
         float lo = (float)vmin; if ((double)lo > vmin) lo = next_down(lo);
         float hi = (float)vmax; if ((double)hi < vmax) hi = next_up(hi);
         v.lo[a] = lo; v.hi[a] = hi;
+        v.ext[a] = next_up((float)((vmax - vmin) * v.inv[a] * (1.0 + 1e-7)));
     }
     const size_t nbits = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
     const size_t nwords = ((nbits + 31) / 32 + 7) / 8 * 8;           // whole 8-word (256-bit) rank blocks
@@ -192,14 +194,23 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
     return 0;
 }
 
+// DMF_GRID_BYTE: the per-voxel Chebyshev distance bytes (dmf_distance.cuh), built on first use
 int ensure_bytes(dmf_ctx* c, cudaStream_t st) {
     if (c->bytes_built) return 0;
     VolDev& v = c->vol;
-    size_t n = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
+    const size_t n = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
     DMF_TRY(c->d_bytes.reserve(n));
-    k_expand_bytes<<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(v, c->d_bytes.as<unsigned char>());
-    c->launches++;
-    DMF_CUDA(cudaGetLastError());
+    DevBuf tmp;
+    DMF_TRY(tmp.reserve(n));
+    const unsigned nlines = (unsigned)v.pdim[0] * (unsigned)v.pdim[1];
+    k_dt_z<<<(nlines + 127) / 128, 128, 0, st>>>(v, c->d_bytes.as<unsigned char>());
+    k_dt_axis<1, false><<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(v, c->d_bytes.as<unsigned char>(), tmp.as<unsigned char>());
+    k_dt_axis<0, true><<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(v, tmp.as<unsigned char>(), c->d_bytes.as<unsigned char>());
+    c->launches += 3;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    tmp.release();
+    if (e != cudaSuccess) return fail("distance transform failed: %s", cudaGetErrorString(e));
     v.bytes = c->d_bytes.as<unsigned char>();
     c->bytes_built = true;
     return 0;

@@ -16,7 +16,8 @@ typedef unsigned long long u64;
 //            reads out of bounds there) lands on it, so the forward march needs no index range check.
 //   prefix   uint32 per 8 words (256 bits): number of occupied voxels before that block (rank directory)
 //   rank2occ [n_occ] rank (linear order) -> index into occupied_cells_
-//   bytes    optional byte-per-voxel copy over the same padded index space (DMF_GRID_BYTE)
+//   bytes    optional per-voxel Chebyshev distance bytes over the same padded index space, 0 = occupied
+//            (DMF_GRID_BYTE, dmf_distance.cuh)
 //   macro    1 bit per 8x8x8-voxel macro cell: "contains an occupied voxel" (empty-space skipping)
 //   noff/normals  CSR of Voxel::normals in occupied order
 struct VolDev {
@@ -43,6 +44,7 @@ struct VolDev {
     float err32[3];  // bound on |fmaf(p,inv32,c32) - reference quotient|  (0 => the float quotient is exact)
     float lo[3];     // largest float <= vmin   (validPoints: x<=xmin_  <=>  !(x > lo))
     float hi[3];     // smallest float >= vmax  (validPoints: x>=xmax_  <=>  !(x < hi))
+    float ext[3];    // >= (vmax-vmin)/delta: the volume's extent in voxel units (dim <= ext < dim+1, constructVolume truncates)
 };
 
 // floor(((double)p - vmin) / delta) exactly as VoxelVolume::getVoxel (Volume.hpp:150-156) computes it, in double.
@@ -96,7 +98,7 @@ template <int FMT>
 __device__ __forceinline__ bool occupied(const VolDev& v, int x, int y, int z) {
     const unsigned idx = linear_index(v, x, y, z);
     if (FMT == 0) return (__ldg(v.bits + (idx >> 5)) >> (idx & 31)) & 1u;
-    return __ldg(v.bytes + idx) != 0;
+    return __ldg(v.bytes + idx) == 0;   // distance bytes: 0 = occupied (dmf_distance.cuh)
 }
 
 // index into occupied_cells_ of an occupied voxel

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
                 }
                 // voxels_[xid][yid][zid] != nullptr: indices are in [0,dim] here, the padded grid covers index == dim
                 const unsigned idx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
-                const bool occ_here = FMT == 0 ? ((__ldg(gbits + (idx >> 5)) >> (idx & 31)) & 1u) != 0u : __ldg(gbytes + idx) != 0;
+                const bool occ_here = FMT == 0 ? ((__ldg(gbits + (idx >> 5)) >> (idx & 31)) & 1u) != 0u : __ldg(gbytes + idx) == 0;
                 if (occ_here) {
                     hit_k = k0 + kk; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz;
                     done = true;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward_skip(const FwdArgs a) {
     const float qa0 = fmaf(fmaf(z0m, g0, m03), in0, cc0), qa1 = fmaf(fmaf(z0m, g1, m13), in1, cc1), qa2 = fmaf(fmaf(z0m, g2, m23), in2, cc2);
     const float qb0 = zdm * g0 * in0, qb1 = zdm * g1 * in1, qb2 = zdm * g2 * in2;
     const float qbmax = fmaxf(fabsf(qb0), fmaxf(fabsf(qb1), fabsf(qb2)));
-    const float rq = 1.0f / fmaxf(qbmax, 1e-6f);
+    const float rq = 1.0f / fmaxf(qbmax, 1e-3f);   // <= 1000: keeps (d-1.25)*rq inside the shifter's integer range
     // per-view error bound in voxel units (uniform over the block)
     const float kEps = 9.5367431640625e-07f;   // 16 * 2^-24
     const float e0 = kEps * (fabsf(m00) * a.dcx_max + fabsf(m01) * a.dcy_max + fabsf(m02) + fabsf(m03) + fabsf((float)v.vmin[0])) * fabsf(in0);
@@ -312,15 +312,17 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward_skip(const FwdArgs a) {
     const float* __restrict__ yt = a.ytab + ric;
     const float* __restrict__ zt = a.ztab;
     const float kM = 12582912.0f;
+    const float fd0 = v.ext[0], fd1 = v.ext[1], fd2 = v.ext[2];   // volume extent in voxel units (>= dim, < dim+1)
     unsigned iter = 0;
+    int oob_wait = 0;
     if (active) {
         while (k < S) {
             if (MODE == 4 && (iter++ & 15u) == 0u) {   // rayTraceAndGetMinimum: planes behind the current minimum cannot matter
                 const int cur = *((volatile int*)(a.min_depth + view));
                 if (a.z0 + k * a.zdelta > cur) break;
             }
-            if (skip_ok) {
-                // macro cell of the line point (floor(q/8) through the round-down shifter; no F2I)
+            if (FMT == 0 && skip_ok) {
+                // bit grid: macro cell of the line point (floor(q/8) through the round-down shifter; no F2I)
                 const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
                 const unsigned mx = (unsigned)(__float_as_int(__fadd_rd(q0 * 0.125f, kM)) - 0x4B400000);
                 const unsigned my = (unsigned)(__float_as_int(__fadd_rd(q1 * 0.125f, kM)) - 0x4B400000);
@@ -340,8 +342,31 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward_skip(const FwdArgs a) {
             const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, xf), __fmul_rn(m01, yf)), __fmul_rn(m02, zf)), m03);
             const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, xf), __fmul_rn(m11, yf)), __fmul_rn(m12, zf)), m13);
             const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, xf), __fmul_rn(m21, yf)), __fmul_rn(m22, zf)), m23);
-            k++; kf += 1.0f;
-            if (!(px > lo0 && px < hi0 && py > lo1 && py < hi1 && pz > lo2 && pz < hi2)) continue;
+            if (!(px > lo0 && px < hi0 && py > lo1 && py < hi1 && pz > lo2 && pz < hi2)) {
+                // validPoints failed: the reference just moves on.  Once per excursion, use the line to jump over the samples
+                // that are provably outside (some axis of the line is > 0.25 voxel beyond the volume, eps_q <= 0.1).
+                int kn = k + 1;
+                if (skip_ok && oob_wait == 0) {
+                    // real-valued k interval where the line is inside the volume inflated by 0.25 voxel on every side
+                    float t0 = -1e30f, t1 = 1e30f;
+                    const float qa[3] = {qa0, qa1, qa2}, qb[3] = {qb0, qb1, qb2}, fd[3] = {fd0, fd1, fd2};
+#pragma unroll
+                    for (int ax = 0; ax < 3; ax++) {
+                        if (fabsf(qb[ax]) > 1e-12f) {
+                            const float r = 1.0f / qb[ax];
+                            const float ta = (-0.25f - qa[ax]) * r, tb = (fd[ax] + 0.25f - qa[ax]) * r;
+                            t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+                        } else if (qa[ax] < -0.25f || qa[ax] > fd[ax] + 0.25f) { t0 = 1e30f; }
+                    }
+                    // t0,t1 carry a relative error of a few ulps: move the entry 1 sample earlier and the exit 1 later
+                    if (!(t0 <= t1) || t1 + 1.0f < kf) kn = S;                               // never (again) inside: all remaining samples fail validPoints
+                    else if (t0 - 1.0f > kf + 1.0f) kn = min(S, max(k + 1, __float2int_rd(t0 - 1.0f)));
+                    if (kn == k + 1) oob_wait = 4;                                           // inconclusive (grazing the boundary): retry a few samples later
+                } else if (oob_wait > 0) oob_wait--;
+                kf += (float)(kn - k); k = kn;
+                continue;
+            }
+            oob_wait = 0;
             n_inb++;
             bool unsafe = false;
             int ix = voxel_index_f32(px, in0, cc0, er0, unsafe);
@@ -354,10 +379,29 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward_skip(const FwdArgs a) {
                 iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
             }
             const unsigned idx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
-            const bool occ_here = FMT == 0 ? ((__ldg(gbits + (idx >> 5)) >> (idx & 31)) & 1u) != 0u : __ldg(gbytes + idx) != 0;
-            if (occ_here) {
-                hit_k = k - 1; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz;
-                break;
+            if (FMT == 0) {
+                if ((__ldg(gbits + (idx >> 5)) >> (idx & 31)) & 1u) {
+                    hit_k = k; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz;
+                    k++;
+                    break;
+                }
+                k++; kf += 1.0f;
+            } else {
+                // distance bytes (dmf_distance.cuh): 0 = occupied; d >= 2 => every voxel within d-1 (L-inf) of this one is an
+                // empty interior voxel, so the samples whose line offset stays within d - 1.25 voxels are in-bounds misses
+                const unsigned d = __ldg(gbytes + idx);
+                if (d == 0u) {
+                    hit_k = k; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz;
+                    k++;
+                    break;
+                }
+                int n = 0;
+                if (skip_ok && d >= 2u) {
+                    const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;        // (float)d without I2F
+                    n = min(__float_as_int(__fadd_rd((df - 1.25f) * rq, kM)) - 0x4B400000, S - k - 1);
+                    n_skip += (unsigned)n; n_inb += (unsigned)n;
+                }
+                k += n + 1; kf += (float)(n + 1);
             }
         }
     }

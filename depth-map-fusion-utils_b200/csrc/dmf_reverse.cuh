@@ -38,12 +38,6 @@ __global__ void k_centroid_hash(const VolDev v, u64* out) {
     }
 }
 
-__global__ void k_expand_bytes(const VolDev v, unsigned char* bytes) {
-    const size_t n = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];   // same padded linear index space as the bit grid
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        bytes[i] = (unsigned char)((__ldg(v.bits + (i >> 5)) >> (i & 31)) & 1u);
-}
-
 // Eigen::Affine3f::inverse() (rule E5 of oracle/dmf_oracle.hpp): cofactor inverse * (1/det), translation = -(Linv*t)
 __global__ void k_invert_poses(const float* __restrict__ poses, float* __restrict__ inv, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

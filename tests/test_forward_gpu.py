@@ -74,9 +74,27 @@ def _check_forward_one(dmf, oracle, ctx, sc, ov, gv, poses, mode, zdelta, sparse
 
 @pytest.mark.parametrize("name", ["S64", "S128", "S128-odd", "S128-clutter"])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_points_and_good_points_dense(dmf, oracle, ctx, name, mode):
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_points_and_good_points_dense(dmf, oracle, ctx, name, mode, fmt):
+    """fmt 0: bit grid + macro-cell clearance; fmt 1: per-voxel Chebyshev distance bytes"""
     sc, ov, gv = _scene_pair(dmf, oracle, ctx, name)
-    _check_forward(dmf, oracle, ctx, sc, ov, gv, _poses(dmf, sc), mode, sc.zdelta, False)
+    _check_forward(dmf, oracle, ctx, sc, ov, gv, _poses(dmf, sc), mode, sc.zdelta, False, grid_format=fmt)
+
+
+def test_cameras_outside_the_volume(dmf, oracle, ctx):
+    """rays that start outside the AABB, graze it, or cross it and leave: the out-of-bounds jump must not change a probe"""
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S128")
+    L = float(sc.bounds[1])
+    poses = np.stack([
+        dmf.scenes.look_at([-0.4 * L, 0.5 * L, 0.5 * L], [0.5 * L, 0.5 * L, 0.5 * L]),      # outside, looking in
+        dmf.scenes.look_at([0.5 * L, 0.5 * L, 1.3 * L], [0.5 * L, 0.45 * L, 0.5 * L]),
+        dmf.scenes.look_at([-0.2 * L, -0.2 * L, 0.001], [L, L, 0.004]),                      # grazing the z = 0 face
+        dmf.scenes.look_at([0.5 * L, 0.5 * L, 0.99 * L], [0.5 * L, 0.5 * L, 2 * L]),         # inside, leaving immediately
+        dmf.scenes.look_at([1.2 * L, 0.3 * L, 0.5 * L], [1.2 * L, 0.9 * L, 0.5 * L]),        # parallel to a face, never inside
+    ] + list(dmf.scenes.poses_position_camera(L, 60)[::12]))
+    for fmt in (0, 1):
+        for sparse, zd in ((False, sc.zdelta), (True, 3)):
+            _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, 0, zd, sparse, grid_format=fmt)
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -84,11 +102,6 @@ def test_sparse_default_arguments(dmf, oracle, ctx, mode):
     """reference defaults: zdelta=10, sparse=true (pixel stride 5)"""
     sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S128")
     _check_forward(dmf, oracle, ctx, sc, ov, gv, _poses(dmf, sc), mode, 10, True)
-
-
-def test_byte_grid_matches(dmf, oracle, ctx):
-    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S128")
-    _check_forward(dmf, oracle, ctx, sc, ov, gv, _poses(dmf, sc, 2), 0, sc.zdelta, False, grid_format=dmf.GRID_BYTE)
 
 
 def test_ragged_image_and_odd_zdelta(dmf, oracle, ctx):
@@ -157,6 +170,7 @@ def test_config1_512_dyadic_single_view(dmf, oracle, ctx):
     """BASELINE.json configs[1]: one 640x480 view into the 512^3 grid (dyadic bounds => op-order independent)."""
     sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S512")
     poses = np.stack([dmf.scenes.pose_p1(1.0)[0], dmf.scenes.poses_sphere_lookat(1.0, 64)[37]])
+    _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, 0, sc.zdelta, False, grid_format=1)
     cnt = _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, 0, sc.zdelta, False)
     assert cnt["exact_div"] == 0 and cnt["f64_path"] == 0   # power-of-two voxel size, vmin = 0: the float quotient is exact
     assert cnt["skipped"] > 0.5 * cnt["inbounds"]            # most of the box scene is empty space
