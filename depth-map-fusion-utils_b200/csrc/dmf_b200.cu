@@ -243,8 +243,9 @@ int ensure_tables(dmf_ctx* c, int z0, int zdelta, int cstride, int rstride, cuda
 template <int MODE>
 void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, dim3 grid, cudaStream_t st) {
     if (skip) {
-        if (fmt == DMF_GRID_BYTE) k_forward_skip<MODE, 1><<<grid, FWD_THREADS, 0, st>>>(a);
-        else k_forward_skip<MODE, 0><<<grid, FWD_THREADS, 0, st>>>(a);
+        dim3 g((a.Wc + SKIP_TILE_W - 1) / SKIP_TILE_W, (a.Hc + SKIP_TILE_H - 1) / SKIP_TILE_H, grid.z);
+        if (fmt == DMF_GRID_BYTE) k_forward_skip<MODE, 1><<<g, SKIP_THREADS, 0, st>>>(a);
+        else k_forward_skip<MODE, 0><<<g, SKIP_THREADS, 0, st>>>(a);
     } else {
         if (fmt == DMF_GRID_BYTE) k_forward<MODE, 1><<<grid, FWD_THREADS, 0, st>>>(a);
         else k_forward<MODE, 0><<<grid, FWD_THREADS, 0, st>>>(a);

@@ -125,7 +125,8 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
         }
     }
 
-    // ---- counters: warp reduce -> shared -> 4 global atomics per block ------------------------------
+    // ---- counters: warp reduce -> shared; the LAST warp of the block to get here flushes them with a few global atomics.
+    // No block barrier: warps whose rays ended early must not sit on a barrier waiting for the longest ray of the block.
     unsigned long long c0 = n_samples, c1 = n_inb, c2 = hit ? 1u : 0u, c3 = n_exact, c5 = ties, c8 = n_f64, c9 = n_skip;
     for (int o = 16; o; o >>= 1) {
         c0 += __shfl_down_sync(0xffffffffu, c0, o); c1 += __shfl_down_sync(0xffffffffu, c1, o);
@@ -133,13 +134,22 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
         c5 += __shfl_down_sync(0xffffffffu, c5, o); c8 += __shfl_down_sync(0xffffffffu, c8, o); c9 += __shfl_down_sync(0xffffffffu, c9, o);
     }
     if (lane == 0) {
-        atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); atomicAdd(&s_cnt[2], c2); atomicAdd(&s_cnt[3], c3);
+        atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); atomicAdd(&s_cnt[2], c2); atomicAdd(&s_cnt[3], c9);
+        if (c3) atomicAdd(a.counters + 3, c3);
         if (c5) atomicAdd(a.counters + 5, c5);
         if (c8) atomicAdd(a.counters + 8, c8);
-        if (c9) atomicAdd(a.counters + 9, c9);
+        __threadfence_block();
+        const unsigned long long ticket = atomicAdd(&s_cnt[4], 1ull);
+        if (ticket == (unsigned long long)(blockDim.x >> 5) - 1ull) {
+            __threadfence_block();
+            const int slot[4] = {0, 1, 2, 9};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned long long val = *((volatile unsigned long long*)&s_cnt[j]);
+                if (val) atomicAdd(a.counters + slot[j], val);
+            }
+        }
     }
-    __syncthreads();
-    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(a.counters + threadIdx.x, s_cnt[threadIdx.x]);
 }
 
 
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
     __shared__ float sx[FWD_CHUNK][FWD_TILE_W];
     __shared__ float sy[FWD_CHUNK][FWD_TILE_H];
     __shared__ __align__(16) float sz[FWD_CHUNK][4];   // m02*z, m12*z, m22*z
-    __shared__ unsigned long long s_cnt[4];
+    __shared__ unsigned long long s_cnt[5];
 
     const int view = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,7 +172,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
     const int ci = blockIdx.x * FWD_TILE_W + lc;  // lattice column
     const int ri = blockIdx.y * FWD_TILE_H + lr;  // lattice row
     const bool active = ci < a.Wc && ri < a.Hc;
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0ull;
 
     const float* P = a.poses + 12 * (size_t)view;
     const float m00 = __ldg(P + 0), m01 = __ldg(P + 1), m02 = __ldg(P + 2), m03 = __ldg(P + 3);
@@ -261,15 +271,18 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
 // Error budget: |float sample - line| <= eps_p = 16*2^-24 * (|m0|X + |m1|Y + |m2|Z + |m3|) per axis (5 roundings of the
 // reference evaluation + <= 8 of the line's own float evaluation, doubled), eps_q = eps_p/delta.  A view whose eps_q
 // exceeds 0.1 voxel on any axis does not skip at all (skip_ok = false).  2*eps_q <= 0.2 < the 0.25 voxel margin.
+constexpr int SKIP_THREADS = 128;     // 4 warps: 2 across x 2 down, each warp an 8x4 pixel tile
+constexpr int SKIP_TILE_W = 16, SKIP_TILE_H = 8;
+
 template <int MODE, int FMT>
-__global__ void __launch_bounds__(FWD_THREADS) k_forward_skip(const FwdArgs a) {
-    __shared__ unsigned long long s_cnt[4];
+__global__ void __launch_bounds__(SKIP_THREADS, 8) k_forward_skip(const FwdArgs a) {
+    __shared__ unsigned long long s_cnt[5];
     const int view = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci = blockIdx.x * FWD_TILE_W + (warp & 3) * 8 + (lane & 7);
-    const int ri = blockIdx.y * FWD_TILE_H + (warp >> 2) * 4 + (lane >> 3);
+    const int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
+    const int ri = blockIdx.y * SKIP_TILE_H + (warp >> 1) * 4 + (lane >> 3);
     const bool active = ci < a.Wc && ri < a.Hc;
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0ull;
     __syncthreads();
 
     const float* P = a.poses + 12 * (size_t)view;
