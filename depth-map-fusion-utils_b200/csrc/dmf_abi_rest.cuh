@@ -27,6 +27,7 @@ int fill_rev_args(dmf_ctx* c, RevArgs& a) {
 int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_views, unsigned* d_vis, unsigned* d_unocc, int* d_found,
                     u64* d_emit_list, unsigned* d_emit_count, unsigned emit_cap, cudaStream_t st) {
     if (n_views <= 0) return 0;
+    if (c->reverse_format == DMF_GRID_BYTE && c->vol_set) DMF_TRY(ensure_bytes(c, st));
     if (n_views > 65535) return fail("at most 65535 views per launch (got %d)", n_views);
     RevArgs a; DMF_TRY(fill_rev_args(c, a));
     DMF_TRY(c->d_inv_poses.reserve((size_t)n_views * 48));
@@ -45,14 +46,14 @@ int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_v
     if (fast) {
         if (!c->n_occ) return 0;
         dim3 grid((unsigned)((c->n_occ + 127) / 128), n_views);
-        k_reverse<true><<<grid, 128, 0, st>>>(a);
+        if (c->reverse_format == DMF_GRID_BYTE) k_reverse<true, 1><<<grid, 128, 0, st>>>(a); else k_reverse<true, 0><<<grid, 128, 0, st>>>(a);
     } else {
         size_t total = (size_t)a.nax[0] * a.nax[1] * a.nax[2];
         if (!total) return 0;
         size_t gx = (total + 127) / 128;
         if (gx > 0x7fffffffull) return fail("grid too large for the whole-grid reverse scan");
         dim3 grid((unsigned)gx, n_views);
-        k_reverse<false><<<grid, 128, 0, st>>>(a);
+        if (c->reverse_format == DMF_GRID_BYTE) k_reverse<false, 1><<<grid, 128, 0, st>>>(a); else k_reverse<false, 0><<<grid, 128, 0, st>>>(a);
     }
     DMF_CUDA(cudaEventRecord(c->ev_h1, st));
     c->hot_timed = true;
@@ -187,6 +188,27 @@ int dmf_zbuffer(dmf_ctx* c, const float pose[12], int32_t* depth, int64_t* n_spl
     if (depth) DMF_CUDA(cudaMemcpyAsync(depth, a.zbuf, HW * 4, cudaMemcpyDeviceToHost, st));
     DMF_CUDA(cudaStreamSynchronize(st));
     if (n_splat) *n_splat = (int64_t)h_cnt[0];
+    return 0;
+}
+
+int dmf_set_reverse_format(dmf_ctx* c, int grid_format) {
+    if (!c) return fail("null context");
+    if (grid_format != DMF_GRID_BIT && grid_format != DMF_GRID_BYTE) return fail("bad grid_format %d", grid_format);
+    c->reverse_format = grid_format;
+    return 0;
+}
+
+int dmf_selftest_div1000(dmf_ctx* c, uint64_t mismatches[5]) {
+    if (!c || !mismatches) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    DMF_TRY(c->d_misc[3].reserve(40));
+    const unsigned long long init[5] = {0, 0, 0, 0xffffffffull, 0};
+    DMF_CUDA(cudaMemcpyAsync(c->d_misc[3].p, init, 40, cudaMemcpyHostToDevice, c->stream));
+    k_selftest_div1000<<<148 * 16, 256, 0, c->stream>>>(c->d_misc[3].as<unsigned long long>());
+    c->launches++;
+    DMF_CUDA(cudaGetLastError());
+    DMF_CUDA(cudaMemcpyAsync(mismatches, c->d_misc[3].p, 40, cudaMemcpyDeviceToHost, c->stream));
+    DMF_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -68,6 +68,7 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
         float lo = (float)vmin; if ((double)lo > vmin) lo = next_down(lo);
         float hi = (float)vmax; if ((double)hi < vmax) hi = next_up(hi);
         v.lo[a] = lo; v.hi[a] = hi;
+        v.rev_eps[a] = (float)(std::ldexp(8.0, -24) * std::max(std::fabs(vmin), std::fabs(vmax)) * v.inv[a] * 2.0);
         v.ext[a] = next_up((float)((vmax - vmin) * v.inv[a] * (1.0 + 1e-7)));
     }
     const size_t nbits = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];

@@ -44,6 +44,7 @@ struct VolDev {
     float err32[3];  // bound on |fmaf(p,inv32,c32) - reference quotient|  (0 => the float quotient is exact)
     float lo[3];     // largest float <= vmin   (validPoints: x<=xmin_  <=>  !(x > lo))
     float hi[3];     // smallest float >= vmax  (validPoints: x>=xmax_  <=>  !(x < hi))
+    float rev_eps[3]; // bound (voxel units) on |reverse-march sample - its line point|; > 0.1 disables skipping there
     float ext[3];    // >= (vmax-vmin)/delta: the volume's extent in voxel units (dim <= ext < dim+1, constructVolume truncates)
 };
 
@@ -152,6 +153,24 @@ __device__ __forceinline__ bool any_normal_faces(const VolDev& v, const AngleTes
         if (d >= at.dot_min && d <= 1.0f) return true;
     }
     return false;
+}
+
+// a / 1000.0f without the IEEE-division sequence (the reverse march divides three times per step:
+// `centroid + v*double(depth)/1000.0`, RayTracingEngine.hpp:82,173).  r = RN(1/1000) and one Markstein correction.
+// Exhaustion over all 2^32 float inputs on the B200 (k_selftest_div1000, tests/test_reverse_gpu.py::test_div1000_exhaustive)
+// shows it equals __fdiv_rn(a, 1000.0f) bit for bit for every finite |a| > 2^-101; it differs only where the quotient is
+// subnormal (|a| < 2^-122), for -0 and for +-inf.  Callers therefore use it only when |a| >= 2^-100 is guaranteed
+// (k_reverse checks the direction components once per ray) and fall back to __fdiv_rn otherwise.
+__device__ __forceinline__ float div1000_short(float a) {
+    const float r = 1.0f / 1000.0f;
+    const float q = __fmul_rn(a, r);
+    return fmaf(fmaf(-1000.0f, q, a), r, q);
+}
+__device__ __forceinline__ float div1000(float a) {      // two corrections; same exactness domain, kept for the self-test
+    const float r = 1.0f / 1000.0f;
+    float q = __fmul_rn(a, r);
+    q = fmaf(fmaf(-1000.0f, q, a), r, q);
+    return fmaf(fmaf(-1000.0f, q, a), r, q);
 }
 
 // x86 cvttsd2si semantics (INT_MIN on NaN / overflow) for the reference's int(round(...)) casts (Camera.hpp:35-36)

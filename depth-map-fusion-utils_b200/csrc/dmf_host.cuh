@@ -135,6 +135,7 @@ struct dmf_ctx {
     std::vector<uint64_t> h_occ; std::vector<uint32_t> h_noff; std::vector<float> h_normals;
     dmf::DevBuf d_bricks /* bit grid words */, d_macro, d_prefix, d_rank2occ, d_bytes, d_noff, d_normals, d_occ_ids, d_centroid_hash;
     bool bytes_built = false;
+    int reverse_format = DMF_GRID_BYTE;   // grid the reverse march probes (dmf_set_reverse_format)
     dmf::DevBuf d_view_mark, d_good_bits, d_first_view;
     // reverseRayTrace / rayTraceVolume float-accumulated axes
     dmf::DevBuf d_axis[3]; int n_axis[3] = {0, 0, 0};

@@ -38,6 +38,29 @@ __global__ void k_centroid_hash(const VolDev v, u64* out) {
     }
 }
 
+// exhaustive check of div1000 / div1000_short against __fdiv_rn over every float bit pattern
+__global__ void k_selftest_div1000(unsigned long long* mismatches) {
+    unsigned long long bad_long = 0, bad_short = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < (1ull << 32); i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float a = __uint_as_float((unsigned)i);
+        const float ref = __fdiv_rn(a, 1000.0f);
+        const float l = div1000(a), sh = div1000_short(a);
+        const bool nan_ref = ref != ref;
+        if (nan_ref ? !(l != l) : (__float_as_uint(l) != __float_as_uint(ref))) {
+            bad_long++;
+            const unsigned mag = (unsigned)i & 0x7fffffffu;          // |a| as bits: track the range of failing magnitudes
+            if (mag < 0x7f800000u) { atomicMax((unsigned*)(mismatches + 2), mag); atomicMin((unsigned*)(mismatches + 3), mag); }
+        }
+        if (nan_ref ? !(sh != sh) : (__float_as_uint(sh) != __float_as_uint(ref))) {
+            bad_short++;
+            const unsigned mag = (unsigned)i & 0x7fffffffu;
+            if (mag < 0x7f800000u && mag > 0x0d000000u) atomicAdd(mismatches + 4, 1ull);   // failures of the short form above 2^-101
+        }
+    }
+    if (bad_long) atomicAdd(mismatches, bad_long);
+    if (bad_short) atomicAdd(mismatches + 1, bad_short);
+}
+
 // Eigen::Affine3f::inverse() (rule E5 of oracle/dmf_oracle.hpp): cofactor inverse * (1/det), translation = -(Linv*t)
 __global__ void k_invert_poses(const float* __restrict__ poses, float* __restrict__ inv, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,35 +114,74 @@ __device__ __forceinline__ void camera_pixel(const RevArgs& a, float xx, float y
 }
 
 // The 1 mm march from `centroid` towards (and past) the camera (:81-103, :172-200).  true = occluded.
+// FMT 0: bit grid, every step evaluated.  FMT 1: distance bytes -- a step that lands in a voxel with distance byte
+// d >= 2 proves that the next floor((d-1.25)/step) steps land in empty interior voxels (they cannot collide, cannot be the
+// origin voxel, cannot leave the volume), so they are counted and skipped; results and counters are unchanged.
+// Samples are c + (v*depth)/1000 in float: within 3 roundings (< rev_eps voxels) of the line c + depth*(v/1000).
 template <int FMT>
 __device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float cy, float cz, float vx, float vy, float vz, u64 chash, int d0,
-                                               unsigned& n_samples, unsigned& n_inb, unsigned& n_exact, unsigned& n_runaway) {
+                                               unsigned& n_samples, unsigned& n_inb, unsigned& n_exact, unsigned& n_runaway,
+                                               unsigned& n_f64, unsigned& n_skip) {
     const VolDev& v = a.vol;
-    for (int depth = d0;; depth++) {
+    const float lo0 = v.lo[0], lo1 = v.lo[1], lo2 = v.lo[2], hi0 = v.hi[0], hi1 = v.hi[1], hi2 = v.hi[2];
+    const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2], cc0 = v.c32[0], cc1 = v.c32[1], cc2 = v.c32[2];
+    const float er0 = v.err32[0], er1 = v.err32[1], er2 = v.err32[2];
+    const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
+    // the fast a/1000 is exact only for |a| >= 2^-100 (dmf_device.cuh); a = v_i * depth with depth >= 1
+    const bool fast_div = fminf(fabsf(vx), fminf(fabsf(vy), fabsf(vz))) >= 7.888609052210118e-31f;
+    const float step = fmaxf(fabsf(vx) * fabsf(in0), fmaxf(fabsf(vy) * fabsf(in1), fabsf(vz) * fabsf(in2))) * 0.001f;   // voxels per 1 mm step
+    const float rq = 1.0f / fmaxf(step, 1e-3f);
+    const bool skip_ok = FMT == 1 && fmaxf(v.rev_eps[0], fmaxf(v.rev_eps[1], v.rev_eps[2])) <= 0.1f;
+    const float kM = 12582912.0f;
+    int depth = d0;
+    float s = (float)d0;
+    for (;;) {
         if (depth - d0 > a.step_cap) { n_runaway++; return false; }
-        const float s = (float)depth;
         // centroid + v*double(depth)/1000.0 in float (rule E4)
-        const float px = __fadd_rn(cx, __fdiv_rn(__fmul_rn(vx, s), 1000.0f));
-        const float py = __fadd_rn(cy, __fdiv_rn(__fmul_rn(vy, s), 1000.0f));
-        const float pz = __fadd_rn(cz, __fdiv_rn(__fmul_rn(vz, s), 1000.0f));
+        const float ax = __fmul_rn(vx, s), ay = __fmul_rn(vy, s), az = __fmul_rn(vz, s);
+        float qx, qy, qz;
+        if (fast_div) { qx = div1000_short(ax); qy = div1000_short(ay); qz = div1000_short(az); }
+        else { qx = __fdiv_rn(ax, 1000.0f); qy = __fdiv_rn(ay, 1000.0f); qz = __fdiv_rn(az, 1000.0f); }
+        const float px = __fadd_rn(cx, qx), py = __fadd_rn(cy, qy), pz = __fadd_rn(cz, qz);
         n_samples++;
-        if (!in_bounds(v, px, py, pz)) return false;
+        if (!(px > lo0 && px < hi0 && py > lo1 && py < hi1 && pz > lo2 && pz < hi2)) return false;   // validPoints == false: break
         n_inb++;
-        const int ix = voxel_index(px, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
-        const int iy = voxel_index(py, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
-        const int iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
-        if (hash_coords(ix, iy, iz) == chash) continue;       // same voxel as the origin
-        if (!coords_valid(v, ix, iy, iz)) return false;        // validCoords == false: break
-        if (occupied<FMT>(v, ix, iy, iz)) return true;
+        bool unsafe = false;
+        int ix = voxel_index_f32(px, in0, cc0, er0, unsafe);
+        int iy = voxel_index_f32(py, in1, cc1, er1, unsafe);
+        int iz = voxel_index_f32(pz, in2, cc2, er2, unsafe);
+        if (unsafe) {
+            n_f64++;
+            ix = voxel_index(px, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+            iy = voxel_index(py, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+            iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+        }
+        int n = 0;
+        if (hash_coords(ix, iy, iz) != chash) {                    // hash == centroid_hash: same voxel as the origin, continue
+            if (!coords_valid(v, ix, iy, iz)) return false;        // validCoords == false: break
+            const unsigned idx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+            if (FMT == 0) {
+                if ((__ldg(v.bits + (idx >> 5)) >> (idx & 31)) & 1u) return true;
+            } else {
+                const unsigned d = __ldg(v.bytes + idx);
+                if (d == 0u) return true;
+                if (skip_ok && d >= 2u) {
+                    const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
+                    n = min(__float_as_int(__fadd_rd((df - 1.25f) * rq, kM)) - 0x4B400000, a.step_cap);
+                    n_samples += (unsigned)n; n_inb += (unsigned)n; n_skip += (unsigned)n;
+                }
+            }
+        }
+        depth += n + 1; s += (float)(n + 1);
     }
 }
 
 __device__ __forceinline__ void flush_counters(u64* counters, unsigned n_samples, unsigned n_inb, unsigned n_hits, unsigned n_exact,
-                                               unsigned n_oob, unsigned n_ties, unsigned n_runaway) {
-    unsigned long long c[7] = {n_samples, n_inb, n_hits, n_exact, n_oob, n_ties, n_runaway};
-    const int slot[7] = {0, 1, 2, 3, 4, 5, 7};
+                                               unsigned n_oob, unsigned n_ties, unsigned n_runaway, unsigned n_f64 = 0, unsigned n_skip = 0) {
+    unsigned long long c[9] = {n_samples, n_inb, n_hits, n_exact, n_oob, n_ties, n_runaway, n_f64, n_skip};
+    const int slot[9] = {0, 1, 2, 3, 4, 5, 7, 8, 9};
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
+    for (int j = 0; j < 9; j++) {
         for (int o = 16; o; o >>= 1) c[j] += __shfl_down_sync(0xffffffffu, c[j], o);
         if ((threadIdx.x & 31) == 0 && c[j]) atomicAdd(counters + slot[j], c[j]);
     }
@@ -127,12 +189,12 @@ __device__ __forceinline__ void flush_counters(u64* counters, unsigned n_samples
 
 // FAST = true : one thread per occupied voxel (grid.x covers n_occ), reverseRayTraceFast :136-226
 // FAST = false: one thread per visited position of the float-accumulated whole-grid scan, reverseRayTrace :45-134
-template <bool FAST>
+template <bool FAST, int FMT>
 __global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
     const VolDev& v = a.vol;
     const int view = blockIdx.y;
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    unsigned n_samples = 0, n_inb = 0, n_hits = 0, n_exact = 0, n_oob = 0, n_ties = 0, n_runaway = 0;
+    unsigned n_samples = 0, n_inb = 0, n_hits = 0, n_exact = 0, n_oob = 0, n_ties = 0, n_runaway = 0, n_f64 = 0, n_skip = 0;
     const float* T = a.poses + 12 * (size_t)view;
     const float* I = a.inv_poses + 12 * (size_t)view;
     bool live = true;
@@ -176,7 +238,7 @@ __global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
             float vx = __fsub_rn(__ldg(T + 3), cx), vy = __fsub_rn(__ldg(T + 7), cy), vz = __fsub_rn(__ldg(T + 11), cz);
             const float n2 = sum3(__fmul_rn(vx, vx), __fmul_rn(vy, vy), __fmul_rn(vz, vz));
             if (n2 > 0.0f) { const float s = __fsqrt_rn(n2); vx = __fdiv_rn(vx, s); vy = __fdiv_rn(vy, s); vz = __fdiv_rn(vz, s); }
-            const bool collided = march_collides<0>(a, cx, cy, cz, vx, vy, vz, chash, FAST ? 50 : 1, n_samples, n_inb, n_exact, n_runaway);
+            const bool collided = march_collides<FMT>(a, cx, cy, cz, vx, vy, vz, chash, FAST ? 50 : 1, n_samples, n_inb, n_exact, n_runaway, n_f64, n_skip);
             if (!collided) {
                 n_hits++;
                 if (a.found_any) a.found_any[view] = 1;
@@ -200,7 +262,7 @@ __global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
             }
         }
     }
-    flush_counters(a.counters, n_samples, n_inb, n_hits, n_exact, n_oob, n_ties, n_runaway);
+    flush_counters(a.counters, n_samples, n_inb, n_hits, n_exact, n_oob, n_ties, n_runaway, n_f64, n_skip);
 }
 
 // visibility bitset -> occupied ordinals in ascending order (= emission order of reverseRayTraceFast), one block per view

@@ -65,6 +65,8 @@ SYMBOLS = {
     "dmf_greedy_set_cover_dev": (C.c_int, [vp, vp, C.c_int, C.c_size_t, i32p, ip]),
     "dmf_or_reduce_dev": (C.c_int, [vp, vp, vp, C.c_int, C.c_size_t, vp]),
     "dmf_host_angle_test": (C.c_int, [fp]),
+    "dmf_set_reverse_format": (C.c_int, [vp, C.c_int]),
+    "dmf_selftest_div1000": (C.c_int, [vp, u64p]),
     "dmf_counters": (C.c_int, [vp, u64p]),
     "dmf_reset_counters": (C.c_int, [vp]),
     "dmf_last_kernel_ms": (C.c_int, [vp, fp]),

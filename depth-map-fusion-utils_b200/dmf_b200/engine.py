@@ -84,6 +84,15 @@ class Context:
         check(self.lib.dmf_last_hot_kernel_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def set_reverse_format(self, grid_format: int):
+        """GRID_BYTE (default): the reverse march skips provably empty steps via distance bytes; GRID_BIT: every step."""
+        check(self.lib.dmf_set_reverse_format(self.h, int(grid_format)))
+
+    def selftest_div1000(self):
+        out = np.zeros(5, np.uint64)
+        check(self.lib.dmf_selftest_div1000(self.h, _ptr(out, C.c_uint64)))
+        return [int(x) for x in out]
+
     def synchronize(self):
         check(self.lib.dmf_synchronize(self.h))
 

@@ -136,6 +136,9 @@ typedef struct {
 
 /* fast = 1: reverseRayTraceFast (:136-226); fast = 0: reverseRayTrace (:45-134).  viz != 0 also updates
  * Voxel::view / Voxel::good on the device (dmf_download_marks). */
+/* Grid the reverse march probes: DMF_GRID_BYTE (default; distance bytes, skips provably empty steps) or DMF_GRID_BIT
+ * (every step evaluated).  Results and counters are identical. */
+int dmf_set_reverse_format(dmf_ctx* ctx, int grid_format);
 int dmf_reverse(dmf_ctx* ctx, int fast, int viz, const float* poses, int n_views, const dmf_reverse_out* out);
 int dmf_reverse_dev(dmf_ctx* ctx, int fast, int viz, const float* d_poses, int n_views, const dmf_reverse_out* d_out, void* stream);
 
@@ -159,6 +162,11 @@ int dmf_or_reduce_dev(dmf_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int 
  * depends on the HOST libm's float acos.  The library bisects it once; the kernels then test dot_min <= d <= 1.
  * out[0] = dot_min, out[1..2] = [band_lo, band_hi) where the host acosf was seen non-monotonic (empty if lo >= hi). */
 int dmf_host_angle_test(float out[3]);
+
+/* GPU self-test: exhaustive comparison (all 2^32 float inputs) of the kernels' division-free `x / 1000.0f` against the
+ * IEEE division the reference performs (RayTracingEngine.hpp:82,173).  mismatches[0] = the two-step form the kernels use
+ * (must be 0), mismatches[1] = the one-step form (informational). */
+int dmf_selftest_div1000(dmf_ctx* ctx, uint64_t mismatches[5]);
 
 /* ---- counters ---------------------------------------------------------------------------------- */
 enum {

@@ -22,15 +22,32 @@ def _poses(dmf, sc):
     return np.stack([dmf.scenes.pose_p1(L)[0]] + list(dmf.scenes.poses_sphere_lookat(L, 300)[::60]) + list(dmf.scenes.poses_position_camera(L, 40)[[7, 23]]))
 
 
+@pytest.fixture(autouse=True)
+def _default_reverse_format(dmf, ctx):
+    yield
+    ctx.set_reverse_format(dmf.GRID_BYTE)
+
+
+def test_div1000_exhaustive(ctx):
+    """every float bit pattern: the division-free x/1000 of the reverse march == IEEE division wherever the kernels use it"""
+    long_bad, short_bad, hi_bits, lo_bits, short_bad_above = ctx.selftest_div1000()
+    assert short_bad_above == 0                         # one-correction form exact for all finite |a| > 2^-101
+    assert hi_bits < 0x0d000000                         # every finite failure of the two-step form lies below 2^-101 too
+    assert long_bad < 100000 and short_bad < 100000     # (subnormal quotients, -0, +-inf only)
+
+
 @pytest.mark.parametrize("name", ["S64", "S128", "S128-odd", "S128-clutter", "S256"])
-def test_reverse_fast(dmf, oracle, ctx, name):
+@pytest.mark.parametrize("fmt", [1, 0])
+def test_reverse_fast(dmf, oracle, ctx, name, fmt):
     sc, ov, gv = _pair(dmf, oracle, ctx, name)
     K = dmf.scenes.REFERENCE_K
     eng = dmf.RayTracingEngine(dmf.Camera(K), ctx)
+    ctx.set_reverse_format(fmt)
     poses = _poses(dmf, sc)
     ctx.reset_counters()
     g = eng.reverse_views(gv, poses, fast=True, viz=False)
     cnt = ctx.counters()
+    assert (cnt["skipped"] > 0) == (fmt == 1)
     occ = gv.occupied_cells_
     tot = dict(samples=0, inbounds=0, hits=0)
     n_vis = 0
@@ -64,12 +81,14 @@ def test_reverse_fast_viz_marks(dmf, oracle, ctx):
 
 
 @pytest.mark.parametrize("name", ["S64", "S128", "S256"])
-def test_reverse_whole_grid(dmf, oracle, ctx, name):
+@pytest.mark.parametrize("fmt", [1, 0])
+def test_reverse_whole_grid(dmf, oracle, ctx, name, fmt):
     """reverseRayTrace: float-accumulated whole-grid scan.  S256 is dyadic (scan visits each voxel once);
     S64/S128 (8/16 mm voxels on a 1.024 m cube) exercise the drifting float loop positions."""
     sc, ov, gv = _pair(dmf, oracle, ctx, name)
     K = dmf.scenes.REFERENCE_K
     eng = dmf.RayTracingEngine(dmf.Camera(K), ctx)
+    ctx.set_reverse_format(fmt)
     gv._commit(ctx); gv.clear_marks(); ov.clear_marks()
     any_found = False
     for p in _poses(dmf, sc)[:4]:
