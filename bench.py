@@ -129,6 +129,8 @@ def cpu_baseline(scenes, n_views_serial=2, with_all_cores=True) -> dict:
     out = {"value": n_views_serial * H * W / sec, "unit": "rays/s", "cores": 1, "kind": "port",
            "sample": f"{n_views_serial} views of the same workload, 1 thread, reference vector<vector<vector<Voxel*>>> grid; the reference hot path is single-threaded",
            "sec_per_view": sec / n_views_serial}
+    secr, _ = O.time_views(vol, K, H, W, poses[:1], 11, sc.zdelta, False, threads=1)
+    out["reverse_sweep"] = {"views_per_s": 1.0 / secr, "sample": "1 view of reverseRayTraceFast incl. its dead getNeighborHashes work, 1 thread", "sec_per_view": secr}
     if with_all_cores:
         nt = O.max_threads()
         nv = max(nt, 2)
@@ -316,6 +318,30 @@ def run_b200(args):
     for p in (p0, p1, p2, p3, p4):
         ctx.lib.dmf_host_free(p)
 
+    # ---- secondary: the sweep the shipped drivers run (tests/SetCover.cpp:218-240): reverseRayTraceFast per view,
+    # host poses in, per-view visibility bitsets out, through dmf_reverse
+    from dmf_b200._lib import ReverseOut
+    rv_vis = np.zeros((V, max(vw, 1)), np.uint64)
+    rv_found = np.zeros(V, np.int32)
+    ro = ReverseOut()
+    ro.visibility, ro.found_any = rv_vis.ctypes.data, rv_found.ctypes.data
+    pp = np.ascontiguousarray(poses)
+    ppf = pp.ctypes.data_as(C.POINTER(C.c_float))
+    for _ in range(2):
+        check(ctx.lib.dmf_reverse(ctx.h, 1, 0, ppf, V, C.byref(ro)))
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rv_steps = max(3, min(args.steps, 10))
+    for _ in range(rv_steps):
+        check(ctx.lib.dmf_reverse(ctx.h, 1, 0, ppf, V, C.byref(ro)))
+    torch.cuda.synchronize(); barrier()
+    rv_s = time.perf_counter() - t0
+    rv_hot = ctx.last_hot_kernel_ms()
+    t = torch.tensor([rv_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    rv_s = float(t.item())
+
     if rank == 0:
         peak, peak_src = measured_peak()
         # algorithmic bytes of one k_forward launch: 1/8 B (bit grid) or 1 B (byte grid) per in-bounds sample,
@@ -347,6 +373,9 @@ def run_b200(args):
             "gpu_launches": int(launches_total),
             "probes": {"reference_equivalent_per_step": samples_total / args.steps, "in_bounds_per_step": inbounds_total / args.steps,
                        "skipped_as_provably_empty_per_step": skipped_total / args.steps, "redone_in_f64_per_step": f64_total / args.steps},
+            "reverse_sweep": {"what": "reverseRayTraceFast over the same views via dmf_reverse (host poses in, visibility bitsets out)",
+                              "views_per_s": rv_steps * V * world / rv_s, "voxel_rays_per_s": rv_steps * V * world * n_occ / rv_s,
+                              "ms_per_step": 1e3 * rv_s / rv_steps, "kernel_ms_per_step": rv_hot},
             "clocks": clocks,
             "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
         }

@@ -214,3 +214,51 @@ def test_full_size_properties_512(dmf, ctx):
         assert len(uniq) == len(a["ids"][i]) == int(np.unpackbits(a["visibility"][i].view(np.uint8)).sum())
         assert np.array_equal(np.sort(a["ids"][i]), uniq)
         assert np.isin(uniq, gv.occupied_cells_).all()
+
+
+def test_config3_1024_grid_against_oracle(dmf, oracle, ctx):
+    """BASELINE.json configs[3]: 1024^3 grid (0.977 mm voxels, zdelta = 1 mm).  Oracle on a 320x240 camera to keep it to seconds."""
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S1024")
+    assert sc.zdelta == 1 and len(ov.occupied()) == 565496
+    K = dmf.scenes.REFERENCE_K.copy(); K[[0, 2, 4, 5]] *= 0.5
+    poses = np.stack([dmf.scenes.pose_p1(1.0)[0], dmf.scenes.poses_helix(1.0, 40)[17]])
+    for fmt in (1, 0):
+        cnt = _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, 0, 1, False, grid_format=fmt, H=240, W=320, K=K)
+        assert cnt["f64_path"] == 0 and cnt["skipped"] > 0.8 * cnt["inbounds"]
+
+
+def test_config4_1080p_camera_against_oracle(dmf, oracle, ctx):
+    """BASELINE.json configs[4] camera: 1080x1920 with 3x intrinsics (2 073 600 rays: close to the 2^21 limit of the id-list keys)."""
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S128")
+    K = dmf.scenes.scaled_K(3.0)
+    poses = dmf.scenes.poses_fibonacci(float(sc.bounds[1]), 50)[[21]]
+    _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, 0, sc.zdelta, False, grid_format=1, H=1080, W=1920, K=K)
+
+
+def test_full_size_properties_1024_1080p(dmf, ctx):
+    """configs[4] at full size without the oracle: 1080x1920 into 1024^3 -- distance bytes == bit grid == brute force,
+    counters identical, id list == unique hit voxels == visibility popcount."""
+    sc = dmf.scenes.scene("S1024")
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+    K = dmf.scenes.scaled_K(3.0)
+    poses = dmf.scenes.poses_fibonacci(1.0, 64)[[5, 40]]
+    res, cnts = [], []
+    for fmt, skip in ((dmf.GRID_BYTE, True), (dmf.GRID_BIT, True), (dmf.GRID_BIT, False)):
+        eng = dmf.RayTracingEngine(dmf.Camera(K, 1080, 1920), ctx, fmt, skip_empty=skip)
+        ctx.reset_counters()
+        res.append(eng.forward_views(gv, poses, 0, 1, False, want=("depth", "voxel", "visibility", "ids")))
+        cnts.append(ctx.counters())
+    for r in res[1:]:
+        for k in ("depth", "voxel", "visibility"):
+            assert np.array_equal(res[0][k], r[k]), k
+        assert all(np.array_equal(a, b) for a, b in zip(res[0]["ids"], r["ids"]))
+    for c in cnts[1:]:
+        assert (c["samples"], c["inbounds"], c["hits"]) == (cnts[0]["samples"], cnts[0]["inbounds"], cnts[0]["hits"])
+    a = res[0]
+    for i in range(len(poses)):
+        hit = a["depth"][i] >= 0
+        uniq = np.unique(a["voxel"][i][hit])
+        assert hit.sum() > 100000
+        assert len(uniq) == len(a["ids"][i]) == int(np.unpackbits(a["visibility"][i].view(np.uint8)).sum())
+        assert np.array_equal(np.sort(a["ids"][i]), uniq)
