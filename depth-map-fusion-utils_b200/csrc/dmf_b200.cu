@@ -245,8 +245,11 @@ template <int MODE>
 void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, dim3 grid, cudaStream_t st) {
     if (skip) {
         dim3 g((a.Wc + SKIP_TILE_W - 1) / SKIP_TILE_W, (a.Hc + SKIP_TILE_H - 1) / SKIP_TILE_H, grid.z);
-        if (fmt == DMF_GRID_BYTE) k_forward_skip<MODE, 1><<<g, SKIP_THREADS, 0, st>>>(a);
-        else k_forward_skip<MODE, 0><<<g, SKIP_THREADS, 0, st>>>(a);
+        const bool exact = a.vol.err32[0] == 0.0f && a.vol.err32[1] == 0.0f && a.vol.err32[2] == 0.0f;
+        if (fmt == DMF_GRID_BYTE) {
+            if (exact) k_forward_dist<MODE, true><<<g, SKIP_THREADS, 0, st>>>(a);
+            else k_forward_dist<MODE, false><<<g, SKIP_THREADS, 0, st>>>(a);
+        } else k_forward_skip<MODE, 0><<<g, SKIP_THREADS, 0, st>>>(a);
     } else {
         if (fmt == DMF_GRID_BYTE) k_forward<MODE, 1><<<grid, FWD_THREADS, 0, st>>>(a);
         else k_forward<MODE, 0><<<grid, FWD_THREADS, 0, st>>>(a);

@@ -127,17 +127,17 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
 
     // ---- counters: warp reduce -> shared; the LAST warp of the block to get here flushes them with a few global atomics.
     // No block barrier: warps whose rays ended early must not sit on a barrier waiting for the longest ray of the block.
-    unsigned long long c0 = n_samples, c1 = n_inb, c2 = hit ? 1u : 0u, c3 = n_exact, c5 = ties, c8 = n_f64, c9 = n_skip;
-    for (int o = 16; o; o >>= 1) {
-        c0 += __shfl_down_sync(0xffffffffu, c0, o); c1 += __shfl_down_sync(0xffffffffu, c1, o);
-        c2 += __shfl_down_sync(0xffffffffu, c2, o); c3 += __shfl_down_sync(0xffffffffu, c3, o);
-        c5 += __shfl_down_sync(0xffffffffu, c5, o); c8 += __shfl_down_sync(0xffffffffu, c8, o); c9 += __shfl_down_sync(0xffffffffu, c9, o);
-    }
+    const unsigned c0 = __reduce_add_sync(0xffffffffu, n_samples), c1 = __reduce_add_sync(0xffffffffu, n_inb);
+    const unsigned c2 = __reduce_add_sync(0xffffffffu, hit ? 1u : 0u), c9 = __reduce_add_sync(0xffffffffu, n_skip);
+    const unsigned c358 = __reduce_add_sync(0xffffffffu, n_exact | ties | n_f64);      // almost always 0: reduce individually only then
+    unsigned c3 = 0, c5 = 0, c8 = 0;
+    if (c358) { c3 = __reduce_add_sync(0xffffffffu, n_exact); c5 = __reduce_add_sync(0xffffffffu, ties); c8 = __reduce_add_sync(0xffffffffu, n_f64); }
     if (lane == 0) {
-        atomicAdd(&s_cnt[0], c0); atomicAdd(&s_cnt[1], c1); atomicAdd(&s_cnt[2], c2); atomicAdd(&s_cnt[3], c9);
-        if (c3) atomicAdd(a.counters + 3, c3);
-        if (c5) atomicAdd(a.counters + 5, c5);
-        if (c8) atomicAdd(a.counters + 8, c8);
+        atomicAdd(&s_cnt[0], (unsigned long long)c0); atomicAdd(&s_cnt[1], (unsigned long long)c1);
+        atomicAdd(&s_cnt[2], (unsigned long long)c2); atomicAdd(&s_cnt[3], (unsigned long long)c9);
+        if (c3) atomicAdd(a.counters + 3, (unsigned long long)c3);
+        if (c5) atomicAdd(a.counters + 5, (unsigned long long)c5);
+        if (c8) atomicAdd(a.counters + 8, (unsigned long long)c8);
         __threadfence_block();
         const unsigned long long ticket = atomicAdd(&s_cnt[4], 1ull);
         if (ticket == (unsigned long long)(blockDim.x >> 5) - 1ull) {
@@ -416,6 +416,156 @@ __global__ void __launch_bounds__(SKIP_THREADS, 8) k_forward_skip(const FwdArgs 
                 }
                 k += n + 1; kf += (float)(n + 1);
             }
+        }
+    }
+    const unsigned n_samples = active ? (unsigned)min(k, S) : 0u;
+    forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23, n_samples, n_inb, n_exact, n_f64, n_skip);
+}
+
+// ---- K1 on distance bytes: k_forward_dist ---------------------------------------------------------------------
+// DMF_GRID_BYTE march.  Every exactly evaluated probe reads its voxel's distance byte d (dmf_distance.cuh): 0 = hit;
+// d >= 2 proves the next floor((d - 1.25) / max|QB|) probes are in-bounds misses (same error budget as k_forward_skip:
+// eps_q <= 0.1 voxel per probe, 0.25 voxel margin), so they are counted and skipped.  Two consecutive probes (k, k+1) are
+// evaluated per iteration so that their table and grid loads are in flight together; the second is used only if the
+// first neither hits nor skips.  EXACT: every axis has err32 == 0 (power-of-two voxel size, vmin == 0): the float
+// quotient is exact and floor() is one round-down add.
+template <bool EXACT>
+__device__ __forceinline__ unsigned probe_index(const VolDev& v, float px, float py, float pz, float in0, float in1, float in2,
+                                                float cc0, float cc1, float cc2, float er0, float er1, float er2, unsigned pny, unsigned pnz,
+                                                int& ix, int& iy, int& iz, unsigned& n_f64, unsigned& n_exact) {
+    const float kM = 12582912.0f;
+    if (EXACT) {
+        ix = __float_as_int(__fadd_rd(fmaf(px, in0, cc0), kM)) - 0x4B400000;
+        iy = __float_as_int(__fadd_rd(fmaf(py, in1, cc1), kM)) - 0x4B400000;
+        iz = __float_as_int(__fadd_rd(fmaf(pz, in2, cc2), kM)) - 0x4B400000;
+    } else {
+        bool unsafe = false;
+        ix = voxel_index_f32(px, in0, cc0, er0, unsafe);
+        iy = voxel_index_f32(py, in1, cc1, er1, unsafe);
+        iz = voxel_index_f32(pz, in2, cc2, er2, unsafe);
+        if (unsafe) {
+            n_f64++;
+            ix = voxel_index(px, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+            iy = voxel_index(py, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+            iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+        }
+    }
+    return ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+}
+
+template <int MODE, bool EXACT>
+__global__ void __launch_bounds__(SKIP_THREADS, 8) k_forward_dist(const FwdArgs a) {
+    __shared__ unsigned long long s_cnt[5];
+    const int view = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
+    const int ri = blockIdx.y * SKIP_TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    const bool active = ci < a.Wc && ri < a.Hc;
+    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    const float* P = a.poses + 12 * (size_t)view;
+    const float m00 = __ldg(P + 0), m01 = __ldg(P + 1), m02 = __ldg(P + 2), m03 = __ldg(P + 3);
+    const float m10 = __ldg(P + 4), m11 = __ldg(P + 5), m12 = __ldg(P + 6), m13 = __ldg(P + 7);
+    const float m20 = __ldg(P + 8), m21 = __ldg(P + 9), m22 = __ldg(P + 10), m23 = __ldg(P + 11);
+    const VolDev& v = a.vol;
+    const float lo0 = v.lo[0], lo1 = v.lo[1], lo2 = v.lo[2], hi0 = v.hi[0], hi1 = v.hi[1], hi2 = v.hi[2];
+    const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2], cc0 = v.c32[0], cc1 = v.c32[1], cc2 = v.c32[2];
+    const float er0 = v.err32[0], er1 = v.err32[1], er2 = v.err32[2];
+    const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
+    const unsigned char* __restrict__ gbytes = v.bytes;
+
+    // slope of the ray in voxel units per probe (approximate; only steers skipping) and the per-view error bound
+    const int cic = active ? ci : 0, ric = active ? ri : 0;
+    const float dcx = __ldg(a.dcx + cic), dcy = __ldg(a.dcy + ric);
+    const float g0 = fmaf(m00, dcx, fmaf(m01, dcy, m02)), g1 = fmaf(m10, dcx, fmaf(m11, dcy, m12)), g2 = fmaf(m20, dcx, fmaf(m21, dcy, m22));
+    const float zdm = (float)a.zdelta * 0.001f;
+    const float qbmax = fmaxf(fabsf(zdm * g0 * in0), fmaxf(fabsf(zdm * g1 * in1), fabsf(zdm * g2 * in2)));
+    const float kEps = 9.5367431640625e-07f;   // 16 * 2^-24
+    const float e0 = kEps * (fabsf(m00) * a.dcx_max + fabsf(m01) * a.dcy_max + fabsf(m02) + fabsf(m03) + fabsf((float)v.vmin[0])) * fabsf(in0);
+    const float e1 = kEps * (fabsf(m10) * a.dcx_max + fabsf(m11) * a.dcy_max + fabsf(m12) + fabsf(m13) + fabsf((float)v.vmin[1])) * fabsf(in1);
+    const float e2 = kEps * (fabsf(m20) * a.dcx_max + fabsf(m21) * a.dcy_max + fabsf(m22) + fabsf(m23) + fabsf((float)v.vmin[2])) * fabsf(in2);
+    const bool skip_ok = fmaxf(e0, fmaxf(e1, e2)) <= 0.1f;   // NaN poses compare false: no skipping
+    // probes that may be skipped after a probe with distance byte d:  n(d) = ((4d - 5) * rfix) >> 12 <= (d - 1.25) / qbmax.
+    // rfix = floor(2^10 / qbmax) rounded down (<= 2^20 so the product stays below 2^31); 0 disables skipping.
+    const int rfix = skip_ok ? __float2int_rd(fminf(__fdividef(1024.0f, fmaxf(qbmax, 1e-3f)) * 0.999999f, 1048576.0f)) : 0;
+
+    int hit_k = -1, hx = 0, hy = 0, hz = 0;
+    float hpx = 0.f, hpy = 0.f, hpz = 0.f;
+    unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
+    int k = 0;
+    const int S = a.S;
+    const float* __restrict__ xt = a.xtab + cic;
+    const float* __restrict__ yt = a.ytab + ric;
+    const float* __restrict__ zt = a.ztab;
+    const int Wc = a.Wc, Hc = a.Hc;
+    unsigned iter = 0;
+    int oob_wait = 0;
+    if (active) {
+        while (k < S) {
+            if (MODE == 4 && (iter++ & 7u) == 0u) {   // rayTraceAndGetMinimum: planes behind the current minimum cannot matter
+                const int cur = *((volatile int*)(a.min_depth + view));
+                if (a.z0 + k * a.zdelta > cur) break;
+            }
+            // ---- probes A = k and B = k+1: loads first, so that both are in flight together ----
+            const int kb = min(k + 1, S - 1);
+            const float xa = __ldg(xt + k * Wc), ya = __ldg(yt + k * Hc), za = __ldg(zt + k);
+            const float xb = __ldg(xt + kb * Wc), yb = __ldg(yt + kb * Hc), zb = __ldg(zt + kb);
+            const float pxa = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, xa), __fmul_rn(m01, ya)), __fmul_rn(m02, za)), m03);
+            const float pya = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, xa), __fmul_rn(m11, ya)), __fmul_rn(m12, za)), m13);
+            const float pza = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, xa), __fmul_rn(m21, ya)), __fmul_rn(m22, za)), m23);
+            if (!(pxa > lo0 && pxa < hi0 && pya > lo1 && pya < hi1 && pza > lo2 && pza < hi2)) {
+                // validPoints failed: the reference just moves on.  Use the line to jump over the probes that are provably
+                // outside (some axis of the line > 0.25 voxel beyond the volume, eps_q <= 0.1); retried every few probes.
+                int kn = k + 1;
+                if (skip_ok && oob_wait == 0) {
+                    const float z0m = (float)a.z0 * 0.001f, kf = (float)k;
+                    const float qa[3] = {fmaf(fmaf(z0m, g0, m03), in0, cc0), fmaf(fmaf(z0m, g1, m13), in1, cc1), fmaf(fmaf(z0m, g2, m23), in2, cc2)};
+                    const float qb[3] = {zdm * g0 * in0, zdm * g1 * in1, zdm * g2 * in2};
+                    float t0 = -1e30f, t1 = 1e30f;
+#pragma unroll
+                    for (int ax = 0; ax < 3; ax++) {
+                        if (fabsf(qb[ax]) > 1e-12f) {
+                            const float r = 1.0f / qb[ax];
+                            const float ta = (-0.25f - qa[ax]) * r, tb = (v.ext[ax] + 0.25f - qa[ax]) * r;
+                            t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+                        } else if (qa[ax] < -0.25f || qa[ax] > v.ext[ax] + 0.25f) { t0 = 1e30f; }
+                    }
+                    if (!(t0 <= t1) || t1 + 1.0f < kf) kn = S;                               // never (again) inside the volume
+                    else if (t0 - 1.0f > kf + 1.0f) kn = min(S, max(k + 1, __float2int_rd(t0 - 1.0f)));
+                    if (kn == k + 1) oob_wait = 4;
+                } else if (oob_wait > 0) oob_wait--;
+                k = kn;
+                continue;
+            }
+            oob_wait = 0;
+            const float pxb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, xb), __fmul_rn(m01, yb)), __fmul_rn(m02, zb)), m03);
+            const float pyb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, xb), __fmul_rn(m11, yb)), __fmul_rn(m12, zb)), m13);
+            const float pzb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, xb), __fmul_rn(m21, yb)), __fmul_rn(m22, zb)), m23);
+            const bool inb_b = (k + 1 < S) && pxb > lo0 && pxb < hi0 && pyb > lo1 && pyb < hi1 && pzb > lo2 && pzb < hi2;
+            int ixa, iya, iza, ixb = 0, iyb = 0, izb = 0;
+            const unsigned idxa = probe_index<EXACT>(v, pxa, pya, pza, in0, in1, in2, cc0, cc1, cc2, er0, er1, er2, pny, pnz, ixa, iya, iza, n_f64, n_exact);
+            const unsigned da = __ldg(gbytes + idxa);
+            unsigned db = 1u;
+            if (inb_b) {
+                const unsigned idxb = probe_index<EXACT>(v, pxb, pyb, pzb, in0, in1, in2, cc0, cc1, cc2, er0, er1, er2, pny, pnz, ixb, iyb, izb, n_f64, n_exact);
+                db = __ldg(gbytes + idxb);
+            }
+            n_inb++;
+            if (da == 0u) { hit_k = k; hx = ixa; hy = iya; hz = iza; hpx = pxa; hpy = pya; hpz = pza; k++; break; }
+            const int na = min(((int)(4u * da) - 5) * rfix >> 12, S - k - 1);       // da >= 1: (4*da-5) >= -1, and -1*rfix>>12 is -1 or 0
+            if (na >= 1 || !inb_b) {
+                const int n = max(na, 0);
+                n_inb += (unsigned)n; n_skip += (unsigned)n;
+                k += n + 1;                                                         // (an out-of-bounds B is re-examined as the next A)
+                continue;
+            }
+            // A neither hit nor skipped: B is the next probe of this ray
+            n_inb++;
+            if (db == 0u) { hit_k = k + 1; hx = ixb; hy = iyb; hz = izb; hpx = pxb; hpy = pyb; hpz = pzb; k += 2; break; }
+            const int nb = max(min(((int)(4u * db) - 5) * rfix >> 12, S - k - 2), 0);
+            n_inb += (unsigned)nb; n_skip += (unsigned)nb;
+            k += nb + 2;
         }
     }
     const unsigned n_samples = active ? (unsigned)min(k, S) : 0u;
