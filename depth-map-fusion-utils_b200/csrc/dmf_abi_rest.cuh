@@ -191,6 +191,80 @@ int dmf_zbuffer(dmf_ctx* c, const float pose[12], int32_t* depth, int64_t* n_spl
     return 0;
 }
 
+int dmf_segments_collide(dmf_ctx* c, const float* a, const float* b, int n, int guard_coords, uint8_t* out) {
+    if (!c || (!a && n > 0) || (!b && n > 0) || (!out && n > 0)) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    if (!c->vol_set) return fail("no volume uploaded");
+    if (n <= 0) return 0;
+    cudaStream_t st = c->stream;
+    if (c->reverse_format == DMF_GRID_BYTE) DMF_TRY(ensure_bytes(c, st));
+    DMF_TRY(c->d_misc[0].reserve((size_t)n * 12)); DMF_TRY(c->d_misc[1].reserve((size_t)n * 12)); DMF_TRY(c->d_misc[2].reserve((size_t)n));
+    DMF_CUDA(cudaMemcpyAsync(c->d_misc[0].p, a, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    DMF_CUDA(cudaMemcpyAsync(c->d_misc[1].p, b, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    DMF_CUDA(cudaEventRecord(c->ev_h0, st));
+    if (c->reverse_format == DMF_GRID_BYTE)
+        k_segments_collide<1><<<(n + 127) / 128, 128, 0, st>>>(c->vol, c->d_misc[0].as<float>(), c->d_misc[1].as<float>(), n, guard_coords, c->d_misc[2].as<unsigned char>(), c->d_counters.as<u64>());
+    else
+        k_segments_collide<0><<<(n + 127) / 128, 128, 0, st>>>(c->vol, c->d_misc[0].as<float>(), c->d_misc[1].as<float>(), n, guard_coords, c->d_misc[2].as<unsigned char>(), c->d_counters.as<u64>());
+    DMF_CUDA(cudaEventRecord(c->ev_h1, st));
+    c->hot_timed = true;
+    c->launches++;
+    DMF_CUDA(cudaGetLastError());
+    DMF_CUDA(cudaMemcpyAsync(out, c->d_misc[2].p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    DMF_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// Algorithms::moveCamera / repositionCamera (Algorithms.hpp:170-188) in float: t -= row2(linear) * distance / 1000
+static void reposition_camera(const float* pose12, unsigned distance, float* out12) {
+    std::memcpy(out12, pose12, 48);
+    const float d = (float)(double)distance;
+    for (int i = 0; i < 3; i++) {
+        volatile float prod = pose12[8 + i] * d;       // separate roundings, as Eigen evaluates n*distance/1000.0
+        volatile float q = prod / 1000.0f;
+        out12[4 * i + 3] = pose12[4 * i + 3] - q;
+    }
+}
+
+int dmf_optimize_standoff(dmf_ctx* c, const float* poses, int n, unsigned low0, unsigned high0, uint32_t* mid_out, float* poses_out) {
+    if (!c || (!poses && n > 0)) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    if (!c->vol_set) return fail("no volume uploaded");
+    if (n <= 0) return 0;
+    std::vector<unsigned> low(n, low0), high(n, high0), mid(n, low0);
+    cudaStream_t st = c->stream;
+    for (;;) {
+        std::vector<int> act;
+        for (int i = 0; i < n; i++) if (low[i] < high[i]) act.push_back(i);
+        if (act.empty()) break;
+        const int nv = 2 * (int)act.size();
+        std::vector<float> batch(12 * (size_t)nv);
+        for (size_t j = 0; j < act.size(); j++) {
+            reposition_camera(poses + 12 * (size_t)act[j], low[act[j]], &batch[12 * (2 * j)]);
+            reposition_camera(poses + 12 * (size_t)act[j], high[act[j]], &batch[12 * (2 * j + 1)]);
+        }
+        std::vector<unsigned> counts(nv, 0);
+        for (int v0 = 0; v0 < nv; v0 += 4096) {                       // reverseRayTrace launches one thread per scan position and view
+            const int m = std::min(4096, nv - v0);
+            DMF_TRY(c->d_poses[0].reserve((size_t)m * 48)); DMF_TRY(c->d_misc[1].reserve((size_t)m * 4));
+            DMF_CUDA(cudaMemcpyAsync(c->d_poses[0].p, &batch[12 * (size_t)v0], (size_t)m * 48, cudaMemcpyHostToDevice, st));
+            DMF_TRY(enqueue_reverse(c, /*fast=*/0, /*viz=*/0, c->d_poses[0].as<float>(), m, nullptr, nullptr, nullptr, nullptr, c->d_misc[1].as<unsigned>(), 0, st));
+            DMF_CUDA(cudaMemcpyAsync(&counts[v0], c->d_misc[1].p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            DMF_CUDA(cudaStreamSynchronize(st));
+        }
+        for (size_t j = 0; j < act.size(); j++) {                     // Algorithms.hpp:409-417
+            const int i = act[j];
+            mid[i] = (low[i] + high[i]) / 2;
+            if (counts[2 * j + 1] > counts[2 * j]) low[i] = mid[i] + 1; else high[i] = mid[i];
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        if (mid_out) mid_out[i] = mid[i];
+        if (poses_out) reposition_camera(poses + 12 * (size_t)i, mid[i], poses_out + 12 * (size_t)i);
+    }
+    return 0;
+}
+
 int dmf_set_reverse_format(dmf_ctx* c, int grid_format) {
     if (!c) return fail("null context");
     if (grid_format != DMF_GRID_BIT && grid_format != DMF_GRID_BYTE) return fail("bad grid_format %d", grid_format);

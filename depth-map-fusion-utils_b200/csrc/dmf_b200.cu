@@ -74,7 +74,7 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
     const size_t nbits = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
     const size_t nwords = ((nbits + 31) / 32 + 7) / 8 * 8;           // whole 8-word (256-bit) rank blocks
     const size_t nmacro = (size_t)v.mdim[0] * v.mdim[1] * v.mdim[2];
-    std::vector<uint32_t> words(nwords, 0), prefix(nwords / 8, 0), macro((nmacro + 31) / 32, 0);
+    std::vector<uint32_t> words(nwords, 0), prefix(nwords, 0), macro((nmacro + 31) / 32, 0);
     auto locate = [&](uint64_t id, size_t& idx) -> bool {
         const uint64_t mask = (1u << 20) - 1;
         long long x = (long long)(id >> 40), y = (long long)((id >> 20) & mask), z = (long long)(id & mask);   // getVoxelCoords :158-165
@@ -90,15 +90,14 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
         if ((words[idx >> 5] >> (idx & 31)) & 1u) return fail("duplicate occupied id %llu (#%zu)", (unsigned long long)ids[i], i);
         words[idx >> 5] |= 1u << (idx & 31);
     }
-    std::vector<uint32_t> word_rank(nwords);
+    std::vector<uint32_t>& word_rank = prefix;
     uint32_t run = 0;
-    for (size_t w = 0; w < nwords; w++) { if ((w & 7) == 0) prefix[w >> 3] = run; word_rank[w] = run; run += (uint32_t)__builtin_popcount(words[w]); }
+    for (size_t w = 0; w < nwords; w++) { prefix[w] = run; run += (uint32_t)__builtin_popcount(words[w]); }
     std::vector<uint32_t> rank2occ(std::max<size_t>(n_occ, 1));
     for (size_t i = 0; i < n_occ; i++) {
         size_t idx; locate(ids[i], idx);
         rank2occ[word_rank[idx >> 5] + __builtin_popcount(words[idx >> 5] & ((1u << (idx & 31)) - 1u))] = (uint32_t)i;
     }
-    std::vector<uint32_t>().swap(word_rank);
     // Chebyshev distance (in macro cells) from every macro cell to the nearest "blocked" cell: one that holds an occupied
     // voxel, is not entirely inside [0,dim) on every axis, or lies outside the grid.  Box dilation is separable, so each
     // radius step is three 1-D passes.  clearance = 8*(D-1) - 0.25 voxels for D >= 2, else 0 (see k_forward_skip).

@@ -14,7 +14,7 @@ typedef unsigned long long u64;
 //            (pdim = dim + 1 per axis, z fastest like voxels_[x][y][z]); bit index = (x*pdim_y + y)*pdim_z + z.
 //            The padding plane is always empty: a probe whose quotient rounds up to exactly `dim` (the reference
 //            reads out of bounds there) lands on it, so the forward march needs no index range check.
-//   prefix   uint32 per 8 words (256 bits): number of occupied voxels before that block (rank directory)
+//   prefix   uint32 per word: number of occupied voxels in all earlier words (rank directory; one load + one popc per hit)
 //   rank2occ [n_occ] rank (linear order) -> index into occupied_cells_
 //   bytes    optional per-voxel Chebyshev distance bytes over the same padded index space, 0 = occupied
 //            (DMF_GRID_BYTE, dmf_distance.cuh)
@@ -106,9 +106,7 @@ __device__ __forceinline__ bool occupied(const VolDev& v, int x, int y, int z) {
 __device__ __forceinline__ int occupied_ordinal(const VolDev& v, int x, int y, int z) {
     const unsigned idx = linear_index(v, x, y, z);
     const unsigned w = idx >> 5;
-    unsigned rank = __ldg(v.prefix + (w >> 3));
-    for (unsigned j = w & ~7u; j < w; j++) rank += __popc(__ldg(v.bits + j));
-    rank += __popc(__ldg(v.bits + w) & ((1u << (idx & 31)) - 1u));
+    const unsigned rank = __ldg(v.prefix + w) + __popc(__ldg(v.bits + w) & ((1u << (idx & 31)) - 1u));
     return (int)__ldg(v.rank2occ + rank);
 }
 

@@ -251,9 +251,9 @@ __global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
                 if (emit) {
                     if (a.viz) atomicOr(a.good_bits + (occ >> 5), 1u << (occ & 31)); // :112, :215
                     if (a.vis) atomicOr(a.vis + (size_t)view * a.vis_words32 + (occ >> 5), 1u << (occ & 31));
-                    if (!FAST && a.emit_list) {
+                    if (!FAST && a.emit_count) {
                         unsigned slot = atomicAdd(a.emit_count + view, 1u);
-                        if (slot < a.emit_cap) {
+                        if (a.emit_list && slot < a.emit_cap) {
                             a.emit_list[2 * ((size_t)view * a.emit_cap + slot)] = (u64)t;
                             a.emit_list[2 * ((size_t)view * a.emit_cap + slot) + 1] = chash;
                         }
@@ -263,6 +263,81 @@ __global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
         }
     }
     flush_counters(a.counters, n_samples, n_inb, n_hits, n_exact, n_oob, n_ties, n_runaway, n_f64, n_skip);
+}
+
+// ---- K7: willCollide (tests/CameraPathGen.cpp:128-156 and the unguarded copies in CameraMotionTSP.cpp:236-261,
+// CameraMotionPlanner.cpp:246-271), one thread per segment a->b: 1 mm float march `a + v*double(depth)/1000.0` while
+// depth <= |a-b|*1000; samples outside the volume are skipped (continue), an occupied voxel ends the march.
+// FMT 1 skips provably empty in-bounds steps through the distance bytes exactly like march_collides.
+template <int FMT>
+__global__ void __launch_bounds__(128) k_segments_collide(const VolDev v, const float* __restrict__ A, const float* __restrict__ B, int n,
+                                                          int guard_coords, unsigned char* __restrict__ out, u64* counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n_samples = 0, n_inb = 0, n_hits = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
+    if (i < n) {
+        const float ax = A[3 * i], ay = A[3 * i + 1], az = A[3 * i + 2], bx = B[3 * i], by = B[3 * i + 1], bz = B[3 * i + 2];
+        const float ex = __fsub_rn(ax, bx), ey = __fsub_rn(ay, by), ez = __fsub_rn(az, bz);
+        const double distance = (double)__fsqrt_rn(sum3(__fmul_rn(ex, ex), __fmul_rn(ey, ey), __fmul_rn(ez, ez)));   // (a-b).norm()
+        float vx = __fsub_rn(bx, ax), vy = __fsub_rn(by, ay), vz = __fsub_rn(bz, az);                                // (b-a).normalized()
+        const float n2 = sum3(__fmul_rn(vx, vx), __fmul_rn(vy, vy), __fmul_rn(vz, vz));
+        if (n2 > 0.0f) { const float s = __fsqrt_rn(n2); vx = __fdiv_rn(vx, s); vy = __fdiv_rn(vy, s); vz = __fdiv_rn(vz, s); }
+        // `if(depth > distance*1000) break;`  <=>  run while depth <= floor(distance*1000)
+        const double lim = floor(__dmul_rn(distance, 1000.0));
+        const int dmax = lim >= 1.0e9 ? 1000000000 : (lim >= 0.0 ? (int)lim : 0);       // NaN/negative: no step passes the test
+        const float lo0 = v.lo[0], lo1 = v.lo[1], lo2 = v.lo[2], hi0 = v.hi[0], hi1 = v.hi[1], hi2 = v.hi[2];
+        const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2], cc0 = v.c32[0], cc1 = v.c32[1], cc2 = v.c32[2];
+        const float er0 = v.err32[0], er1 = v.err32[1], er2 = v.err32[2];
+        const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
+        const bool fast_div = fminf(fabsf(vx), fminf(fabsf(vy), fabsf(vz))) >= 7.888609052210118e-31f;
+        const float step = fmaxf(fabsf(vx) * fabsf(in0), fmaxf(fabsf(vy) * fabsf(in1), fabsf(vz) * fabsf(in2))) * 0.001f;
+        const float rq = 1.0f / fmaxf(step, 1e-3f);
+        const bool skip_ok = FMT == 1 && fmaxf(v.rev_eps[0], fmaxf(v.rev_eps[1], v.rev_eps[2])) <= 0.1f;
+        const float kM = 12582912.0f;
+        bool collided = false;
+        int depth = 1;
+        float s = 1.0f;
+        while (depth <= dmax) {
+            const float qx0 = __fmul_rn(vx, s), qy0 = __fmul_rn(vy, s), qz0 = __fmul_rn(vz, s);
+            float qx, qy, qz;
+            if (fast_div) { qx = div1000_short(qx0); qy = div1000_short(qy0); qz = div1000_short(qz0); }
+            else { qx = __fdiv_rn(qx0, 1000.0f); qy = __fdiv_rn(qy0, 1000.0f); qz = __fdiv_rn(qz0, 1000.0f); }
+            const float px = __fadd_rn(ax, qx), py = __fadd_rn(ay, qy), pz = __fadd_rn(az, qz);
+            n_samples++;
+            int nskip = 0;
+            if (px > lo0 && px < hi0 && py > lo1 && py < hi1 && pz > lo2 && pz < hi2) {
+                n_inb++;
+                bool unsafe = false;
+                int ix = voxel_index_f32(px, in0, cc0, er0, unsafe);
+                int iy = voxel_index_f32(py, in1, cc1, er1, unsafe);
+                int iz = voxel_index_f32(pz, in2, cc2, er2, unsafe);
+                if (unsafe) {
+                    n_f64++;
+                    ix = voxel_index(px, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+                    iy = voxel_index(py, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+                    iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+                }
+                // index == dim (the unguarded copies read out of range there): the padded plane is empty either way
+                if (!guard_coords || coords_valid(v, ix, iy, iz)) {
+                    const unsigned idx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+                    if (FMT == 0) {
+                        if ((__ldg(v.bits + (idx >> 5)) >> (idx & 31)) & 1u) { collided = true; break; }
+                    } else {
+                        const unsigned d = __ldg(v.bytes + idx);
+                        if (d == 0u) { collided = true; break; }
+                        if (skip_ok && d >= 2u) {
+                            const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
+                            nskip = min(__float_as_int(__fadd_rd((df - 1.25f) * rq, kM)) - 0x4B400000, dmax - depth);
+                            n_samples += (unsigned)nskip; n_inb += (unsigned)nskip; n_skip += (unsigned)nskip;
+                        }
+                    }
+                }
+            }
+            depth += nskip + 1; s += (float)(nskip + 1);
+        }
+        out[i] = collided ? 1 : 0;
+        n_hits = collided ? 1u : 0u;
+    }
+    flush_counters(counters, n_samples, n_inb, n_hits, n_exact, 0u, 0u, 0u, n_f64, n_skip);
 }
 
 // visibility bitset -> occupied ordinals in ascending order (= emission order of reverseRayTraceFast), one block per view

@@ -2,8 +2,8 @@
 from . import scenes
 from ._lib import DmfError, LIB_PATH, SYMBOLS, load
 from .engine import (GRID_BIT, GRID_BYTE, MODE_CLASSIFY, MODE_GOOD_POINTS, MODE_MARK, MODE_MINIMUM, MODE_POINTS, NO_VOXEL,
-                     Camera, Context, RayTracingEngine, VoxelVolume, bits_to_indices, greedySetCover)
+                     Camera, Context, RayTracingEngine, VoxelVolume, bits_to_indices, greedySetCover, optimizeCameraPosition, willCollide)
 
 __all__ = ["scenes", "DmfError", "LIB_PATH", "SYMBOLS", "load", "Camera", "Context", "RayTracingEngine", "VoxelVolume",
-           "greedySetCover", "bits_to_indices", "MODE_POINTS", "MODE_GOOD_POINTS", "MODE_CLASSIFY", "MODE_MARK", "MODE_MINIMUM",
+           "greedySetCover", "willCollide", "optimizeCameraPosition", "bits_to_indices", "MODE_POINTS", "MODE_GOOD_POINTS", "MODE_CLASSIFY", "MODE_MARK", "MODE_MINIMUM",
            "GRID_BIT", "GRID_BYTE", "NO_VOXEL"]

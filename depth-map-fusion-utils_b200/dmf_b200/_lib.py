@@ -60,6 +60,8 @@ SYMBOLS = {
     "dmf_forward_dev": (C.c_int, [vp, C.POINTER(ForwardParams), vp, C.c_int, C.POINTER(ForwardOut), vp]),
     "dmf_reverse": (C.c_int, [vp, C.c_int, C.c_int, fp, C.c_int, C.POINTER(ReverseOut)]),
     "dmf_reverse_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(ReverseOut), vp]),
+    "dmf_optimize_standoff": (C.c_int, [vp, fp, C.c_int, C.c_uint, C.c_uint, u32p, fp]),
+    "dmf_segments_collide": (C.c_int, [vp, fp, fp, C.c_int, C.c_int, u8p]),
     "dmf_zbuffer": (C.c_int, [vp, fp, i32p, i64p]),
     "dmf_greedy_set_cover": (C.c_int, [vp, u64p, C.c_int, C.c_size_t, i32p, ip]),
     "dmf_greedy_set_cover_dev": (C.c_int, [vp, vp, C.c_int, C.c_size_t, i32p, ip]),

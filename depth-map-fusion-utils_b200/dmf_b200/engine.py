@@ -320,6 +320,29 @@ class RayTracingEngine:
             return depth, n.value
 
 
+def willCollide(engine_or_ctx, volume: VoxelVolume, a, b, guard_coords: bool = True) -> np.ndarray:
+    """willCollide(volume, a, b) of the reference drivers (tests/CameraPathGen.cpp:128-156) for a batch of segments:
+    a, b are (n,3).  guard_coords=False reproduces the copies without the validCoords guard."""
+    ctx = engine_or_ctx.ctx if isinstance(engine_or_ctx, RayTracingEngine) else engine_or_ctx
+    volume._commit(ctx)
+    a = np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(b, np.float32).reshape(-1, 3)
+    out = np.zeros(len(a), np.uint8)
+    check(ctx.lib.dmf_segments_collide(ctx.h, _ptr(a, C.c_float), _ptr(b, C.c_float), len(a), int(guard_coords), _ptr(out, C.c_uint8)))
+    return out.astype(bool)
+
+
+def optimizeCameraPosition(volume: VoxelVolume, engine: "RayTracingEngine", cameras, low: int = 300, high: int = 600):
+    """Algorithms::optimizeCameraPosition(volume, engine, res, Affine3f camera) (Algorithms.hpp:394-421) for a batch of
+    cameras.  Returns (mid[n], repositioned poses [n,12])."""
+    engine._prepare(volume)
+    poses = _poses12(cameras)
+    mid = np.zeros(len(poses), np.uint32)
+    out = np.zeros_like(poses)
+    check(engine.ctx.lib.dmf_optimize_standoff(engine.ctx.h, _ptr(poses, C.c_float), len(poses), low, high, _ptr(mid, C.c_uint32), _ptr(out, C.c_float)))
+    return mid, out
+
+
 def greedySetCover(candidate_bitsets: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
     """Algorithms::greedySetCover (Algorithms.hpp:38-86) over visibility bitsets [n_sets][words]."""
     ctx = ctx or Context.default()

@@ -133,6 +133,8 @@ def scene(name: str) -> Scene:
         return box_shell(1.024, 64, "S64")
     if name == "S128":
         return box_shell(1.024, 128, "S128")
+    if name == "S128d":  # dyadic 128^3 (voxel = 2^-7 m): the float-accumulating whole-grid loops are exact here
+        return box_shell(1.0, 128, "S128d")
     if name == "S256":
         return box_shell(1.0, 256, "S256")
     if name == "S512":

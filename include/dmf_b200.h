@@ -142,6 +142,19 @@ int dmf_set_reverse_format(dmf_ctx* ctx, int grid_format);
 int dmf_reverse(dmf_ctx* ctx, int fast, int viz, const float* poses, int n_views, const dmf_reverse_out* out);
 int dmf_reverse_dev(dmf_ctx* ctx, int fast, int viz, const float* d_poses, int n_views, const dmf_reverse_out* d_out, void* stream);
 
+/* ---- batched stand-off search: Algorithms::optimizeCameraPosition(volume, engine, res, Affine3f camera)
+ *      (Algorithms.hpp:394-421; repositionCamera/moveCamera :170-188) for n cameras at once ------------------------- */
+/* Binary search of the stand-off in [low0, high0] mm (reference: 300, 600) on the number of ids reverseRayTrace returns
+ * at the two ends; every search step evaluates all still-active cameras in one batched reverse march.  mid_out[n] gets
+ * the final `mid`, poses_out[n][12] the repositioned cameras; either may be NULL. */
+int dmf_optimize_standoff(dmf_ctx* ctx, const float* poses, int n, unsigned low0, unsigned high0, uint32_t* mid_out, float* poses_out);
+
+/* ---- segment collision: willCollide(volume, a, b) (tests/CameraPathGen.cpp:128-156) for n segments --------------- */
+/* a, b: [n][3] end points; guard_coords != 0 reproduces the validCoords guard of CameraPathGen.cpp:147, 0 the unguarded
+ * copies (CameraMotionTSP.cpp:236-261, CameraMotionPlanner.cpp:246-271).  out[i] = 1 if the 1 mm march from a to b meets
+ * an occupied voxel. */
+int dmf_segments_collide(dmf_ctx* ctx, const float* a, const float* b, int n, int guard_coords, uint8_t* out);
+
 /* ---- z-buffer splat: rayTraceVolume (:498-564) ------------------------------------------------ */
 /* depth receives the H*W z-buffer (mm, -1 = empty; not returned by the reference, exposed for parity);
  * Voxel::view is set to 1 on the device for voxels whose depth equals the buffer. */

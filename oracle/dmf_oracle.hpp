@@ -547,6 +547,48 @@ public:
     }
 };
 
+// willCollide (tests/CameraPathGen.cpp:128-156; variants without the validCoords guard at
+// tests/CameraMotionTSP.cpp:236-261 and tests/CameraMotionPlanner.cpp:246-271): 1 mm march from a towards b.
+inline bool willCollide(VoxelVolume& volume, const Vec3& a, const Vec3& b, bool guard_coords, long long* steps = nullptr) {
+    Vec3 ab = a - b;
+    double distance = std::sqrt(sum3(ab.v[0]*ab.v[0], ab.v[1]*ab.v[1], ab.v[2]*ab.v[2]));   // Vector3f::norm(): float sqrt, widened
+    Vec3 v = normalized(b - a);
+    bool collided = false;
+    for (int depth = 1; collided == false; depth++) {
+        float s = (float)(double)depth;                                            // rule E4
+        float px = a.v[0] + (v.v[0]*s)/1000.0f, py = a.v[1] + (v.v[1]*s)/1000.0f, pz = a.v[2] + (v.v[2]*s)/1000.0f;
+        double xx = px, yy = py, zz = pz;
+        if (depth > distance*1000) break;
+        if (steps) (*steps)++;
+        if (volume.validPoints(xx,yy,zz) == false) continue;
+        int xidn,yidn,zidn; std::tie(xidn,yidn,zidn) = volume.getVoxel(xx,yy,zz);
+        if (guard_coords && volume.validCoords(xidn,yidn,zidn) == false) continue;
+        if (volume.at(xidn,yidn,zidn) != nullptr) collided = true;
+    }
+    return collided;
+}
+
+// Algorithms::moveCamera / repositionCamera (Algorithms.hpp:170-188): translation -= row2(linear) * distance / 1000, in float
+inline Affine repositionCamera(Affine camera, unsigned distance) {
+    float d = (float)(double)distance;
+    for (int i = 0; i < 3; i++) camera.m[i][3] = camera.m[i][3] - (camera.m[2][i]*d)/1000.0f;
+    return camera;
+}
+
+// Algorithms::optimizeCameraPosition(volume, engine, res, Affine3f camera) (Algorithms.hpp:394-421): binary search of the
+// stand-off in [300,600] mm on the number of ids reverseRayTrace returns.
+inline Affine optimizeCameraPosition(VoxelVolume& volume, const RayTracingEngine& engine, const Affine& camera, unsigned* mid_out = nullptr) {
+    unsigned low = 300, high = 600, mid = low;
+    while (low < high) {
+        auto lo_ids = engine.reverseRayTrace(volume, repositionCamera(camera, low), false).second;
+        auto hi_ids = engine.reverseRayTrace(volume, repositionCamera(camera, high), false).second;
+        mid = (low + high) / 2;
+        if (hi_ids.size() > lo_ids.size()) low = mid + 1; else high = mid;
+    }
+    if (mid_out) *mid_out = mid;
+    return repositionCamera(camera, mid);
+}
+
 // Algorithms::greedySetCover (Algorithms.hpp:38-86).  candidate_sets must be sorted.
 inline std::vector<u64> greedySetCover(const std::vector<std::vector<u64>>& candidate_sets) {
     std::vector<u64> covered, selected_sets, set_ids(candidate_sets.size());

@@ -120,6 +120,20 @@ long orc_greedy_set_cover(const u64* ids, const long long* offsets, long n_sets,
     return (long)sel.size();
 }
 
+int orc_will_collide(void* h, const float* a, const float* b, int guard_coords, long long* steps) {
+    Vec3 va = {{a[0],a[1],a[2]}}, vb = {{b[0],b[1],b[2]}};
+    return willCollide(*(VoxelVolume*)h, va, vb, guard_coords != 0, steps) ? 1 : 0;
+}
+
+// optimizeCameraPosition(volume, engine, res, camera): returns mid; out12 = repositioned camera
+unsigned orc_optimize_standoff(void* h, const float* K, int H, int W, const float* pose12, float* out12) {
+    RayTracingEngine eng(cam_from(K,H,W));
+    unsigned mid = 0;
+    Affine r = optimizeCameraPosition(*(VoxelVolume*)h, eng, pose_from12(pose12), &mid);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) out12[4*i+j] = r.m[i][j];
+    return mid;
+}
+
 // Timed CPU baseline: n_views poses (12 floats each) through one forward/reverse routine, no instrumentation,
 // no per-pixel outputs -- i.e. exactly the reference's work.  threads = 1 is the reference's own (serial) path;
 // threads > 1 distributes views over OpenMP threads (read-only modes only: 0, 1, 4 and reverse with viz = 0).

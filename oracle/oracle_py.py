@@ -61,6 +61,10 @@ def lib():
         L.orc_degree_acosf.argtypes = [C.c_float]
         L.orc_greedy_set_cover.restype = C.c_long
         L.orc_greedy_set_cover.argtypes = [u64p, llp, C.c_long, u64p]
+        L.orc_will_collide.restype = C.c_int
+        L.orc_will_collide.argtypes = [vp, fp, fp, C.c_int, llp]
+        L.orc_optimize_standoff.restype = C.c_uint
+        L.orc_optimize_standoff.argtypes = [vp, fp, C.c_int, C.c_int, fp, fp]
         L.orc_time_views.restype = C.c_double
         L.orc_time_views.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, llp]
         L.orc_max_threads.restype = C.c_int
@@ -190,6 +194,22 @@ def greedy_set_cover(sets):
     sel = np.zeros(max(len(sets), 1), np.uint64)
     n = lib().orc_greedy_set_cover(_p(ids, C.c_ulonglong), _p(off, C.c_longlong), len(sets), _p(sel, C.c_ulonglong))
     return sel[:n].astype(np.int64)
+
+
+def will_collide(vol: Volume, a, b, guard_coords=True):
+    a = np.ascontiguousarray(a, np.float32).reshape(3)
+    b = np.ascontiguousarray(b, np.float32).reshape(3)
+    steps = C.c_longlong(0)
+    r = lib().orc_will_collide(vol.h, _p(a, C.c_float), _p(b, C.c_float), int(guard_coords), C.byref(steps))
+    return bool(r), steps.value
+
+
+def optimize_standoff(vol: Volume, K, H, W, pose12):
+    K = np.ascontiguousarray(K, np.float32)
+    pose = np.ascontiguousarray(pose12, np.float32).reshape(12)
+    out = np.zeros(12, np.float32)
+    mid = lib().orc_optimize_standoff(vol.h, _p(K, C.c_float), H, W, _p(pose, C.c_float), _p(out, C.c_float))
+    return int(mid), out
 
 
 def time_views(vol: Volume, K, H, W, poses, kind, zdelta, sparse, threads=1):

@@ -159,3 +159,42 @@ def test_or_reduce_dev(dmf, ctx):
     check(ctx.lib.dmf_or_reduce_dev(ctx.h, C.c_void_p(d_dst.data_ptr()), C.c_void_p(d_src.data_ptr()), 5, 1000, None))
     ctx.synchronize()
     assert np.array_equal(d_dst.cpu().numpy(), np.bitwise_or.reduce(src, axis=0) | dst)
+
+
+@pytest.mark.parametrize("fmt", [1, 0])
+def test_will_collide_batch(dmf, oracle, ctx, fmt):
+    """willCollide (tests/CameraPathGen.cpp:128-156 and the unguarded copies) on a batch of segments"""
+    sc, ov, gv = _pair(dmf, oracle, ctx, "S128-clutter")
+    ctx.set_reverse_format(fmt)
+    L = float(sc.bounds[1])
+    rng = np.random.default_rng(11)
+    a = rng.uniform(-0.3 * L, 1.3 * L, size=(96, 3)).astype(np.float32)
+    b = rng.uniform(-0.3 * L, 1.3 * L, size=(96, 3)).astype(np.float32)
+    # a few structured cases: through the box, along an edge of the volume, zero length, fully outside
+    a[:6] = [[0.1 * L, 0.5 * L, 0.5 * L], [0.0, 0.0, 0.0], [0.5 * L, 0.5 * L, 0.5 * L], [2 * L, 2 * L, 2 * L], [0.5 * L, 0.5 * L, 0.01 * L], [0.34 * L, 0.2 * L, 0.5 * L]]
+    b[:6] = [[0.9 * L, 0.5 * L, 0.5 * L], [L, 0.0, 0.0], [0.5 * L, 0.5 * L, 0.5 * L], [3 * L, 2 * L, 2 * L], [0.5 * L, 0.5 * L, 0.30 * L], [0.34 * L, 0.8 * L, 0.5 * L]]
+    for guard in (True, False):
+        ctx.reset_counters()
+        got = dmf.willCollide(ctx, gv, a, b, guard_coords=guard)
+        cnt = ctx.counters()
+        want, steps = zip(*[oracle.will_collide(ov, a[i], b[i], guard) for i in range(len(a))])
+        assert np.array_equal(got, np.array(want)), np.nonzero(got != np.array(want))
+        assert cnt["samples"] == sum(steps)
+        assert 0 < got.sum() < len(a)
+
+
+def test_optimize_standoff_batch(dmf, oracle, ctx):
+    """Algorithms::optimizeCameraPosition (Algorithms.hpp:394-421): batched binary search == per-camera reference search"""
+    sc, ov, gv = _pair(dmf, oracle, ctx, "S128d")
+    K = dmf.scenes.REFERENCE_K
+    eng = dmf.RayTracingEngine(dmf.Camera(K), ctx)
+    L = float(sc.bounds[1])
+    cams = np.concatenate([dmf.scenes.poses_sphere_lookat(L, 200, radius=0.1)[::50], dmf.scenes.poses_position_camera(L, 40, standoff=0.0)[[5, 22]]])
+    mid, poses = dmf.optimizeCameraPosition(gv, eng, cams)
+    mids = []
+    for i, c in enumerate(cams):
+        m, p = oracle.optimize_standoff(ov, K, H, W, c)
+        mids.append(m)
+        assert int(mid[i]) == m, (i, int(mid[i]), m)
+        assert np.array_equal(poses[i], p)
+    assert len(set(mids)) > 1     # the search actually depends on the camera
