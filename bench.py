@@ -282,14 +282,19 @@ def run_b200(args):
     h_poses, p0 = pinned((V, 12), np.float32)
     h_poses[:] = poses
     h_depth, p1 = pinned((V, H, W), np.int32)
+    h_depth16, p5 = pinned((V, H, W), np.uint16)
     h_points, p2 = pinned((V, H, W, 3), np.float32)
     h_vis, p3 = pinned((V, max(vw, 1)), np.uint64)
     h_found, p4 = pinned((V,), np.int32)
     fp = h_poses.ctypes.data_as(C.POINTER(C.c_float))
 
-    def time_host(with_points: bool):
+    def time_host(with_points: bool, compact: bool = False):
         oh = ForwardOut()
-        oh.depth_mm, oh.visibility, oh.found_any = h_depth.ctypes.data, h_vis.ctypes.data, h_found.ctypes.data
+        oh.visibility, oh.found_any = h_vis.ctypes.data, h_found.ctypes.data
+        if compact:
+            oh.depth_u16 = h_depth16.ctypes.data
+        else:
+            oh.depth_mm = h_depth.ctypes.data
         if with_points:
             oh.points = h_points.ctypes.data
         n = max(3, min(args.steps, 10))
@@ -315,7 +320,11 @@ def run_b200(args):
     # the same with the float3 simulated point cloud copied back as well (PCIe-bound: 12 more bytes per pixel)
     e2e_pts_s, e2e_pts_steps = time_host(True)
     e2e_pts_value = e2e_pts_steps * V * H * W * world / e2e_pts_s
-    for p in (p0, p1, p2, p3, p4):
+    # and with the depth map as uint16 (z_depth < 1000): half the D2H bytes
+    e2e_u16_s, e2e_u16_steps = time_host(False, compact=True)
+    e2e_u16_value = e2e_u16_steps * V * H * W * world / e2e_u16_s
+    same = same and bool(np.array_equal(np.where(h_depth < 0, 0xFFFF, h_depth), h_depth16.astype(np.int32)))
+    for p in (p0, p1, p2, p3, p4, p5):
         ctx.lib.dmf_host_free(p)
 
     # ---- secondary: the sweep the shipped drivers run (tests/SetCover.cpp:218-240): reverseRayTraceFast per view,
@@ -369,7 +378,8 @@ def run_b200(args):
                          "note": "algorithmic bytes are the reference-equivalent ones (every in-bounds probe reads the grid once); the skipping kernel proves most of them empty without touching memory, so measured DRAM traffic is far lower; instruction-issue bound, see DESIGN.md"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_run": same, "result": "depth_mm + visibility + found_any per view",
-                    "with_points": {"value": e2e_pts_value, "d2h_bytes_per_step": d2h + V * H * W * 12, "ms_per_step": 1e3 * e2e_pts_s / e2e_pts_steps}},
+                    "with_points": {"value": e2e_pts_value, "d2h_bytes_per_step": d2h + V * H * W * 12, "ms_per_step": 1e3 * e2e_pts_s / e2e_pts_steps},
+                    "depth_as_uint16": {"value": e2e_u16_value, "d2h_bytes_per_step": d2h - V * H * W * 2, "ms_per_step": 1e3 * e2e_u16_s / e2e_u16_steps}},
             "gpu_launches": int(launches_total),
             "probes": {"reference_equivalent_per_step": samples_total / args.steps, "in_bounds_per_step": inbounds_total / args.steps,
                        "skipped_as_provably_empty_per_step": skipped_total / args.steps, "redone_in_f64_per_step": f64_total / args.steps},

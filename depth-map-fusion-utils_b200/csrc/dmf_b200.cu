@@ -279,6 +279,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     const size_t vis_words64 = (c->n_occ + 63) / 64;
     const bool sparse_lattice = pl.cstride > 1;
     if (out.depth_mm && sparse_lattice) DMF_CUDA(cudaMemsetAsync(out.depth_mm, 0xFF, n_views * HW * 4, st));
+    if (out.depth_u16 && sparse_lattice) DMF_CUDA(cudaMemsetAsync(out.depth_u16, 0xFF, n_views * HW * 2, st));
     if (out.hit_voxel && sparse_lattice) DMF_CUDA(cudaMemsetAsync(out.hit_voxel, 0xFF, n_views * HW * 8, st));
     if (out.points && sparse_lattice) DMF_CUDA(cudaMemsetAsync(out.points, 0, n_views * HW * 12, st));
     if (out.visibility && vis_words64) DMF_CUDA(cudaMemsetAsync(out.visibility, 0, (size_t)n_views * vis_words64 * 8, st));
@@ -293,7 +294,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     a.vol = c->vol; a.angle = c->angle; a.poses = d_poses;
     a.xtab = c->d_xtab.as<float>(); a.ytab = c->d_ytab.as<float>(); a.ztab = c->d_ztab.as<float>();
     a.S = c->S; a.Wc = c->Wc; a.Hc = c->Hc; a.W = c->W; a.H = c->H; a.cstride = pl.cstride; a.rstride = pl.rstride; a.z0 = pl.z0; a.zdelta = p->zdelta;
-    a.depth = out.depth_mm; a.points = out.points; a.hit_voxel = (u64*)out.hit_voxel;
+    a.depth = out.depth_mm; a.depth16 = out.depth_u16; a.points = out.points; a.hit_voxel = (u64*)out.hit_voxel;
     a.vis = (unsigned*)out.visibility; a.vis_words32 = (int)(vis_words64 * 2);
     a.found_any = out.found_any; a.min_depth = out.min_depth;
     a.first_key = first_key; a.ray_key = ray_key; a.ray_occ = ray_occ;
@@ -520,10 +521,11 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
     if (want_ids && (R > (1u << 21) || S > 1024)) return fail("id lists need <= 2^21 cast pixels and <= 1024 z-planes (got %zu, %d)", R, S);
     if (want_ids) out->ids_offsets[0] = 0;
     // views per chunk: keep the per-chunk device footprint around 1 GiB
-    size_t per_view = 48 + (out->depth_mm ? HW * 4 : 0) + (out->points ? HW * 12 : 0) + (out->hit_voxel ? HW * 8 : 0) +
+    size_t per_view = 48 + (out->depth_u16 ? HW * 2 : 0) + (out->depth_mm ? HW * 4 : 0) + (out->points ? HW * 12 : 0) + (out->hit_voxel ? HW * 8 : 0) +
                       (out->visibility ? vw * 8 : 0) + 8 + (want_ids ? c->n_occ * 4 + R * 20 : 0);
     int chunk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n_views, (size_t)4096, ((size_t)1 << 30) / per_view}));
-    if (!want_ids && n_views >= 8) chunk = std::min(chunk, (n_views + 3) / 4);   // >= 4 chunks: D2H of one overlaps the march of the next
+    if (!want_ids && n_views >= 16) chunk = std::min(chunk, (n_views + 7) / 8);      // >= 8 chunks: D2H of one overlaps the march of the next
+    else if (!want_ids && n_views >= 8) chunk = std::min(chunk, (n_views + 3) / 4);
     cudaStream_t st = c->stream, cs = c->copy_stream;
     DMF_CUDA(cudaEventRecord(c->ev_k0, st));
     int64_t ids_total = 0;
@@ -537,6 +539,7 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
         dmf_forward_out d{};
         DevBuf* ob = c->d_out[b];
         if (out->depth_mm) { DMF_TRY(ob[0].reserve(nv * HW * 4)); d.depth_mm = ob[0].as<int32_t>(); }
+        if (out->depth_u16) { DMF_TRY(ob[7].reserve(nv * HW * 2)); d.depth_u16 = ob[7].as<uint16_t>(); }
         if (out->points) { DMF_TRY(ob[1].reserve(nv * HW * 12)); d.points = ob[1].as<float>(); }
         if (out->hit_voxel) { DMF_TRY(ob[2].reserve(nv * HW * 8)); d.hit_voxel = ob[2].as<uint64_t>(); }
         if (out->visibility && vw) { DMF_TRY(ob[3].reserve(nv * vw * 8)); d.visibility = ob[3].as<uint64_t>(); }
@@ -576,6 +579,7 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
         DMF_CUDA(cudaEventRecord(c->ev_compute[b], st));
         DMF_CUDA(cudaStreamWaitEvent(cs, c->ev_compute[b], 0));
         if (out->depth_mm) DMF_CUDA(cudaMemcpyAsync(out->depth_mm + v0 * HW, d.depth_mm, nv * HW * 4, cudaMemcpyDeviceToHost, cs));
+        if (out->depth_u16) DMF_CUDA(cudaMemcpyAsync(out->depth_u16 + v0 * HW, d.depth_u16, nv * HW * 2, cudaMemcpyDeviceToHost, cs));
         if (out->points) DMF_CUDA(cudaMemcpyAsync(out->points + v0 * HW * 3, d.points, nv * HW * 12, cudaMemcpyDeviceToHost, cs));
         if (out->hit_voxel) DMF_CUDA(cudaMemcpyAsync(out->hit_voxel + v0 * HW, d.hit_voxel, nv * HW * 8, cudaMemcpyDeviceToHost, cs));
         if (out->visibility && vw) DMF_CUDA(cudaMemcpyAsync(out->visibility + v0 * vw, d.visibility, nv * vw * 8, cudaMemcpyDeviceToHost, cs));

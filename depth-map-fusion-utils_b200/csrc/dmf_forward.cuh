@@ -26,6 +26,7 @@ struct FwdArgs {
     float dcx_max, dcy_max;            // max |dcx|, |dcy| (for the per-view error bound)
     // outputs (may be null)
     int* depth;                        // [n_views][H][W]
+    unsigned short* depth16;           // [n_views][H][W]  same, 0xFFFF = none
     float* points;                     // [n_views][H][W][3]
     u64* hit_voxel;                    // [n_views][H][W]
     unsigned* vis;                     // [n_views][vis_words32] bitset over occupied order
@@ -79,6 +80,7 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
     if (active) {
         const size_t pix = ((size_t)view * a.H + (size_t)ri * a.rstride) * a.W + (size_t)ci * a.cstride;
         if (a.depth) a.depth[pix] = hit ? z_depth : -1;
+        if (a.depth16) a.depth16[pix] = hit ? (unsigned short)z_depth : (unsigned short)0xFFFFu;
         if (a.hit_voxel) a.hit_voxel[pix] = hit ? voxel_id(hx, hy, hz) : ~0ull;
         if (a.points) {
             a.points[3 * pix] = hit ? hpx : 0.f; a.points[3 * pix + 1] = hit ? hpy : 0.f; a.points[3 * pix + 2] = hit ? hpz : 0.f;

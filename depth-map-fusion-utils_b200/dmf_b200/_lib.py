@@ -24,7 +24,7 @@ class ForwardOut(C.Structure):
     _fields_ = [
         ("depth_mm", C.c_void_p), ("points", C.c_void_p), ("hit_voxel", C.c_void_p), ("visibility", C.c_void_p),
         ("found_any", C.c_void_p), ("min_depth", C.c_void_p), ("ids", C.c_void_p), ("ids_offsets", C.c_void_p),
-        ("ids_capacity", C.c_size_t),
+        ("ids_capacity", C.c_size_t), ("depth_u16", C.c_void_p),
     ]
 
 

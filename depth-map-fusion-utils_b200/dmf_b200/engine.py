@@ -240,6 +240,8 @@ class RayTracingEngine:
         o = ForwardOut()
         if "depth" in want:
             res["depth"] = np.empty((n, H, W), np.int32); o.depth_mm = _vptr(res["depth"])
+        if "depth16" in want:
+            res["depth16"] = np.empty((n, H, W), np.uint16); o.depth_u16 = _vptr(res["depth16"])
         if "points" in want:
             res["points"] = np.empty((n, H, W, 3), np.float32); o.points = _vptr(res["points"])
         if "voxel" in want:

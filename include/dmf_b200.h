@@ -111,6 +111,8 @@ typedef struct {
     uint64_t* ids;         /* returned id lists, discovery order (z_depth, r, c), views concatenated       */
     int64_t*  ids_offsets; /* [n_views+1]        view v owns ids[ids_offsets[v] .. ids_offsets[v+1])       */
     size_t    ids_capacity;/* entries available in ids; fails (no partial write) if too small             */
+    uint16_t* depth_u16;   /* [n_views][H][W]    the same first-hit z_depth as 16 bits (z_depth < 1000 always), 0xFFFF = none/not cast:
+                              half the device->host bytes of depth_mm for consumers that only need the depth map */
 } dmf_forward_out;
 
 size_t dmf_visibility_words(dmf_ctx* ctx);   /* ceil(n_occ/64) */

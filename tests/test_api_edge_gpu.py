@@ -1,0 +1,122 @@
+"""GPU tier: error behaviour and edge cases of the C ABI (no reference equivalent: the reference prints and continues or
+hits UB; the library must fail cleanly with a message and never crash)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _vol(dmf, ctx, name="S64"):
+    sc = dmf.scenes.scene(name)
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+    return sc, gv
+
+
+def test_calls_before_setup_fail_cleanly(dmf):
+    from dmf_b200._lib import ForwardOut, ForwardParams
+    c = dmf.Context(0)
+    try:
+        p = ForwardParams(0, 8, 0, 1, 0, 0)
+        o = ForwardOut()
+        pose = dmf.scenes.pose_p1(1.0)[0]
+        rc = c.lib.dmf_forward(c.h, C.byref(p), pose.ctypes.data_as(C.POINTER(C.c_float)), 1, C.byref(o))
+        assert rc != 0 and b"dmf_set_camera" in c.lib.dmf_last_error()
+        K = dmf.scenes.REFERENCE_K
+        assert c.lib.dmf_set_camera(c.h, K.ctypes.data_as(C.POINTER(C.c_float)), 480, 640) == 0
+        rc = c.lib.dmf_forward(c.h, C.byref(p), pose.ctypes.data_as(C.POINTER(C.c_float)), 1, C.byref(o))
+        assert rc != 0 and b"no volume" in c.lib.dmf_last_error()
+        assert c.lib.dmf_set_camera(c.h, K.ctypes.data_as(C.POINTER(C.c_float)), 0, 640) != 0
+    finally:
+        c.close()
+
+
+def test_bad_parameters_and_capacity(dmf, ctx):
+    from dmf_b200._lib import ForwardOut, ForwardParams
+    sc, gv = _vol(dmf, ctx)
+    eng = dmf.RayTracingEngine(dmf.Camera(dmf.scenes.REFERENCE_K), ctx)
+    eng._prepare(gv)
+    pose = np.ascontiguousarray(dmf.scenes.pose_p1(1.024)[0])
+    fp = pose.ctypes.data_as(C.POINTER(C.c_float))
+    o = ForwardOut()
+    for bad in (ForwardParams(7, 8, 0, 1, 0, 0), ForwardParams(0, 0, 0, 1, 0, 0), ForwardParams(0, 8, 0, 1, 5, 0)):
+        assert ctx.lib.dmf_forward(ctx.h, C.byref(bad), fp, 1, C.byref(o)) != 0
+    # id list larger than the caller's buffer: clean failure, message says how many are needed
+    ids = np.zeros(4, np.uint64); offs = np.zeros(2, np.int64)
+    o.ids, o.ids_offsets, o.ids_capacity = ids.ctypes.data, offs.ctypes.data, 4
+    p = ForwardParams(0, 8, 0, 1, 0, 0)
+    assert ctx.lib.dmf_forward(ctx.h, C.byref(p), fp, 1, C.byref(o)) != 0
+    assert b"ids_capacity" in ctx.lib.dmf_last_error()
+    # MINIMUM without an output buffer
+    o2 = ForwardOut()
+    assert ctx.lib.dmf_forward(ctx.h, C.byref(ForwardParams(4, 1, 1, 1, 0, 0)), fp, 1, C.byref(o2)) != 0
+    # zero views is a no-op
+    assert ctx.lib.dmf_forward(ctx.h, C.byref(p), fp, 0, C.byref(ForwardOut())) == 0
+    # the context still works afterwards
+    found, got = eng.rayTraceAndGetPoints(gv, pose, 8, False)
+    assert found and len(got) > 100
+
+
+def test_upload_volume_validation(dmf, ctx):
+    lib = ctx.lib
+    b = np.array([0, 1, 0, 1, 0, 1], np.float64); d = np.full(3, 1 / 8, np.float64); dim = np.array([8, 8, 8], np.int32)
+    dp, ip, u64p = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_uint64)
+    dup = np.array([(1 << 40) | (2 << 20) | 3] * 2, np.uint64)
+    assert lib.dmf_upload_volume(ctx.h, b.ctypes.data_as(dp), d.ctypes.data_as(dp), dim.ctypes.data_as(ip), dup.ctypes.data_as(u64p), 2, None, None) != 0
+    assert b"duplicate" in lib.dmf_last_error()
+    out = np.array([(9 << 40)], np.uint64)
+    assert lib.dmf_upload_volume(ctx.h, b.ctypes.data_as(dp), d.ctypes.data_as(dp), dim.ctypes.data_as(ip), out.ctypes.data_as(u64p), 1, None, None) != 0
+    big = np.array([4096, 8, 8], np.int32)
+    assert lib.dmf_upload_volume(ctx.h, b.ctypes.data_as(dp), d.ctypes.data_as(dp), big.ctypes.data_as(ip), None, 0, None, None) != 0
+    ctx._volume_token = None   # the context's volume is undefined after failed uploads: force the next test to re-upload
+
+
+def test_nan_and_degenerate_poses_do_not_crash(dmf, ctx):
+    sc, gv = _vol(dmf, ctx)
+    eng = dmf.RayTracingEngine(dmf.Camera(dmf.scenes.REFERENCE_K), ctx)
+    nan_pose = np.full(12, np.nan, np.float32)
+    zero_pose = np.zeros(12, np.float32)
+    huge = dmf.scenes.pose_p1(1.024)[0].copy(); huge[[3, 7, 11]] = 1e30
+    for fmt in (dmf.GRID_BYTE, dmf.GRID_BIT):
+        eng.grid_format = fmt
+        r = eng.forward_views(gv, np.stack([nan_pose, zero_pose, huge]), 0, 8, False, want=("depth",))
+        assert (r["depth"] == -1).all() and not r["found_any"].any()
+    rv = eng.reverse_views(gv, np.stack([nan_pose, zero_pose]), fast=True, want=("visibility",))
+    assert not rv["found_any"][0]
+    ctx.synchronize()
+
+
+def test_two_contexts_and_reupload(dmf, oracle, ctx):
+    sc_a, gv_a = _vol(dmf, ctx, "S64")
+    c2 = dmf.Context(0)
+    try:
+        sc_b, gv_b = _vol(dmf, c2, "S128")
+        K = dmf.scenes.REFERENCE_K
+        e1 = dmf.RayTracingEngine(dmf.Camera(K), ctx); e2 = dmf.RayTracingEngine(dmf.Camera(K), c2)
+        pose = dmf.scenes.pose_p1(1.024)[0]
+        ids_a = e1.rayTraceAndGetPoints(gv_a, pose, 8, False)[1]
+        ids_b = e2.rayTraceAndGetPoints(gv_b, pose, 8, False)[1]
+        assert np.array_equal(ids_a, oracle.forward(oracle.volume_from_scene(sc_a), K, 480, 640, pose, 0, 8, False, want_pixels=False)["ids"])
+        assert np.array_equal(ids_b, oracle.forward(oracle.volume_from_scene(sc_b), K, 480, 640, pose, 0, 8, False, want_pixels=False)["ids"])
+        # re-using context 1 for another volume re-uploads transparently
+        ids_b1 = e1.rayTraceAndGetPoints(gv_b, pose, 8, False)[1]
+        assert np.array_equal(ids_b1, ids_b)
+        assert np.array_equal(e1.rayTraceAndGetPoints(gv_a, pose, 8, False)[1], ids_a)
+    finally:
+        c2.close()
+
+
+def test_many_small_views_are_chunked(dmf, oracle, ctx):
+    """5000 views of a 16x12 camera: more than one 4096-view chunk through the double-buffered host path"""
+    sc, gv = _vol(dmf, ctx)
+    K = dmf.scenes.REFERENCE_K.copy(); K[[0, 2, 4, 5]] *= 0.025
+    eng = dmf.RayTracingEngine(dmf.Camera(K, 12, 16), ctx)
+    base = dmf.scenes.poses_sphere_lookat(1.024, 1000)
+    poses = np.tile(base, (5, 1))
+    r = eng.forward_views(gv, poses, 0, 8, False, want=("depth", "visibility"))
+    assert np.array_equal(r["depth"][:1000], r["depth"][4000:]) and np.array_equal(r["visibility"][:1000], r["visibility"][4000:])
+    ov = oracle.volume_from_scene(sc)
+    for i in (0, 777, 4999):
+        assert np.array_equal(r["depth"][i], oracle.forward(ov, K, 12, 16, poses[i], 0, 8, False)["depth"])

@@ -113,6 +113,18 @@ def test_ragged_image_and_odd_zdelta(dmf, oracle, ctx):
         _check_forward(dmf, oracle, ctx, sc, ov, gv, _poses(dmf, sc, 2), 0, 7, sparse, H=123, W=157, K=K)
 
 
+def test_depth_u16_output(dmf, ctx):
+    sc = dmf.scenes.scene("S64")
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+    eng = dmf.RayTracingEngine(dmf.Camera(dmf.scenes.REFERENCE_K), ctx)
+    poses = dmf.scenes.poses_sphere_lookat(1.024, 40)[::10]
+    for sparse in (False, True):
+        r = eng.forward_views(gv, poses, 0, 8, sparse, want=("depth", "depth16"))
+        want = r["depth"].copy(); want[want < 0] = 0xFFFF
+        assert np.array_equal(r["depth16"].astype(np.int32), want) and (r["depth"] >= 0).sum() > 1000
+
+
 def test_empty_volume_and_camera_outside(dmf, oracle, ctx):
     sc = dmf.scenes.scene("S64")
     gv = dmf.VoxelVolume(ctx)
