@@ -112,29 +112,42 @@ def ncu_traffic():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def oracle_volume(O, scenes, flat: bool):
+def cpu_backend():
+    """The reference's own hot-path headers compiled here against a minimal Eigen/PCL shim (oracle/_ref, kind "reference")
+    when that prebuilt library is present, else the oracle port (kind "port")."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_py
+    if ref_py.available():
+        return ref_py, "reference", ("reference include/{Camera,Volume,RayTracingEngine}.hpp compiled unmodified (g++ -O3 -fopenmp) against "
+                                     "oracle/ref_shim, a minimal Eigen/PCL look-alike; stack scrubbed before each call (found[][] VLA is uninitialised in the reference)")
+    import oracle_py
+    return oracle_py, "port", "oracle/dmf_oracle.hpp restatement on the reference's vector<vector<vector<Voxel*>>> grid"
+
+
+def cpu_volume(mod, scenes):
     sc = scenes.scene(SCENE)
-    return sc, O.volume_from_scene(sc, flat=flat)
+    if mod.__name__ == "ref_py":
+        return sc, mod.volume_from_scene(sc)
+    return sc, mod.volume_from_scene(sc, flat=False)
 
 
 def cpu_baseline(scenes, n_views_serial=2, with_all_cores=True) -> dict:
-    """The oracle port (kind 'port') timed on this box's host cores: the reference's own single-threaded path on its
-    own pointer grid, then the same code with views spread over all cores.  Bounded sample, stated."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py as O
-    sc, vol = oracle_volume(O, scenes, flat=False)
+    """The reference's CPU path timed on this box's host cores: single-threaded (as the reference runs it), then the
+    same code with views spread over all cores.  Bounded sample, stated."""
+    M, kind, how = cpu_backend()
+    sc, vol = cpu_volume(M, scenes)
     poses = scenes.bench_poses(float(sc.bounds[1]), 64)
     K = scenes.REFERENCE_K
-    sec, _ = O.time_views(vol, K, H, W, poses[:n_views_serial], O.MODE_POINTS, sc.zdelta, False, threads=1)
-    out = {"value": n_views_serial * H * W / sec, "unit": "rays/s", "cores": 1, "kind": "port",
-           "sample": f"{n_views_serial} views of the same workload, 1 thread, reference vector<vector<vector<Voxel*>>> grid; the reference hot path is single-threaded",
+    sec, _ = M.time_views(vol, K, H, W, poses[:n_views_serial], 0, sc.zdelta, False, threads=1)
+    out = {"value": n_views_serial * H * W / sec, "unit": "rays/s", "cores": 1, "kind": kind,
+           "sample": f"{n_views_serial} views of the same workload, 1 thread (the reference hot path is single-threaded); {how}",
            "sec_per_view": sec / n_views_serial}
-    secr, _ = O.time_views(vol, K, H, W, poses[:1], 11, sc.zdelta, False, threads=1)
+    secr, _ = M.time_views(vol, K, H, W, poses[:1], 10 if kind == "reference" else 11, sc.zdelta, False, threads=1)
     out["reverse_sweep"] = {"views_per_s": 1.0 / secr, "sample": "1 view of reverseRayTraceFast incl. its dead getNeighborHashes work, 1 thread", "sec_per_view": secr}
     if with_all_cores:
-        nt = O.max_threads()
+        nt = M.max_threads()
         nv = max(nt, 2)
-        sec2, _ = O.time_views(vol, K, H, W, poses[:nv], O.MODE_POINTS, sc.zdelta, False, threads=nt)
+        sec2, _ = M.time_views(vol, K, H, W, poses[:nv], 0, sc.zdelta, False, threads=nt)
         out["all_cores"] = {"value": nv * H * W / sec2, "cores": nt, "sample": f"{nv} views over {nt} OpenMP threads"}
     return out
 
@@ -144,30 +157,27 @@ def run_reference(args):
     if rank != 0:
         return
     from dmf_b200 import scenes
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py as O
-    sc, vol = oracle_volume(O, scenes, flat=False)
+    M, kind, how = cpu_backend()
+    sc, vol = cpu_volume(M, scenes)
     K = scenes.REFERENCE_K
-    nt = O.max_threads()
+    nt = M.max_threads()
     nv = max(nt, 1)                      # one view per host thread per step: a bounded sample of the V-view batch
     poses = scenes.bench_poses(float(sc.bounds[1]), 1024)
-    cnt = O.forward(vol, K, H, W, poses[0], O.MODE_POINTS, sc.zdelta, False, want_pixels=False)["counters"]
-    steps, warm = max(1, min(args.steps, 6)), max(0, min(args.warmup, 1))   # ~5 s per step: keep the run to a few minutes
+    steps, warm = max(1, min(args.steps, 6)), max(0, min(args.warmup, 1))   # several seconds per step: keep the run to a few minutes
     for i in range(warm):
-        O.time_views(vol, K, H, W, poses[i * nv:(i + 1) * nv], O.MODE_POINTS, sc.zdelta, False, threads=nt)
+        M.time_views(vol, K, H, W, poses[i * nv:(i + 1) * nv], 0, sc.zdelta, False, threads=nt)
     total = 0.0
     for i in range(steps):
-        s, _ = O.time_views(vol, K, H, W, poses[(warm + i) * nv:(warm + i + 1) * nv], O.MODE_POINTS, sc.zdelta, False, threads=nt)
+        s, _ = M.time_views(vol, K, H, W, poses[(warm + i) * nv:(warm + i + 1) * nv], 0, sc.zdelta, False, threads=nt)
         total += s
     val = steps * nv * H * W / total
     line = {
         "impl": "reference", "metric": "rays/s", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "views_per_step": nv, "note": "CPU oracle port of the reference (reference needs Eigen/PCL, not buildable here); "
-                   "each step is a bounded sample of the batch: one view per host thread"},
-        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": nt, "kind": "port", "sample": f"{nv} views per step over {nt} OpenMP threads, reference pointer grid"},
+        "config": {"workload": WORKLOAD, "views_per_step": nv, "note": "CPU: " + how + "; each step is a bounded sample of the batch: one view per host thread"},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": nt, "kind": kind, "sample": f"{nv} views per step over {nt} OpenMP threads; {how}"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "voxel_updates_per_s": val / (H * W) * cnt["inbounds"], "gpu_launches": 0,
+        "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 

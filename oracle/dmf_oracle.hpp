@@ -5,14 +5,17 @@
 // or execute anything in oracle/.  The product (depth-map-fusion-utils_b200/)
 // never includes this file and has no CPU fallback.
 //
-// PARITY UNPINNED.  The reference (REXJJ/depth-map-fusion-utils) ships no golden
-// vectors, no assertions on ray-tracing output and cannot be compiled here
+// PINNING STATUS.  The reference (REXJJ/depth-map-fusion-utils) ships no golden
+// vectors and no assertions on ray-tracing output, and as a whole cannot be built here
 // (Eigen >= 3.3, PCL >= 1.7 ... are absent; CMakeLists.txt:3-29).  This file is a
-// from-scratch restatement of the reference's arithmetic, step for step, with the
-// float/double op order of the un-vendored Eigen 3.3 dependency written out
-// explicitly (rules E1..E5 below).  Where Eigen's order cannot be proven from the
-// reference tree, the alternative order is selectable at run time
-// (set_eigen_order) so tests can COUNT how many samples change ("tie cases").
+// from-scratch restatement of the reference's arithmetic, step for step.  Its LOGIC is
+// pinned: tests/test_reference_build_cpu.py compares it with the reference's own
+// Camera/Volume/RayTracingEngine headers compiled unmodified against a minimal
+// Eigen/PCL shim (oracle/ref_capi.cpp -> oracle/_ref/) -- identical on every routine.
+// PARITY UNPINNED for one remainder: the float op order INSIDE the un-vendored Eigen
+// 3.3, which both this file and the shim write out as rules E1..E5 below.  The
+// alternative order is selectable at run time (set_eigen_order) so tests can COUNT
+// how many samples change ("tie cases").
 //
 // What is restated (reference file:line):
 //   Camera::projectPoint / deProjectPoint / transformPoints / validPixel

@@ -1,0 +1,178 @@
+// ref_capi.cpp -- TEST INFRASTRUCTURE.  C entry points over the reference's OWN hot-path headers, compiled from where they
+// lie (/root/reference/include, read-only, never copied) against oracle/ref_shim (a minimal Eigen/PCL look-alike), into
+// oracle/_ref/libref_dmf.so.  Used to (1) validate the restatement in dmf_oracle.hpp against the real reference code and
+// (2) time the reference's CPU path (bench.py cpu_baseline kind "reference").  The reference source cannot travel to the
+// GPU box; the built library does.
+//
+// Same C API shape as dmf_oracle_capi.cpp (subset), prefix ref_.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <chrono>
+#include <memory>
+#include <vector>
+#include <tuple>
+#include <algorithm>
+#include <Eigen/Dense>
+using namespace Eigen;   // the reference's CommonUtilities.hpp names Vector3f unqualified; its drivers get this from other headers
+
+// The reference's integratePointCloud overloads fall off the end of a bool function (Volume.hpp:197,228): undefined
+// behaviour that g++ -O3 turns into an unreachable.  Compile Volume.hpp without optimisation so the call returns.
+#pragma GCC push_options
+#pragma GCC optimize("O0", "no-unreachable-traps")
+#include <Volume.hpp>
+#pragma GCC pop_options
+#include <RayTracingEngine.hpp>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+Eigen::Affine3f pose_from12(const float* p) {
+    Eigen::Affine3f T = Eigen::Affine3f::Identity();
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) T(r, c) = p[4 * r + c];
+    return T;
+}
+// FINDING: the forward routines declare `bool found[H][W]={false};` on a variable-length array (RayTracingEngine.hpp:272,
+// 315,381,451).  g++ zero-initialises only the first element of a VLA; the rest is whatever the stack held (checked with
+// g++ 13.3: 54 315 of 307 200 entries non-zero after a call that dirtied the stack).  The reference's results therefore
+// depend on stack garbage (UB).  The intended semantics -- no pixel found yet -- is what the oracle and the CUDA path
+// implement; to compare against the real source we hand it a clean stack: zero a region below the current frame right
+// before every call, so the VLA the callee carves out of it reads as all-false.
+__attribute__((noinline)) void scrub_stack() {
+    volatile char pad[3 << 20];
+    for (size_t i = 0; i < sizeof pad; i += 64) pad[i] = 0;          // touch
+    std::memset((void*)pad, 0, sizeof pad);
+    asm volatile("" ::: "memory");
+}
+struct Quiet {   // the reference prints inside the hot path (RayTracingEngine.hpp:224,537-538)
+    std::streambuf* old;
+    Quiet() : old(std::cout.rdbuf(nullptr)) {}
+    ~Quiet() { std::cout.rdbuf(old); }
+};
+}
+
+extern "C" {
+
+void* ref_volume_new(const double* bounds, const int* dims) {
+    auto* v = new VoxelVolume();
+    v->setDimensions(bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5]);
+    v->setVolumeSize(dims[0], dims[1], dims[2]);
+    v->constructVolume();
+    return v;
+}
+void ref_volume_free(void* h) { delete (VoxelVolume*)h; }
+void ref_volume_info(void* h, int* dims, double* deltas, double* voxel_size) {
+    auto* v = (VoxelVolume*)h;
+    dims[0] = v->xdim_; dims[1] = v->ydim_; dims[2] = v->zdim_;
+    deltas[0] = v->xdelta_; deltas[1] = v->ydelta_; deltas[2] = v->zdelta_;
+    *voxel_size = v->voxel_size_;
+}
+void ref_volume_integrate(void* h, const float* xyz, const float* nrm, long n) {
+    auto* v = (VoxelVolume*)h;
+    pcl::PointCloud<pcl::PointXYZRGB>::Ptr cloud(new pcl::PointCloud<pcl::PointXYZRGB>);
+    pcl::PointCloud<pcl::Normal>::Ptr normals(new pcl::PointCloud<pcl::Normal>);
+    for (long i = 0; i < n; i++) {
+        pcl::PointXYZRGB p; p.x = xyz[3 * i]; p.y = xyz[3 * i + 1]; p.z = xyz[3 * i + 2];
+        cloud->points.push_back(p);
+        pcl::Normal q; q.normal[0] = nrm[3 * i]; q.normal[1] = nrm[3 * i + 1]; q.normal[2] = nrm[3 * i + 2];
+        normals->points.push_back(q);
+    }
+    v->integratePointCloud(cloud, normals);
+}
+long ref_volume_num_occupied(void* h) { return (long)((VoxelVolume*)h)->occupied_cells_.size(); }
+void ref_volume_get_occupied(void* h, unsigned long long* ids) { auto* v = (VoxelVolume*)h; std::copy(v->occupied_cells_.begin(), v->occupied_cells_.end(), ids); }
+void ref_volume_get_marks(void* h, int* view, unsigned char* good) {
+    auto* v = (VoxelVolume*)h; size_t i = 0;
+    for (auto id : v->occupied_cells_) { int x, y, z; std::tie(x, y, z) = v->getVoxelCoords(id); Voxel* q = v->voxels_[x][y][z]; view[i] = q->view; good[i] = q->good ? 1 : 0; i++; }
+}
+void ref_volume_clear_marks(void* h) {
+    auto* v = (VoxelVolume*)h;
+    for (auto id : v->occupied_cells_) { int x, y, z; std::tie(x, y, z) = v->getVoxelCoords(id); v->voxels_[x][y][z]->view = 0; v->voxels_[x][y][z]->good = false; }
+}
+
+// mode: 0 rayTraceAndGetPoints, 1 rayTraceAndGetGoodPoints, 2 rayTraceAndClassify, 3 rayTrace, 4 rayTraceAndGetMinimum
+long ref_forward(void* h, const float* K, int H, int W, const float* pose12, int mode, int zdelta, int sparse, int view,
+                 unsigned long long* ids_out, long ids_cap, int* found_any, int* min_depth) {
+    Quiet q;
+    std::vector<float> Kv(K, K + 9);
+    Camera cam(Kv, H, W);
+    RayTracingEngine eng(cam);
+    Eigen::Affine3f T = pose_from12(pose12);
+    VoxelVolume& vol = *(VoxelVolume*)h;
+    std::pair<bool, std::vector<unsigned long long int>> res(false, {});
+    int md = -1;
+    scrub_stack();
+    switch (mode) {
+        case 0: res = eng.rayTraceAndGetPoints(vol, T, zdelta, sparse != 0); break;
+        case 1: res = eng.rayTraceAndGetGoodPoints(vol, T, zdelta, sparse != 0); break;
+        case 2: eng.rayTraceAndClassify(vol, T, zdelta, view, sparse != 0); break;
+        case 3: eng.rayTrace(vol, T, zdelta, sparse != 0); break;
+        default: md = eng.rayTraceAndGetMinimum(vol, T, zdelta, sparse != 0); res.first = md >= 0; break;
+    }
+    if (found_any) *found_any = res.first ? 1 : 0;
+    if (min_depth) *min_depth = md;
+    long n = (long)res.second.size();
+    if (ids_out) std::copy(res.second.begin(), res.second.begin() + std::min(n, ids_cap), ids_out);
+    return n;
+}
+
+long ref_reverse(void* h, const float* K, int H, int W, const float* pose12, int fast, int viz,
+                 unsigned long long* ids_out, long ids_cap, int* found_any) {
+    Quiet q;
+    std::vector<float> Kv(K, K + 9);
+    Camera cam(Kv, H, W);
+    RayTracingEngine eng(cam);
+    VoxelVolume& vol = *(VoxelVolume*)h;
+    auto res = fast ? eng.reverseRayTraceFast(vol, pose_from12(pose12), viz != 0) : eng.reverseRayTrace(vol, pose_from12(pose12), viz != 0);
+    if (found_any) *found_any = res.first ? 1 : 0;
+    long n = (long)res.second.size();
+    if (ids_out) std::copy(res.second.begin(), res.second.begin() + std::min(n, ids_cap), ids_out);
+    return n;
+}
+
+void ref_zbuffer(void* h, const float* K, int H, int W, const float* pose12) {
+    Quiet q;
+    std::vector<float> Kv(K, K + 9);
+    Camera cam(Kv, H, W);
+    RayTracingEngine eng(cam);
+    Eigen::Affine3f T = pose_from12(pose12);
+    eng.rayTraceVolume(*(VoxelVolume*)h, T);
+}
+
+// seconds for n_views calls of one routine; kind 0..4 forward mode, 10 reverseRayTraceFast, 12 reverseRayTrace.
+// threads > 1 spreads views over OpenMP threads (read-only kinds 0, 1, 4, 10, 12 with viz = false).
+double ref_time_views(void* h, const float* K, int H, int W, const float* poses, long n_views, int kind, int zdelta, int sparse, int threads, long long* total_out) {
+    Quiet q;
+    std::vector<float> Kv(K, K + 9);
+    Camera cam(Kv, H, W);
+    RayTracingEngine eng(cam);
+    VoxelVolume& vol = *(VoxelVolume*)h;
+    long long total = 0;
+    auto t0 = std::chrono::steady_clock::now();
+#ifdef _OPENMP
+    #pragma omp parallel for schedule(dynamic,1) num_threads(threads > 0 ? threads : 1) reduction(+:total)
+#endif
+    for (long i = 0; i < n_views; i++) {
+        Eigen::Affine3f T = pose_from12(poses + 12 * i);
+        scrub_stack();
+        if (kind == 0) total += (long long)eng.rayTraceAndGetPoints(vol, T, zdelta, sparse != 0).second.size();
+        else if (kind == 1) total += (long long)eng.rayTraceAndGetGoodPoints(vol, T, zdelta, sparse != 0).second.size();
+        else if (kind == 4) total += eng.rayTraceAndGetMinimum(vol, T, zdelta, sparse != 0);
+        else if (kind == 12) total += (long long)eng.reverseRayTrace(vol, T, false).second.size();
+        else total += (long long)eng.reverseRayTraceFast(vol, T, false).second.size();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (total_out) *total_out = total;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int ref_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,7 @@
+// oracle/ref_shim/pcl/point_types.h -- TEST INFRASTRUCTURE: the two PCL point types the reference's Volume.hpp stores.
+#pragma once
+#include <cstdint>
+namespace pcl {
+struct PointXYZRGB { float x = 0, y = 0, z = 0; std::uint8_t r = 0, g = 0, b = 0; };
+struct Normal { float normal[3] = {0, 0, 0}; float curvature = 0; };
+}
