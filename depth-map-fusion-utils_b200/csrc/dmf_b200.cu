@@ -378,8 +378,8 @@ int dmf_create(dmf_ctx** out, int device) {
         DMF_CUDA(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
         DMF_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
     }
-    DMF_TRY(c->d_counters.reserve(DMF_CNT_COUNT * 8));
-    DMF_CUDA(cudaMemset(c->d_counters.p, 0, DMF_CNT_COUNT * 8));
+    DMF_TRY(c->d_counters.reserve(DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
+    DMF_CUDA(cudaMemset(c->d_counters.p, 0, DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
     DMF_CUDA(cudaFuncSetAttribute(k_order_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * ORD_THREADS * 4));
     c->angle = bisect_angle_test();
     *out = c;
@@ -598,7 +598,9 @@ int dmf_counters(dmf_ctx* c, uint64_t out[DMF_CNT_COUNT]) {
     if (!c) return fail("null context");
     DMF_CUDA(cudaSetDevice(c->device));
     DMF_CUDA(cudaDeviceSynchronize());
-    DMF_CUDA(cudaMemcpy(out, c->d_counters.p, DMF_CNT_COUNT * 8, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> all((size_t)DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE);
+    DMF_CUDA(cudaMemcpy(all.data(), c->d_counters.p, all.size() * 8, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < DMF_CNT_COUNT; j++) { out[j] = 0; for (int s = 0; s < DMF_COUNTER_SLOTS; s++) out[j] += all[(size_t)s * DMF_COUNTER_STRIDE + j]; }
     out[DMF_CNT_LAUNCHES] = c->launches;
     return 0;
 }
@@ -606,7 +608,7 @@ int dmf_reset_counters(dmf_ctx* c) {
     if (!c) return fail("null context");
     DMF_CUDA(cudaSetDevice(c->device));
     DMF_CUDA(cudaDeviceSynchronize());
-    DMF_CUDA(cudaMemset(c->d_counters.p, 0, DMF_CNT_COUNT * 8));
+    DMF_CUDA(cudaMemset(c->d_counters.p, 0, DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
     c->launches = 0;
     return 0;
 }

@@ -9,6 +9,16 @@
 
 typedef unsigned long long u64;
 
+// The DMF_CNT_* counters are kept in DMF_COUNTER_SLOTS replicas, one 128-byte line each, and summed by dmf_counters():
+// millions of blocks adding to four shared addresses would serialise in one L2 slice (same-address atomics retire at
+// about one per clock), which at ~5 M atomics per launch was a measurable part of the march kernels' duration.
+#define DMF_COUNTER_SLOTS 256
+#define DMF_COUNTER_STRIDE 16
+__device__ __forceinline__ u64* counter_slot(u64* base) {
+    const unsigned b = blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * gridDim.x * gridDim.y;
+    return base + (size_t)((b * 2654435761u) >> 24) * DMF_COUNTER_STRIDE;    // multiplicative hash -> 256 slots
+}
+
 // HBM layout of a VoxelVolume (reference include/Volume.hpp:50-78):
 //   bits     uint32 words of a linear bit grid over the PADDED index space [0,dim_x] x [0,dim_y] x [0,dim_z]
 //            (pdim = dim + 1 per axis, z fastest like voxels_[x][y][z]); bit index = (x*pdim_y + y)*pdim_z + z.

@@ -135,11 +135,12 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
     unsigned c3 = 0, c5 = 0, c8 = 0;
     if (c358) { c3 = __reduce_add_sync(0xffffffffu, n_exact); c5 = __reduce_add_sync(0xffffffffu, ties); c8 = __reduce_add_sync(0xffffffffu, n_f64); }
     if (lane == 0) {
+        u64* const gcnt = counter_slot(a.counters);
         atomicAdd(&s_cnt[0], (unsigned long long)c0); atomicAdd(&s_cnt[1], (unsigned long long)c1);
         atomicAdd(&s_cnt[2], (unsigned long long)c2); atomicAdd(&s_cnt[3], (unsigned long long)c9);
-        if (c3) atomicAdd(a.counters + 3, (unsigned long long)c3);
-        if (c5) atomicAdd(a.counters + 5, (unsigned long long)c5);
-        if (c8) atomicAdd(a.counters + 8, (unsigned long long)c8);
+        if (c3) atomicAdd(gcnt + 3, (unsigned long long)c3);
+        if (c5) atomicAdd(gcnt + 5, (unsigned long long)c5);
+        if (c8) atomicAdd(gcnt + 8, (unsigned long long)c8);
         __threadfence_block();
         const unsigned long long ticket = atomicAdd(&s_cnt[4], 1ull);
         if (ticket == (unsigned long long)(blockDim.x >> 5) - 1ull) {
@@ -148,7 +149,7 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const unsigned long long val = *((volatile unsigned long long*)&s_cnt[j]);
-                if (val) atomicAdd(a.counters + slot[j], val);
+                if (val) atomicAdd(gcnt + slot[j], val);
             }
         }
     }
@@ -456,7 +457,7 @@ __device__ __forceinline__ unsigned probe_index(const VolDev& v, float px, float
 }
 
 template <int MODE, bool EXACT>
-__global__ void __launch_bounds__(SKIP_THREADS, 8) k_forward_dist(const FwdArgs a) {
+__global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs a) {
     __shared__ unsigned long long s_cnt[5];
     const int view = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

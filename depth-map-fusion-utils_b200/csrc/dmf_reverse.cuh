@@ -183,7 +183,7 @@ __device__ __forceinline__ void flush_counters(u64* counters, unsigned n_samples
 #pragma unroll
     for (int j = 0; j < 9; j++) {
         for (int o = 16; o; o >>= 1) c[j] += __shfl_down_sync(0xffffffffu, c[j], o);
-        if ((threadIdx.x & 31) == 0 && c[j]) atomicAdd(counters + slot[j], c[j]);
+        if ((threadIdx.x & 31) == 0 && c[j]) atomicAdd(counter_slot(counters) + slot[j], c[j]);
     }
 }
 
