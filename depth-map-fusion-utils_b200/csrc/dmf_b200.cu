@@ -5,6 +5,7 @@
 #include "dmf_forward.cuh"
 #include "dmf_reverse.cuh"
 #include "dmf_distance.cuh"
+#include "dmf_integrate.cuh"
 #include "dmf_setcover.cuh"
 #include <algorithm>
 #include <climits>

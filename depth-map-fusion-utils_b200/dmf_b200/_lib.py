@@ -49,6 +49,7 @@ SYMBOLS = {
     "dmf_set_camera": (C.c_int, [vp, fp, C.c_int, C.c_int]),
     "dmf_upload_volume": (C.c_int, [vp, dp, dp, ip, u64p, C.c_size_t, u32p, fp]),
     "dmf_volume_from_points": (C.c_int, [vp, dp, ip, fp, fp, C.c_size_t]),
+    "dmf_volume_from_points_gpu": (C.c_int, [vp, dp, ip, fp, fp, C.c_size_t]),
     "dmf_volume_info": (C.c_int, [vp, ip, dp, dp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "dmf_volume_get_occupied": (C.c_int, [vp, u64p]),
     "dmf_volume_get_normals": (C.c_int, [vp, u32p, fp]),

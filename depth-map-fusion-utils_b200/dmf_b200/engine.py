@@ -117,8 +117,9 @@ class Camera:
 class VoxelVolume:
     """VoxelVolume -- include/Volume.hpp:50-78.  The occupancy itself lives in HBM (bit bricks + rank directory)."""
 
-    def __init__(self, ctx: Optional[Context] = None):
+    def __init__(self, ctx: Optional[Context] = None, integrate_on_gpu: bool = False):
         self.ctx = ctx
+        self.integrate_on_gpu = integrate_on_gpu     # True: dmf_volume_from_points_gpu (K0) instead of the host builder
         self.occupied_cells_ = np.zeros(0, np.uint64)
         self._pts = []
         self._nrm = []
@@ -165,8 +166,8 @@ class VoxelVolume:
             raise DmfError("VoxelVolume: setDimensions/setVolumeSize/constructVolume must be called first")
         pts = np.concatenate(self._pts) if self._pts else np.zeros((0, 3), np.float32)
         nrm = np.concatenate(self._nrm) if self._nrm else None
-        check(ctx.lib.dmf_volume_from_points(ctx.h, _ptr(self._bounds, C.c_double), _ptr(self._req_dims, C.c_int),
-                                             _ptr(pts, C.c_float), _ptr(nrm, C.c_float), len(pts)))
+        build = ctx.lib.dmf_volume_from_points_gpu if self.integrate_on_gpu else ctx.lib.dmf_volume_from_points
+        check(build(ctx.h, _ptr(self._bounds, C.c_double), _ptr(self._req_dims, C.c_int), _ptr(pts, C.c_float), _ptr(nrm, C.c_float), len(pts)))
         dims = np.zeros(3, np.int32)
         deltas = np.zeros(3, np.float64)
         vs, no, nn = C.c_double(), C.c_size_t(), C.c_size_t()

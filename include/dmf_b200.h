@@ -74,6 +74,11 @@ int dmf_upload_volume(dmf_ctx* ctx, const double bounds[6], const double delta[3
 int dmf_volume_from_points(dmf_ctx* ctx, const double bounds[6], const int dims[3],
                            const float* xyz, const float* normals, size_t n_points);
 
+/* The same with integratePointCloud itself on the GPU (first-insertion order of occupied_cells_ and point order of every
+ * voxel's normal list preserved); for large clouds.  Host pointers in, identical volume out. */
+int dmf_volume_from_points_gpu(dmf_ctx* ctx, const double bounds[6], const int dims[3],
+                               const float* xyz, const float* normals, size_t n_points);
+
 /* dims[3], deltas[3], n_occ, n_normals of the uploaded volume (any pointer may be NULL) */
 int dmf_volume_info(dmf_ctx* ctx, int dims[3], double deltas[3], double* voxel_size, size_t* n_occ, size_t* n_normals);
 int dmf_volume_get_occupied(dmf_ctx* ctx, uint64_t* ids /* n_occ */);

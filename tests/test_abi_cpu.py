@@ -82,3 +82,22 @@ def test_scenes_are_deterministic(dmf):
     assert p.shape == (1024, 12) and p.dtype == np.float32 and len(np.unique(p, axis=0)) == 1024
     bits = np.array([0b101, 1 << 63], np.uint64)
     assert list(dmf.bits_to_indices(bits)) == [0, 2, 127]
+
+
+def test_pose_file_wire_format(dmf, tmp_path):
+    """FileRoutines.hpp:69-112: count line, then 3 comma-separated rows per pose, %g formatting"""
+    from dmf_b200.posefile import read_camera_locations, write_camera_locations
+    poses = dmf.scenes.poses_sphere_lookat(1.0, 5)
+    path = str(tmp_path / "cams.txt")
+    write_camera_locations(path, poses)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "5" and len(lines) == 16 and all(len(l.split(",")) == 4 for l in lines[1:])
+    assert lines[2].split(",")[0] in ("-1", "1") or "." in lines[2] or "e" in lines[2]
+    back = read_camera_locations(path)
+    assert back.shape == (5, 12)
+    np.testing.assert_allclose(back, poses, rtol=1e-5, atol=1e-6)       # 6 significant digits survive
+    write_camera_locations(path, back)                                   # idempotent from the second write on
+    assert np.array_equal(read_camera_locations(path), back)
+    open(path, "w").write("1\n1,0,0\n0,1,0,0\n0,0,1,0\n")
+    with pytest.raises(ValueError):
+        read_camera_locations(path)

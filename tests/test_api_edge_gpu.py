@@ -120,3 +120,48 @@ def test_many_small_views_are_chunked(dmf, oracle, ctx):
     ov = oracle.volume_from_scene(sc)
     for i in (0, 777, 4999):
         assert np.array_equal(r["depth"][i], oracle.forward(ov, K, 12, 16, poses[i], 0, 8, False)["depth"])
+
+
+@pytest.mark.parametrize("dims,L", [((32, 32, 32), 1.0), ((93, 40, 57), 0.937), ((128, 128, 128), 1.024)])
+def test_integrate_point_cloud_on_gpu(dmf, oracle, ctx, dims, L):
+    """K0: integratePointCloud on the device == the oracle's (Volume.hpp:199-228): first-insertion order of
+    occupied_cells_, per-voxel normal lists in point order; ragged clouds with repeats, out-of-bounds and boundary points"""
+    rng = np.random.default_rng(5)
+    n = 60000
+    pts = rng.uniform(-0.05 * L, 1.05 * L, size=(n, 3)).astype(np.float32)
+    pts[:2000] = pts[rng.integers(2000, n, 2000)]                        # exact repeats -> several normals per voxel
+    pts[100] = [0.0, 0.5 * L, 0.5 * L]; pts[101] = [L, 0.5 * L, 0.5 * L]  # on the faces: validPoints is strict
+    pts[102] = [np.float32(L) - np.float32(1e-7), 0.5 * L, 0.5 * L]
+    nrm = rng.normal(size=(n, 3)).astype(np.float32)
+    bounds = [0, L, 0, L, 0, L]
+    ov = oracle.Volume(bounds, dims)
+    ov.integrate(pts, nrm)
+    off_o, nrm_o = ov.normals_csr()
+    for on_gpu in (True, False):
+        gv = dmf.VoxelVolume(ctx, integrate_on_gpu=on_gpu)
+        gv.setDimensions(*bounds); gv.setVolumeSize(*dims); gv.constructVolume(); gv.integratePointCloud(pts, nrm)
+        gv._commit(ctx)
+        assert (gv.xdim_, gv.ydim_, gv.zdim_) == tuple(int(d) for d in ov.dims)
+        assert np.array_equal(gv.occupied_cells_, ov.occupied()), on_gpu
+        off_g, nrm_g = gv.normals_csr()
+        assert np.array_equal(off_g, off_o) and np.array_equal(nrm_g, nrm_o), on_gpu
+    # empty cloud and a cloud entirely outside
+    for cloud in (np.zeros((0, 3), np.float32), np.full((10, 3), 5.0, np.float32)):
+        gv = dmf.VoxelVolume(ctx, integrate_on_gpu=True)
+        gv.setDimensions(*bounds); gv.setVolumeSize(*dims); gv.constructVolume(); gv.integratePointCloud(cloud, np.zeros_like(cloud))
+        gv._commit(ctx)
+        assert len(gv.occupied_cells_) == 0
+
+
+def test_gpu_integrated_volume_marches_identically(dmf, ctx):
+    sc = dmf.scenes.scene("S128-clutter")
+    K = dmf.scenes.REFERENCE_K
+    poses = dmf.scenes.poses_sphere_lookat(1.024, 60)[::20]
+    res = []
+    for on_gpu in (False, True):
+        gv = dmf.VoxelVolume(ctx, integrate_on_gpu=on_gpu)
+        gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+        eng = dmf.RayTracingEngine(dmf.Camera(K), ctx)
+        res.append((eng.forward_views(gv, poses, dmf.MODE_GOOD_POINTS, sc.zdelta, False, want=("depth", "visibility")), eng.reverse_views(gv, poses, want=("visibility",))))
+    assert np.array_equal(res[0][0]["depth"], res[1][0]["depth"]) and np.array_equal(res[0][0]["visibility"], res[1][0]["visibility"])
+    assert np.array_equal(res[0][1]["visibility"], res[1][1]["visibility"])
