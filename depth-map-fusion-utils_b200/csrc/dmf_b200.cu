@@ -247,40 +247,13 @@ void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, dim3 grid, cudaStr
         dim3 g((a.Wc + SKIP_TILE_W - 1) / SKIP_TILE_W, (a.Hc + SKIP_TILE_H - 1) / SKIP_TILE_H, grid.z);
         const bool exact = a.vol.err32[0] == 0.0f && a.vol.err32[1] == 0.0f && a.vol.err32[2] == 0.0f;
         if (fmt == DMF_GRID_BYTE) {
-            // batches: table rows staged in shared memory once per tile and view group (k_forward_tile); small batches or
-            // very long tables: rows read through L1/L2 (k_forward_dist)
-            const int n_views = (int)grid.z;
-            const size_t smem32 = (size_t)a.S * (32 + TILE_H + 1) * 4, smem16 = (size_t)a.S * (16 + TILE_H + 1) * 4;
-            if (n_views >= 8 && smem32 <= 100 * 1024) {
-                dim3 gt((a.Wc + 31) / 32, (a.Hc + TILE_H - 1) / TILE_H, (n_views + TILE_VIEWS - 1) / TILE_VIEWS);
-                if (exact) k_forward_tile<MODE, true, 32><<<gt, 32 * TILE_H, smem32, st>>>(a, n_views);
-                else k_forward_tile<MODE, false, 32><<<gt, 32 * TILE_H, smem32, st>>>(a, n_views);
-            } else if (n_views >= 8 && smem16 <= 110 * 1024) {
-                dim3 gt((a.Wc + 15) / 16, (a.Hc + TILE_H - 1) / TILE_H, (n_views + TILE_VIEWS - 1) / TILE_VIEWS);
-                if (exact) k_forward_tile<MODE, true, 16><<<gt, 16 * TILE_H, smem16, st>>>(a, n_views);
-                else k_forward_tile<MODE, false, 16><<<gt, 16 * TILE_H, smem16, st>>>(a, n_views);
-            } else if (exact) k_forward_dist<MODE, true><<<g, SKIP_THREADS, 0, st>>>(a);
+            if (exact) k_forward_dist<MODE, true><<<g, SKIP_THREADS, 0, st>>>(a);
             else k_forward_dist<MODE, false><<<g, SKIP_THREADS, 0, st>>>(a);
         } else k_forward_skip<MODE, 0><<<g, SKIP_THREADS, 0, st>>>(a);
     } else {
         if (fmt == DMF_GRID_BYTE) k_forward<MODE, 1><<<grid, FWD_THREADS, 0, st>>>(a);
         else k_forward<MODE, 0><<<grid, FWD_THREADS, 0, st>>>(a);
     }
-}
-
-template <int MODE>
-int enable_tile_smem_mode() {
-    const int bytes = 112 * 1024;
-    DMF_CUDA(cudaFuncSetAttribute(k_forward_tile<MODE, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    DMF_CUDA(cudaFuncSetAttribute(k_forward_tile<MODE, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    DMF_CUDA(cudaFuncSetAttribute(k_forward_tile<MODE, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    DMF_CUDA(cudaFuncSetAttribute(k_forward_tile<MODE, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    return 0;
-}
-int enable_tile_smem() {
-    DMF_TRY(enable_tile_smem_mode<0>()); DMF_TRY(enable_tile_smem_mode<1>()); DMF_TRY(enable_tile_smem_mode<2>());
-    DMF_TRY(enable_tile_smem_mode<3>()); DMF_TRY(enable_tile_smem_mode<4>());
-    return 0;
 }
 
 struct FwdPlan { int z0, cstride, rstride; };
@@ -409,7 +382,6 @@ int dmf_create(dmf_ctx** out, int device) {
     DMF_TRY(c->d_counters.reserve(DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
     DMF_CUDA(cudaMemset(c->d_counters.p, 0, DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
     DMF_CUDA(cudaFuncSetAttribute(k_order_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * ORD_THREADS * 4));
-    DMF_TRY(enable_tile_smem());
     c->angle = bisect_angle_test();
     *out = c;
     return 0;

@@ -69,12 +69,12 @@ __global__ void k_build_tables(float* xtab, float* ytab, float* ztab, float* dcx
 }
 
 // Per-ray epilogue shared by k_forward and k_forward_skip: outputs, visibility, marks, discovery keys, counters.
-// Per-ray outputs of one view: depth / point / voxel id images, visibility bit, marks, discovery keys.  Returns the number
-// of acos-band ties met by the good-point test.
 template <int MODE>
-__device__ __forceinline__ unsigned forward_outputs(const FwdArgs& a, int view, int ci, int ri, bool active, int hit_k,
-                                                    int hx, int hy, int hz, float hpx, float hpy, float hpz, float m03, float m13, float m23) {
+__device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long long* s_cnt, int view, int ci, int ri, bool active, int hit_k,
+                                                 int hx, int hy, int hz, float hpx, float hpy, float hpz, float m03, float m13, float m23,
+                                                 unsigned n_samples, unsigned n_inb, unsigned n_exact, unsigned n_f64, unsigned n_skip) {
     const VolDev& v = a.vol;
+    const int lane = threadIdx.x & 31;
     const bool hit = hit_k >= 0;
     const int z_depth = a.z0 + hit_k * a.zdelta;
     if (active) {
@@ -127,16 +127,10 @@ __device__ __forceinline__ unsigned forward_outputs(const FwdArgs& a, int view, 
         }
     }
 
-    return ties;
-}
-
-// Counters: warp reduce -> shared; the LAST warp of the block to get here flushes them with a few global atomics.
-// No block barrier: warps whose rays ended early must not sit on a barrier waiting for the longest ray of the block.
-__device__ __forceinline__ void forward_counters(const FwdArgs& a, unsigned long long* s_cnt, unsigned n_samples, unsigned n_inb, unsigned n_hits,
-                                                 unsigned n_exact, unsigned n_f64, unsigned n_skip, unsigned ties) {
-    const int lane = threadIdx.x & 31;
+    // ---- counters: warp reduce -> shared; the LAST warp of the block to get here flushes them with a few global atomics.
+    // No block barrier: warps whose rays ended early must not sit on a barrier waiting for the longest ray of the block.
     const unsigned c0 = __reduce_add_sync(0xffffffffu, n_samples), c1 = __reduce_add_sync(0xffffffffu, n_inb);
-    const unsigned c2 = __reduce_add_sync(0xffffffffu, n_hits), c9 = __reduce_add_sync(0xffffffffu, n_skip);
+    const unsigned c2 = __reduce_add_sync(0xffffffffu, hit ? 1u : 0u), c9 = __reduce_add_sync(0xffffffffu, n_skip);
     const unsigned c358 = __reduce_add_sync(0xffffffffu, n_exact | ties | n_f64);      // almost always 0: reduce individually only then
     unsigned c3 = 0, c5 = 0, c8 = 0;
     if (c358) { c3 = __reduce_add_sync(0xffffffffu, n_exact); c5 = __reduce_add_sync(0xffffffffu, ties); c8 = __reduce_add_sync(0xffffffffu, n_f64); }
@@ -161,14 +155,6 @@ __device__ __forceinline__ void forward_counters(const FwdArgs& a, unsigned long
     }
 }
 
-
-template <int MODE>
-__device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long long* s_cnt, int view, int ci, int ri, bool active, int hit_k,
-                                                 int hx, int hy, int hz, float hpx, float hpy, float hpz, float m03, float m13, float m23,
-                                                 unsigned n_samples, unsigned n_inb, unsigned n_exact, unsigned n_f64, unsigned n_skip) {
-    const unsigned ties = forward_outputs<MODE>(a, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23);
-    forward_counters(a, s_cnt, n_samples, n_inb, hit_k >= 0 ? 1u : 0u, n_exact, n_f64, n_skip, ties);
-}
 
 constexpr int FWD_THREADS = 256;      // 8 warps: 4 across x 2 down, each warp an 8x4 pixel tile
 constexpr int FWD_TILE_W = 32, FWD_TILE_H = 8;
@@ -587,146 +573,6 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
     }
     const unsigned n_samples = active ? (unsigned)min(k, S) : 0u;
     forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23, n_samples, n_inb, n_exact, n_f64, n_skip);
-}
-
-// ---- K1 on distance bytes with the projectPoint rows staged in shared memory: k_forward_tile -------------------------
-// The tables x[k][c], y[k][r], z[k] do not depend on the view, and in k_forward_dist they are most of the global loads
-// (six of the eight per iteration, scattered because neighbouring rays sit at different k): the march there is limited by
-// outstanding memory requests, not by arithmetic or occupancy.  Here one block owns a TW x 8 pixel
-// tile, copies the tile's rows for ALL z-planes into shared memory once ((TW + 8 + 1) * S floats: 81 KB for TW = 32,
-// S = 495) and then marches the tile for a whole group of views, so the fill is amortised and the only global loads left
-// in the loop are the distance bytes.  Same probes, same results, same counters as k_forward_dist.
-constexpr int TILE_H = 8;
-constexpr int TILE_VIEWS = 16;        // views marched per block (the table fill is amortised over them)
-
-template <int MODE, bool EXACT, int TW>
-__global__ void __launch_bounds__(TW * TILE_H) k_forward_tile(const FwdArgs a, int n_views) {
-    extern __shared__ __align__(16) float s_tab[];
-    __shared__ unsigned long long s_cnt[5];
-    const int S = a.S;
-    float* const sx = s_tab;                    // [S][TW]
-    float* const sy = s_tab + (size_t)S * TW;   // [S][TILE_H]
-    float* const sz = sy + (size_t)S * TILE_H;  // [S]
-    constexpr int WPR = TW / 8;                 // warps per tile row of warps
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lc = (warp % WPR) * 8 + (lane & 7), lr = (warp / WPR) * 4 + (lane >> 3);
-    const int ci = blockIdx.x * TW + lc, ri = blockIdx.y * TILE_H + lr;
-    const bool active = ci < a.Wc && ri < a.Hc;
-    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0ull;
-    // ---- stage the tile's table rows (coalesced over columns) ----
-    for (int i = threadIdx.x; i < S * TW; i += TW * TILE_H) {
-        const int kk = i / TW, cc = i % TW, col = blockIdx.x * TW + cc;
-        sx[i] = col < a.Wc ? __ldg(a.xtab + (size_t)kk * a.Wc + col) : 0.f;
-    }
-    for (int i = threadIdx.x; i < S * TILE_H; i += TW * TILE_H) {
-        const int kk = i / TILE_H, rr = i % TILE_H, row = blockIdx.y * TILE_H + rr;
-        sy[i] = row < a.Hc ? __ldg(a.ytab + (size_t)kk * a.Hc + row) : 0.f;
-    }
-    for (int i = threadIdx.x; i < S; i += TW * TILE_H) sz[i] = __ldg(a.ztab + i);
-    __syncthreads();
-
-    const VolDev& v = a.vol;
-    const float lo0 = v.lo[0], lo1 = v.lo[1], lo2 = v.lo[2], hi0 = v.hi[0], hi1 = v.hi[1], hi2 = v.hi[2];
-    const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2], cc0 = v.c32[0], cc1 = v.c32[1], cc2 = v.c32[2];
-    const float er0 = v.err32[0], er1 = v.err32[1], er2 = v.err32[2];
-    const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
-    const unsigned char* __restrict__ gbytes = v.bytes;
-    const int cic = active ? ci : 0, ric = active ? ri : 0;
-    const float dcx = __ldg(a.dcx + cic), dcy = __ldg(a.dcy + ric);
-    const float zdm = (float)a.zdelta * 0.001f;
-    const float* const px_tab = sx + lc;
-    const float* const py_tab = sy + lr;
-
-    unsigned t_samples = 0, t_inb = 0, t_hits = 0, t_exact = 0, t_f64 = 0, t_skip = 0, t_ties = 0;
-    const int v_begin = blockIdx.z * TILE_VIEWS, v_end = min(n_views, v_begin + TILE_VIEWS);
-    for (int view = v_begin; view < v_end; view++) {
-        const float* P = a.poses + 12 * (size_t)view;
-        const float m00 = __ldg(P + 0), m01 = __ldg(P + 1), m02 = __ldg(P + 2), m03 = __ldg(P + 3);
-        const float m10 = __ldg(P + 4), m11 = __ldg(P + 5), m12 = __ldg(P + 6), m13 = __ldg(P + 7);
-        const float m20 = __ldg(P + 8), m21 = __ldg(P + 9), m22 = __ldg(P + 10), m23 = __ldg(P + 11);
-        const float g0 = fmaf(m00, dcx, fmaf(m01, dcy, m02)), g1 = fmaf(m10, dcx, fmaf(m11, dcy, m12)), g2 = fmaf(m20, dcx, fmaf(m21, dcy, m22));
-        const float qbmax = fmaxf(fabsf(zdm * g0 * in0), fmaxf(fabsf(zdm * g1 * in1), fabsf(zdm * g2 * in2)));
-        const float kEps = 9.5367431640625e-07f;   // 16 * 2^-24
-        const float e0 = kEps * (fabsf(m00) * a.dcx_max + fabsf(m01) * a.dcy_max + fabsf(m02) + fabsf(m03) + fabsf((float)v.vmin[0])) * fabsf(in0);
-        const float e1 = kEps * (fabsf(m10) * a.dcx_max + fabsf(m11) * a.dcy_max + fabsf(m12) + fabsf(m13) + fabsf((float)v.vmin[1])) * fabsf(in1);
-        const float e2 = kEps * (fabsf(m20) * a.dcx_max + fabsf(m21) * a.dcy_max + fabsf(m22) + fabsf(m23) + fabsf((float)v.vmin[2])) * fabsf(in2);
-        const bool skip_ok = fmaxf(e0, fmaxf(e1, e2)) <= 0.1f;
-        const int rfix = skip_ok ? __float2int_rd(fminf(__fdividef(1024.0f, fmaxf(qbmax, 1e-3f)) * 0.999999f, 1048576.0f)) : 0;
-
-        int hit_k = -1, hx = 0, hy = 0, hz = 0;
-        float hpx = 0.f, hpy = 0.f, hpz = 0.f;
-        unsigned n_inb = 0, n_skip = 0;
-        int k = 0;
-        unsigned iter = 0;
-        int oob_wait = 0;
-        if (active) {
-            while (k < S) {
-                if (MODE == 4 && (iter++ & 7u) == 0u) {
-                    const int cur = *((volatile int*)(a.min_depth + view));
-                    if (a.z0 + k * a.zdelta > cur) break;
-                }
-                const int kb = min(k + 1, S - 1);
-                const float xa = px_tab[k * TW], ya = py_tab[k * TILE_H], za = sz[k];
-                const float xb = px_tab[kb * TW], yb = py_tab[kb * TILE_H], zb = sz[kb];
-                const float pxa = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, xa), __fmul_rn(m01, ya)), __fmul_rn(m02, za)), m03);
-                const float pya = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, xa), __fmul_rn(m11, ya)), __fmul_rn(m12, za)), m13);
-                const float pza = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, xa), __fmul_rn(m21, ya)), __fmul_rn(m22, za)), m23);
-                if (!(pxa > lo0 && pxa < hi0 && pya > lo1 && pya < hi1 && pza > lo2 && pza < hi2)) {
-                    int kn = k + 1;
-                    if (skip_ok && oob_wait == 0) {
-                        const float z0m = (float)a.z0 * 0.001f, kf = (float)k;
-                        const float qa[3] = {fmaf(fmaf(z0m, g0, m03), in0, cc0), fmaf(fmaf(z0m, g1, m13), in1, cc1), fmaf(fmaf(z0m, g2, m23), in2, cc2)};
-                        const float qb[3] = {zdm * g0 * in0, zdm * g1 * in1, zdm * g2 * in2};
-                        float t0 = -1e30f, t1 = 1e30f;
-#pragma unroll
-                        for (int ax = 0; ax < 3; ax++) {
-                            if (fabsf(qb[ax]) > 1e-12f) {
-                                const float r = 1.0f / qb[ax];
-                                const float ta = (-0.25f - qa[ax]) * r, tb = (v.ext[ax] + 0.25f - qa[ax]) * r;
-                                t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
-                            } else if (qa[ax] < -0.25f || qa[ax] > v.ext[ax] + 0.25f) { t0 = 1e30f; }
-                        }
-                        if (!(t0 <= t1) || t1 + 1.0f < kf) kn = S;
-                        else if (t0 - 1.0f > kf + 1.0f) kn = min(S, max(k + 1, __float2int_rd(t0 - 1.0f)));
-                        if (kn == k + 1) oob_wait = 4;
-                    } else if (oob_wait > 0) oob_wait--;
-                    k = kn;
-                    continue;
-                }
-                oob_wait = 0;
-                const float pxb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, xb), __fmul_rn(m01, yb)), __fmul_rn(m02, zb)), m03);
-                const float pyb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, xb), __fmul_rn(m11, yb)), __fmul_rn(m12, zb)), m13);
-                const float pzb = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, xb), __fmul_rn(m21, yb)), __fmul_rn(m22, zb)), m23);
-                const bool inb_b = (k + 1 < S) && pxb > lo0 && pxb < hi0 && pyb > lo1 && pyb < hi1 && pzb > lo2 && pzb < hi2;
-                int ixa, iya, iza, ixb = 0, iyb = 0, izb = 0;
-                const unsigned idxa = probe_index<EXACT>(v, pxa, pya, pza, in0, in1, in2, cc0, cc1, cc2, er0, er1, er2, pny, pnz, ixa, iya, iza, t_f64, t_exact);
-                const unsigned da = __ldg(gbytes + idxa);
-                unsigned db = 1u;
-                if (inb_b) {
-                    const unsigned idxb = probe_index<EXACT>(v, pxb, pyb, pzb, in0, in1, in2, cc0, cc1, cc2, er0, er1, er2, pny, pnz, ixb, iyb, izb, t_f64, t_exact);
-                    db = __ldg(gbytes + idxb);
-                }
-                n_inb++;
-                if (da == 0u) { hit_k = k; hx = ixa; hy = iya; hz = iza; hpx = pxa; hpy = pya; hpz = pza; k++; break; }
-                const int na = min(((int)(4u * da) - 5) * rfix >> 12, S - k - 1);
-                if (na >= 1 || !inb_b) {
-                    const int n = max(na, 0);
-                    n_inb += (unsigned)n; n_skip += (unsigned)n;
-                    k += n + 1;
-                    continue;
-                }
-                n_inb++;
-                if (db == 0u) { hit_k = k + 1; hx = ixb; hy = iyb; hz = izb; hpx = pxb; hpy = pyb; hpz = pzb; k += 2; break; }
-                const int nb = max(min(((int)(4u * db) - 5) * rfix >> 12, S - k - 2), 0);
-                n_inb += (unsigned)nb; n_skip += (unsigned)nb;
-                k += nb + 2;
-            }
-        }
-        t_samples += active ? (unsigned)min(k, S) : 0u;
-        t_inb += n_inb; t_skip += n_skip; t_hits += hit_k >= 0 ? 1u : 0u;
-        t_ties += forward_outputs<MODE>(a, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23);
-    }
-    forward_counters(a, s_cnt, t_samples, t_inb, t_hits, t_exact, t_f64, t_skip, t_ties);
 }
 
 // CLASSIFY: `if(voxel->view==0) voxel->view=view` over a batch of views in call order (:354-355)
