@@ -361,6 +361,19 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     rv_s = float(t.item())
 
+    # ---- single-view calls, the way the reference's drivers use the engine (one pose per call, id list returned) ----
+    single = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        for i in range(20):
+            eng.rayTraceAndGetPoints(vol, poses[i % V], sc.zdelta, False)
+        t1 = time.perf_counter()
+        for i in range(20):
+            eng.reverseRayTraceFast(vol, poses[i % V], False)
+        t2 = time.perf_counter()
+        single = {"rayTraceAndGetPoints_ms_per_call": 1e3 * (t1 - t0) / 20, "reverseRayTraceFast_ms_per_call": 1e3 * (t2 - t1) / 20,
+                  "note": "one pose per call through the host-buffer C ABI incl. the discovery-ordered id list (what the drop-in RayTracingEngine does per call)"}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         # algorithmic bytes of one k_forward launch: 1/8 B (bit grid) or 1 B (byte grid) per in-bounds sample,
@@ -396,6 +409,7 @@ def run_b200(args):
             "reverse_sweep": {"what": "reverseRayTraceFast over the same views via dmf_reverse (host poses in, visibility bitsets out)",
                               "views_per_s": rv_steps * V * world / rv_s, "voxel_rays_per_s": rv_steps * V * world * n_occ / rv_s,
                               "ms_per_step": 1e3 * rv_s / rv_steps, "kernel_ms_per_step": rv_hot},
+            "single_view_calls": single,
             "clocks": clocks,
             "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
         }
