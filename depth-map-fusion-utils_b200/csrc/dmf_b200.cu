@@ -555,9 +555,13 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
         if (want_ids) {
             DMF_TRY(c->d_tmp_a.reserve(nv * R * 4)); DMF_TRY(c->d_tmp_b.reserve(nv * R * 4)); DMF_TRY(c->d_out_occ.reserve(nv * R * 4));
             DMF_TRY(c->d_n_ids.reserve((size_t)nv * 4)); DMF_TRY(c->d_offsets.reserve((size_t)(nv + 1) * 8));
-            k_order_ids<<<nv, ORD_THREADS, 32 * ORD_THREADS * 4, st>>>(rk, ro, fk, c->d_tmp_a.as<unsigned>(), c->d_tmp_b.as<unsigned>(),
-                                                                     c->d_out_occ.as<int>(), c->d_n_ids.as<int>(), (int)R, (int)c->n_occ);
-            c->launches++;
+            const int nb = (int)((R + WIN_BLOCK - 1) / WIN_BLOCK);
+            DMF_TRY(c->d_misc[0].reserve((size_t)nv * nb * 4)); DMF_TRY(c->d_misc[1].reserve((size_t)nv * nb * 4));
+            k_win_count<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[0].as<unsigned>(), (int)R, (int)c->n_occ, nb);
+            k_win_offsets<<<nv, 1024, 0, st>>>(c->d_misc[0].as<unsigned>(), c->d_misc[1].as<unsigned>(), c->d_n_ids.as<int>(), nb);
+            k_win_compact<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[1].as<unsigned>(), c->d_tmp_a.as<unsigned>(), (int)R, (int)c->n_occ, nb);
+            k_order_ids<<<nv, ORD_THREADS, 32 * ORD_THREADS * 4, st>>>(ro, c->d_tmp_a.as<unsigned>(), c->d_tmp_b.as<unsigned>(), c->d_out_occ.as<int>(), c->d_n_ids.as<int>(), (int)R);
+            c->launches += 4;
             DMF_CUDA(cudaGetLastError());
             std::vector<int> n_ids(nv);
             DMF_CUDA(cudaMemcpyAsync(n_ids.data(), c->d_n_ids.p, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));

@@ -652,26 +652,93 @@ __device__ void order_pass(const unsigned* src, const int* ray_occ, const unsign
     __syncthreads();
 }
 
-// grid = n_views.  tmp_a/tmp_b: [n_views][R] scratch.  out_occ: [n_views][R] winners' occupied ordinals in
-// discovery order; n_ids[view] their count.
-__global__ void __launch_bounds__(ORD_THREADS) k_order_ids(const unsigned* ray_key, const int* ray_occ, const unsigned* first_key,
-                                                           unsigned* tmp_a, unsigned* tmp_b, int* out_occ, int* n_ids, int R, int n_occ) {
+// Stage 1 (multi-block, fully parallel over the lattice): stable compaction of the winners' keys in lattice order.
+//   k_win_count   blk_cnt[view][b] = winners among lattice entries [b*WIN_BLOCK, (b+1)*WIN_BLOCK)
+//   k_win_offsets per view: exclusive scan of blk_cnt -> blk_off, total -> n_win[view]
+//   k_win_compact tmp[view][blk_off + rank inside the block] = key
+constexpr int WIN_THREADS = 256, WIN_ITEMS = 8, WIN_BLOCK = WIN_THREADS * WIN_ITEMS;
+
+__device__ __forceinline__ bool is_winner(const unsigned* rk, const int* ro, const unsigned* fk, int i, int R, unsigned& key) {
+    if (i >= R) return false;
+    key = rk[i];
+    return key != 0xFFFFFFFFu && fk[ro[i]] == key;
+}
+
+__global__ void __launch_bounds__(WIN_THREADS) k_win_count(const unsigned* ray_key, const int* ray_occ, const unsigned* first_key,
+                                                           unsigned* blk_cnt, int R, int n_occ, int nb) {
+    __shared__ unsigned s_warp[WIN_THREADS / 32];
+    const int view = blockIdx.y;
+    const unsigned* rk = ray_key + (size_t)view * R; const int* ro = ray_occ + (size_t)view * R; const unsigned* fk = first_key + (size_t)view * n_occ;
+    unsigned cnt = 0, key;
+    for (int j = 0; j < WIN_ITEMS; j++) cnt += is_winner(rk, ro, fk, blockIdx.x * WIN_BLOCK + j * WIN_THREADS + threadIdx.x, R, key) ? 1u : 0u;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned t = 0; for (int w = 0; w < WIN_THREADS / 32; w++) t += s_warp[w]; blk_cnt[(size_t)view * nb + blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(1024) k_win_offsets(const unsigned* blk_cnt, unsigned* blk_off, int* n_win, int nb) {
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    const int view = blockIdx.x;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned val = i < nb ? blk_cnt[(size_t)view * nb + i] : 0u;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned x = val;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) { unsigned w = s_warp[lane]; for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; } s_warp[lane] = w; }
+        __syncthreads();
+        const unsigned excl = s_carry + (warp ? s_warp[warp - 1] : 0u) + x - val;
+        if (i < nb) blk_off[(size_t)view * nb + i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + val;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_win[view] = (int)s_carry;
+}
+
+__global__ void __launch_bounds__(WIN_THREADS) k_win_compact(const unsigned* ray_key, const int* ray_occ, const unsigned* first_key,
+                                                             const unsigned* blk_off, unsigned* tmp, int R, int n_occ, int nb) {
+    __shared__ unsigned s_warp[WIN_THREADS / 32];
+    const int view = blockIdx.y;
+    const unsigned* rk = ray_key + (size_t)view * R; const int* ro = ray_occ + (size_t)view * R; const unsigned* fk = first_key + (size_t)view * n_occ;
+    unsigned* out = tmp + (size_t)view * R;
+    unsigned base = blk_off[(size_t)view * nb + blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = 0; j < WIN_ITEMS; j++) {       // rows of WIN_THREADS consecutive lattice entries keep the lattice order
+        unsigned key = 0;
+        const bool w = is_winner(rk, ro, fk, blockIdx.x * WIN_BLOCK + j * WIN_THREADS + threadIdx.x, R, key);
+        const unsigned ballot = __ballot_sync(0xffffffffu, w);
+        if (lane == 0) s_warp[warp] = __popc(ballot);
+        __syncthreads();
+        unsigned before = 0, total = 0;
+        for (int q = 0; q < WIN_THREADS / 32; q++) { const unsigned c = s_warp[q]; if (q < warp) before += c; total += c; }
+        if (w) out[base + before + __popc(ballot & ((1u << lane) - 1u))] = key;
+        base += total;
+        __syncthreads();
+    }
+}
+
+// Stage 2: one block per view sorts the (few) compacted winners by z-plane with the stable 2-pass counting sort.
+// tmp_a holds the compacted keys (n_win[view] of them); out_occ receives the winners' occupied ordinals in discovery order.
+__global__ void __launch_bounds__(ORD_THREADS) k_order_ids(const int* ray_occ, unsigned* tmp_a, unsigned* tmp_b, int* out_occ, const int* n_win, int R) {
     extern __shared__ unsigned s_dyn[];
     unsigned (*s_off)[ORD_THREADS] = (unsigned (*)[ORD_THREADS])s_dyn;
     __shared__ unsigned s_warp[32];
     const int view = blockIdx.x;
-    const unsigned* rk = ray_key + (size_t)view * R;
     const int* ro = ray_occ + (size_t)view * R;
-    const unsigned* fk = first_key + (size_t)view * n_occ;
     unsigned* ta = tmp_a + (size_t)view * R;
     unsigned* tb = tmp_b + (size_t)view * R;
-    unsigned nw = 0, nw2 = 0;
-    order_pass<0>(rk, ro, fk, ta, R, 21, s_off, s_warp, nw);            // low 5 bits of k
-    __threadfence_block();
-    order_pass<1>(ta, nullptr, nullptr, tb, (int)nw, 26, s_off, s_warp, nw2);   // high 5 bits of k
-    __threadfence_block();
-    for (int i = threadIdx.x; i < (int)nw; i += ORD_THREADS) out_occ[(size_t)view * R + i] = ro[tb[i] & 0x1FFFFFu];
-    if (threadIdx.x == 0) n_ids[view] = (int)nw;
+    const int nw = n_win[view];
+    unsigned n1 = 0, n2 = 0;
+    order_pass<1>(ta, nullptr, nullptr, tb, nw, 21, s_off, s_warp, n1);   // low 5 bits of k
+    order_pass<1>(tb, nullptr, nullptr, ta, nw, 26, s_off, s_warp, n2);   // high 5 bits of k
+    for (int i = threadIdx.x; i < nw; i += ORD_THREADS) out_occ[(size_t)view * R + i] = ro[ta[i] & 0x1FFFFFu];
 }
 
 // compact per-view winner lists into one contiguous uint64 id array at host-computed offsets
