@@ -364,6 +364,9 @@ def run_b200(args):
     # ---- single-view calls, the way the reference's drivers use the engine (one pose per call, id list returned) ----
     single = None
     if rank == 0:
+        for i in range(3):                       # warm-up: first calls allocate the id-list scratch
+            eng.rayTraceAndGetPoints(vol, poses[i % V], sc.zdelta, False)
+            eng.reverseRayTraceFast(vol, poses[i % V], False)
         t0 = time.perf_counter()
         for i in range(20):
             eng.rayTraceAndGetPoints(vol, poses[i % V], sc.zdelta, False)
