@@ -498,10 +498,13 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
     unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
     int k = 0;
     const int S = a.S;
-    const float* __restrict__ xt = a.xtab + cic;
-    const float* __restrict__ yt = a.ytab + ric;
+    const float* xt = a.xtab + cic;
+    const float* yt = a.ytab + ric;
     const float* __restrict__ zt = a.ztab;
-    const int Wc = a.Wc, Hc = a.Hc;
+    const unsigned uWc = (unsigned)a.Wc, uHc = (unsigned)a.Hc;
+    // make the per-thread row pointers opaque register values: otherwise the compiler re-derives base + column from the
+    // kernel parameters in every iteration (five 64-bit instructions per load instead of IMAD + IMAD.WIDE)
+    asm volatile("" : "+l"(xt), "+l"(yt));
     unsigned iter = 0;
     int oob_wait = 0;
     if (active) {
@@ -511,9 +514,9 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
                 if (a.z0 + k * a.zdelta > cur) break;
             }
             // ---- probes A = k and B = k+1: loads first, so that both are in flight together ----
-            const int kb = min(k + 1, S - 1);
-            const float xa = __ldg(xt + k * Wc), ya = __ldg(yt + k * Hc), za = __ldg(zt + k);
-            const float xb = __ldg(xt + kb * Wc), yb = __ldg(yt + kb * Hc), zb = __ldg(zt + kb);
+            const unsigned ka = (unsigned)k, kb = (unsigned)min(k + 1, S - 1);     // unsigned: one IMAD.WIDE.U32 per address
+            const float xa = __ldg(xt + ka * uWc), ya = __ldg(yt + ka * uHc), za = __ldg(zt + ka);
+            const float xb = __ldg(xt + kb * uWc), yb = __ldg(yt + kb * uHc), zb = __ldg(zt + kb);
             const float pxa = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m00, xa), __fmul_rn(m01, ya)), __fmul_rn(m02, za)), m03);
             const float pya = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m10, xa), __fmul_rn(m11, ya)), __fmul_rn(m12, za)), m13);
             const float pza = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m20, xa), __fmul_rn(m21, ya)), __fmul_rn(m22, za)), m23);
