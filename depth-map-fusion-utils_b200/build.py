@@ -42,7 +42,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("DMF_NVCC_EXTRA", "").split()          # e.g. "-DDMF_SKIP_WARPS_X=4" for tile-shape experiments
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); nvcc should use the distro g++ on PATH
     env.pop("CXX", None); env.pop("CC", None)
