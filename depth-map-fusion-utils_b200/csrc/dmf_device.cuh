@@ -15,7 +15,7 @@ typedef unsigned long long u64;
 #define DMF_COUNTER_SLOTS 256
 #define DMF_COUNTER_STRIDE 16
 __device__ __forceinline__ u64* counter_slot(u64* base) {
-    const unsigned b = blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * gridDim.x * gridDim.y;
+    const unsigned b = (blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * gridDim.x * gridDim.y) * 32u + (threadIdx.x >> 5);
     return base + (size_t)((b * 2654435761u) >> 24) * DMF_COUNTER_STRIDE;    // multiplicative hash -> 256 slots
 }
 

@@ -113,10 +113,15 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
                 if (good) atomicOr(a.good_bits + (occ >> 5), 1u << (occ & 31));       // :366
             }
             if (MODE == 3) a.view_mark[occ] = 1;                                       // :302
-            if (emit && a.vis) {
+        }
+        if (a.vis) {
+            // neighbouring rays mostly hit the same few voxels: one atomicOr per distinct voxel of the warp, and none if a
+            // (possibly stale, the bits only ever get set) cached read already shows the bit
+            const unsigned peers = __match_any_sync(__activemask(), emit ? occ : -1);
+            if (emit && (unsigned)(threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
                 unsigned* w = a.vis + (size_t)view * a.vis_words32 + (occ >> 5);
-                unsigned m = 1u << (occ & 31);
-                if (!(*((volatile unsigned*)w) & m)) atomicOr(w, m);
+                const unsigned m = 1u << (occ & 31);
+                if (!(*w & m)) atomicOr(w, m);
             }
         }
         if (active && a.ray_key) {
@@ -135,24 +140,17 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
     unsigned c3 = 0, c5 = 0, c8 = 0;
     if (c358) { c3 = __reduce_add_sync(0xffffffffu, n_exact); c5 = __reduce_add_sync(0xffffffffu, ties); c8 = __reduce_add_sync(0xffffffffu, n_f64); }
     if (lane == 0) {
+        // one warp, a handful of result-less atomics (RED) into one of the 256 counter replicas: nothing to wait for
         u64* const gcnt = counter_slot(a.counters);
-        atomicAdd(&s_cnt[0], (unsigned long long)c0); atomicAdd(&s_cnt[1], (unsigned long long)c1);
-        atomicAdd(&s_cnt[2], (unsigned long long)c2); atomicAdd(&s_cnt[3], (unsigned long long)c9);
+        if (c0) atomicAdd(gcnt + 0, (unsigned long long)c0);
+        if (c1) atomicAdd(gcnt + 1, (unsigned long long)c1);
+        if (c2) atomicAdd(gcnt + 2, (unsigned long long)c2);
+        if (c9) atomicAdd(gcnt + 9, (unsigned long long)c9);
         if (c3) atomicAdd(gcnt + 3, (unsigned long long)c3);
         if (c5) atomicAdd(gcnt + 5, (unsigned long long)c5);
         if (c8) atomicAdd(gcnt + 8, (unsigned long long)c8);
-        __threadfence_block();
-        const unsigned long long ticket = atomicAdd(&s_cnt[4], 1ull);
-        if (ticket == (unsigned long long)(blockDim.x >> 5) - 1ull) {
-            __threadfence_block();
-            const int slot[4] = {0, 1, 2, 9};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const unsigned long long val = *((volatile unsigned long long*)&s_cnt[j]);
-                if (val) atomicAdd(gcnt + slot[j], val);
-            }
-        }
     }
+    (void)s_cnt;
 }
 
 
