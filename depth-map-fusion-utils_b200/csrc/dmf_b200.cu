@@ -247,6 +247,7 @@ void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, dim3 grid, cudaStr
         dim3 g((a.Wc + SKIP_TILE_W - 1) / SKIP_TILE_W, (a.Hc + SKIP_TILE_H - 1) / SKIP_TILE_H, grid.z);
         const bool exact = a.vol.err32[0] == 0.0f && a.vol.err32[1] == 0.0f && a.vol.err32[2] == 0.0f;
         if (fmt == DMF_GRID_BYTE) {
+            k_view_start<<<(grid.z + 127) / 128, 128, 0, st>>>(a, (int)grid.z, const_cast<int*>(a.kstart));
             if (exact) k_forward_dist<MODE, true><<<g, SKIP_THREADS, 0, st>>>(a);
             else k_forward_dist<MODE, false><<<g, SKIP_THREADS, 0, st>>>(a);
         } else k_forward_skip<MODE, 0><<<g, SKIP_THREADS, 0, st>>>(a);
@@ -303,6 +304,8 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     a.counters = c->d_counters.as<u64>();
     a.dcx = c->d_dcx.as<float>(); a.dcy = c->d_dcy.as<float>(); a.clearance = c->d_clearance.as<float>();
     a.dcx_max = c->dcx_max; a.dcy_max = c->dcy_max;
+    DMF_TRY(c->d_kstart.reserve((size_t)n_views * 4));
+    a.kstart = c->d_kstart.as<int>();
     const bool skip = !(p->flags & DMF_FWD_NO_SKIP);
     dim3 grid((c->Wc + FWD_TILE_W - 1) / FWD_TILE_W, (c->Hc + FWD_TILE_H - 1) / FWD_TILE_H, n_views);
     DMF_CUDA(cudaEventRecord(c->ev_h0, st));
@@ -315,7 +318,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     }
     DMF_CUDA(cudaEventRecord(c->ev_h1, st));
     c->hot_timed = true;
-    c->launches++;
+    c->launches += (skip && p->grid_format == DMF_GRID_BYTE) ? 2 : 1;      // k_view_start + the march
     DMF_CUDA(cudaGetLastError());
     if (p->mode == DMF_MODE_CLASSIFY && c->n_occ) {
         k_apply_first_view<<<blocks_for(c->n_occ, 256, 1u << 30), 256, 0, st>>>(c->d_view_mark.as<int>(), c->d_first_view.as<int>(), (int)c->n_occ, view_id0);
@@ -392,7 +395,7 @@ void dmf_destroy(dmf_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->d_bricks, &c->d_macro, &c->d_clearance, &c->d_dcx, &c->d_dcy, &c->d_prefix, &c->d_rank2occ, &c->d_bytes, &c->d_noff, &c->d_normals, &c->d_occ_ids, &c->d_centroid_hash,
-                      &c->d_view_mark, &c->d_good_bits, &c->d_first_view, &c->d_axis[0], &c->d_axis[1], &c->d_axis[2], &c->d_xtab, &c->d_ytab, &c->d_ztab,
+                      &c->d_view_mark, &c->d_good_bits, &c->d_first_view, &c->d_axis[0], &c->d_axis[1], &c->d_axis[2], &c->d_xtab, &c->d_ytab, &c->d_ztab, &c->d_kstart,
                       &c->d_poses[0], &c->d_poses[1], &c->d_inv_poses, &c->d_first_key, &c->d_ray_key, &c->d_ray_occ, &c->d_tmp_a, &c->d_tmp_b,
                       &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters};
     for (auto* b : bufs) b->release();

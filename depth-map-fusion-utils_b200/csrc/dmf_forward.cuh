@@ -24,6 +24,7 @@ struct FwdArgs {
     const float* __restrict__ clearance; // [mdim_x][mdim_y][mdim_z] voxels that can be crossed (L-inf) from anywhere in the cell
                                        //  while provably staying in empty, in-bounds macro cells (0 = evaluate exactly)
     float dcx_max, dcy_max;            // max |dcx|, |dcy| (for the per-view error bound)
+    const int* __restrict__ kstart;    // [n_views] probes 0..kstart-1 of EVERY ray of the view are provably in-bounds misses (k_view_start)
     // outputs (may be null)
     int* depth;                        // [n_views][H][W]
     unsigned short* depth16;           // [n_views][H][W]  same, 0xFFFF = none
@@ -423,6 +424,40 @@ __global__ void __launch_bounds__(SKIP_THREADS, 8) k_forward_skip(const FwdArgs 
     forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23, n_samples, n_inb, n_exact, n_f64, n_skip);
 }
 
+// Per view: how many leading probes every ray may skip.  All rays leave from the camera centre t; probe k of any ray is
+// within z_k * G voxels (L-inf) of it, G = max_i (|m_i0|*max|dcx| + |m_i1|*max|dcy| + |m_i2|) / delta_i.  If the camera
+// sits in a voxel with distance byte d, everything within d-1 voxels of that voxel is empty and interior, so the probes
+// with z_k * G <= d - 1.25 are in-bounds misses for every ray (0.25 = 2 * eps_q + slack, as in k_forward_dist).
+__global__ void k_view_start(const FwdArgs a, int n_views, int* __restrict__ kstart) {
+    const int view = blockIdx.x * blockDim.x + threadIdx.x;
+    if (view >= n_views) return;
+    const VolDev& v = a.vol;
+    const float* P = a.poses + 12 * (size_t)view;
+    const float m[3][4] = {{P[0], P[1], P[2], P[3]}, {P[4], P[5], P[6], P[7]}, {P[8], P[9], P[10], P[11]}};
+    int k0 = 0;
+    const float tx = m[0][3], ty = m[1][3], tz = m[2][3];
+    const float kEps = 9.5367431640625e-07f;   // 16 * 2^-24
+    float emax = 0.f, G = 0.f;
+    for (int i = 0; i < 3; i++) {
+        const float reach = fabsf(m[i][0]) * a.dcx_max + fabsf(m[i][1]) * a.dcy_max + fabsf(m[i][2]);
+        emax = fmaxf(emax, kEps * (reach + fabsf(m[i][3]) + fabsf((float)v.vmin[i])) * fabsf(v.inv32[i]));
+        G = fmaxf(G, reach * fabsf(v.inv32[i]) * 1.00001f);
+    }
+    if (emax <= 0.1f && in_bounds(v, tx, ty, tz) && v.bytes != nullptr) {       // NaN poses fail the comparisons
+        unsigned ne = 0;
+        const int ix = voxel_index(tx, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], ne);
+        const int iy = voxel_index(ty, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], ne);
+        const int iz = voxel_index(tz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], ne);
+        if (coords_valid(v, ix, iy, iz)) {
+            const float d = (float)v.bytes[linear_index(v, ix, iy, iz)];
+            // z_k = (z0 + k*zdelta) mm;  need z_k * 0.001 * G <= d - 1.25  for all k < k0
+            const float zmax_mm = (d - 1.25f) / fmaxf(G, 1e-6f) * 1000.0f * 0.9999f;
+            if (zmax_mm >= (float)a.z0) k0 = min(a.S, (int)floorf((zmax_mm - (float)a.z0) / (float)a.zdelta) + 1);
+        }
+    }
+    kstart[view] = max(k0, 0);
+}
+
 // ---- K1 on distance bytes: k_forward_dist ---------------------------------------------------------------------
 // DMF_GRID_BYTE march.  Every exactly evaluated probe reads its voxel's distance byte d (dmf_distance.cuh): 0 = hit;
 // d >= 2 proves the next floor((d - 1.25) / max|QB|) probes are in-bounds misses (same error budget as k_forward_skip:
@@ -494,8 +529,9 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
     int hit_k = -1, hx = 0, hy = 0, hz = 0;
     float hpx = 0.f, hpy = 0.f, hpz = 0.f;
     unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
-    int k = 0;
     const int S = a.S;
+    int k = active ? min(__ldg(a.kstart + view), S) : 0;      // leading probes that no ray of this view can hit (k_view_start)
+    n_inb = (unsigned)k; n_skip = (unsigned)k;
     const float* xt = a.xtab + cic;
     const float* yt = a.ytab + ric;
     const float* __restrict__ zt = a.ztab;

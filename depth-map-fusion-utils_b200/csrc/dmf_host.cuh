@@ -141,7 +141,7 @@ struct dmf_ctx {
     dmf::DevBuf d_axis[3]; int n_axis[3] = {0, 0, 0};
     // projectPoint tables
     bool tables_valid = false; dmf::TableKey tkey{};
-    dmf::DevBuf d_xtab, d_ytab, d_ztab, d_dcx, d_dcy, d_clearance; int S = 0, Wc = 0, Hc = 0; float dcx_max = 0, dcy_max = 0;
+    dmf::DevBuf d_xtab, d_ytab, d_ztab, d_kstart, d_dcx, d_dcy, d_clearance; int S = 0, Wc = 0, Hc = 0; float dcx_max = 0, dcy_max = 0;
     // scratch
     dmf::DevBuf d_poses[2], d_inv_poses, d_out[2][8], d_first_key, d_ray_key, d_ray_occ, d_tmp_a, d_tmp_b, d_out_occ, d_n_ids, d_offsets, d_ids;
     dmf::DevBuf d_misc[4];
