@@ -400,8 +400,8 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if not traffic else traffic.get("dram_bytes_per_view", 0) * V,
                          "traffic_source": None if not traffic else traffic.get("source"),
-                         "peak_source": peak_src, "kernel": "k_forward" if args.no_skip else "k_forward_skip", "kernel_ms": hot, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "algorithmic bytes are the reference-equivalent ones (every in-bounds probe reads the grid once); the skipping kernel proves most of them empty without touching memory, so measured DRAM traffic is far lower; instruction-issue bound, see DESIGN.md"},
+                         "peak_source": peak_src, "kernel": "k_forward" if args.no_skip else ("k_forward_dist" if fmt == D.GRID_BYTE else "k_forward_skip"), "kernel_ms": hot, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "algorithmic bytes are the reference-equivalent ones (every in-bounds probe reads the grid once); the skipping kernel proves most of them empty without touching memory, so measured DRAM traffic is far lower; bound by dependent memory waits, see DESIGN.md section 5"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_run": same, "result": "depth_mm + visibility + found_any per view",
                     "with_points": {"value": e2e_pts_value, "d2h_bytes_per_step": d2h + V * H * W * 12, "ms_per_step": 1e3 * e2e_pts_s / e2e_pts_steps},
