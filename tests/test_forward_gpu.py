@@ -274,3 +274,33 @@ def test_full_size_properties_1024_1080p(dmf, ctx):
         assert hit.sum() > 100000
         assert len(uniq) == len(a["ids"][i]) == int(np.unpackbits(a["visibility"][i].view(np.uint8)).sum())
         assert np.array_equal(np.sort(a["ids"][i]), uniq)
+
+
+def _aniso_scene(dmf, seed=3):
+    """anisotropic, off-origin, non-dyadic volume (negative vmin, different voxel size per axis) with random blobs"""
+    from dmf_b200.scenes import Scene
+    rng = np.random.default_rng(seed)
+    bounds = np.array([-0.31, 0.47, -0.22, 0.63, 0.11, 0.93], np.float64)
+    dims = np.array([100, 120, 90], np.int32)
+    cen = rng.uniform([-0.2, -0.1, 0.25], [0.35, 0.5, 0.8], size=(40, 3))
+    pts, nrm = [], []
+    for c in cen:
+        r = rng.uniform(0.01, 0.05)
+        d = rng.normal(size=(400, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        pts.append(c + r * d); nrm.append(d)
+    pts = np.concatenate(pts).astype(np.float32); nrm = np.concatenate(nrm).astype(np.float32)
+    return Scene("aniso", bounds, dims, pts, nrm)
+
+
+def test_anisotropic_offset_volume(dmf, oracle, ctx):
+    sc = _aniso_scene(dmf)
+    ov = oracle.volume_from_scene(sc, flat=True)
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+    centre = np.array([0.08, 0.2, 0.52])
+    poses = np.stack([dmf.scenes.look_at(centre + 0.45 * v, centre) for v in dmf.scenes.sphere_directions(6.0)[3::9][:5]]
+                     + [dmf.scenes.look_at([0.9, 0.9, 1.4], centre), dmf.scenes.look_at([-0.30, -0.21, 0.12], centre)])
+    for fmt in (1, 0):
+        for mode, zd, sparse in ((0, 5, False), (1, 3, True)):
+            cnt = _check_forward(dmf, oracle, ctx, sc, ov, gv, poses, mode, zd, sparse, grid_format=fmt)
+    assert cnt["hits"] > 1000

@@ -198,3 +198,32 @@ def test_optimize_standoff_batch(dmf, oracle, ctx):
         assert int(mid[i]) == m, (i, int(mid[i]), m)
         assert np.array_equal(poses[i], p)
     assert len(set(mids)) > 1     # the search actually depends on the camera
+
+
+def test_reverse_anisotropic_offset_volume(dmf, oracle, ctx):
+    from tests.test_forward_gpu import _aniso_scene
+    sc = _aniso_scene(dmf)
+    ov = oracle.volume_from_scene(sc, flat=True)
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+    K = dmf.scenes.REFERENCE_K
+    eng = dmf.RayTracingEngine(dmf.Camera(K), ctx)
+    centre = np.array([0.08, 0.2, 0.52])
+    poses = np.stack([dmf.scenes.look_at(centre + 0.45 * v, centre) for v in dmf.scenes.sphere_directions(6.0)[3::9][:5]])
+    for fmt in (1, 0):
+        ctx.set_reverse_format(fmt)
+        ctx.reset_counters()
+        g = eng.reverse_views(gv, poses, fast=True)
+        cnt = ctx.counters()
+        tot = dict(samples=0, inbounds=0, hits=0)
+        for i, p in enumerate(poses):
+            o = oracle.reverse(ov, K, H, W, p, fast=True)
+            assert np.array_equal(g["ids"][i], o["ids"])
+            for k in tot:
+                tot[k] += o["counters"][k]
+            assert np.array_equal(eng.reverseRayTrace(gv, p, False)[1], oracle.reverse(ov, K, H, W, p, fast=False)["ids"])
+        assert (cnt["samples"], cnt["inbounds"], cnt["hits"]) == (tot["samples"], tot["inbounds"], tot["hits"])
+    a = np.random.default_rng(2).uniform(-0.4, 1.0, size=(64, 3)).astype(np.float32)
+    b = np.random.default_rng(3).uniform(-0.4, 1.0, size=(64, 3)).astype(np.float32)
+    got = dmf.willCollide(ctx, gv, a, b, True)
+    assert np.array_equal(got, np.array([oracle.will_collide(ov, a[i], b[i], True)[0] for i in range(64)]))
