@@ -1,6 +1,7 @@
 // dmf_oracle_capi.cpp -- C entry points over dmf_oracle.hpp so that tests/, smoke() and bench.py's
 // cpu_baseline / --impl reference legs can drive the CPU oracle through ctypes.
-// TEST INFRASTRUCTURE, NOT PRODUCT CODE (see dmf_oracle.hpp header).  PARITY UNPINNED.
+// TEST INFRASTRUCTURE, NOT PRODUCT CODE (see dmf_oracle.hpp header: pinned against
+// oracle/_ref, the reference's own headers compiled here; PARITY UNPINNED only for Eigen's internal op order).
 #include "dmf_oracle.hpp"
 #include <chrono>
 #include <cstdio>

@@ -1,7 +1,8 @@
 """ctypes binding of the CPU oracle (oracle/liboracle_dmf.so).
 
 TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Importable only from tests/, __graft_entry__.smoke() and
-bench.py's cpu_baseline / --impl reference legs.  PARITY UNPINNED (see dmf_oracle.hpp).
+bench.py's cpu_baseline / --impl reference legs.  Pinned against the reference's own headers compiled here (oracle/_ref,
+tests/test_reference_build_cpu.py); PARITY UNPINNED only for Eigen's internal op order (see dmf_oracle.hpp).
 """
 from __future__ import annotations
 
