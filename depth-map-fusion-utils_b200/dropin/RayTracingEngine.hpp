@@ -55,12 +55,11 @@ inline void pose12(const Eigen::Affine3f& T, float out[12])
     for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) out[4 * r + c] = T(r, c);
 }
 
-// make the device mirror current: camera intrinsics every call (cheap), volume only when it changed
+// make the device mirror of the volume current (re-upload only when (&volume, revision) changed)
 template <class Volume>
-inline dmf_ctx* sync(Camera& cam, Volume& volume)
+inline dmf_ctx* sync_volume(Volume& volume)
 {
     Global& g = global();
-    must(dmf_set_camera(g.ctx, cam.intrinsics().data(), cam.getHeight(), cam.getWidth()), "dmf_set_camera");
     if (g.volume != (const void*)&volume || g.revision != volume.revision()) {
         const double bounds[6] = {volume.xmin_, volume.xmax_, volume.ymin_, volume.ymax_, volume.zmin_, volume.zmax_};
         const double delta[3] = {volume.xdelta_, volume.ydelta_, volume.zdelta_};
@@ -72,6 +71,14 @@ inline dmf_ctx* sync(Camera& cam, Volume& volume)
         g.volume = &volume; g.revision = volume.revision();
     }
     return g.ctx;
+}
+
+// volume as above + camera intrinsics every call (cheap)
+template <class Volume>
+inline dmf_ctx* sync(Camera& cam, Volume& volume)
+{
+    must(dmf_set_camera(global().ctx, cam.intrinsics().data(), cam.getHeight(), cam.getWidth()), "dmf_set_camera");
+    return sync_volume(volume);
 }
 
 // Voxel::view / Voxel::good live on the host objects in the reference; push them before and pull them after a call

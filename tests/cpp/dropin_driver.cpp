@@ -13,6 +13,7 @@
 
 #include <Volume.hpp>
 #include <RayTracingEngine.hpp>
+#include <DmfAlgorithms.hpp>
 
 template <class T> static void rd(FILE* f, T* p, size_t n) { if (fread(p, sizeof(T), n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
 template <class T> static void wr(FILE* f, const T* p, size_t n) { if (fwrite(p, sizeof(T), n, f) != n) { fprintf(stderr, "short write\n"); exit(2); } }
@@ -113,6 +114,27 @@ int main(int argc, char** argv)
     // engine passed by value, as the reference's setCover() does
     auto regions = regionsCovered(engine, volume, camera_locations);
     for (auto& r : regions) wr_ids(out, !r.empty(), r);
+    // helpers outside RayTracingEngine (DmfAlgorithms.hpp): willCollide for every ordered pair of camera centres the way
+    // CameraPathGen.cpp:318-330 loops, singly and as one batched matrix; optimizeCameraPosition; setCover
+    {
+        auto matrix = dmf_dropin::collisionMatrix(volume, camera_locations);
+        for (size_t x = 0; x < camera_locations.size(); x++) for (size_t y = 0; y < camera_locations.size(); y++) {
+            if (x == y) continue;
+            Vector3f a, b;
+            for (int k = 0; k < 3; k++) { a(k) = camera_locations[x](k, 3); b(k) = camera_locations[y](k, 3); }
+            uint8_t single = dmf_dropin::willCollide(volume, a, b) == true ? 1 : 0;
+            if (single != matrix[x * camera_locations.size() + y]) { fprintf(stderr, "collisionMatrix != willCollide at %zu,%zu\n", x, y); return 3; }
+        }
+        wr(out, matrix.data(), matrix.size());
+        std::vector<uint32_t> mids;
+        auto moved = dmf_dropin::optimizeCameraPositions(volume, engine, camera_locations, 300, 600, &mids);
+        Affine3f one = dmf_dropin::optimizeCameraPosition(volume, engine, 1, camera_locations[0]);
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) if (one(r, c) != moved[0](r, c)) { fprintf(stderr, "optimizeCameraPosition: single != batched\n"); return 3; }
+        wr(out, mids.data(), mids.size());
+        for (auto& T : moved) { float p[12]; dmf_dropin::pose12(T, p); wr(out, p, 12); }
+        auto cover = dmf_dropin::setCover(engine, volume, camera_locations, 1, false);
+        wr_ids(out, !cover.empty(), cover);
+    }
     fclose(out);
     std::cout << "dropin_driver: " << n_occ << " occupied voxels, " << n_poses << " poses" << std::endl;
     return 0;

@@ -105,4 +105,18 @@ def test_dropin_matches_oracle(driver, dmf, oracle, tmp_path):
     for p in poses:
         f, ids = rd.ids()
         assert np.array_equal(ids, np.sort(oracle.reverse(ov, K, H, W, p, fast=True)["ids"]))
+    # DmfAlgorithms.hpp: willCollide matrix, optimizeCameraPosition, setCover
+    n = len(poses)
+    mat = rd.take(np.uint8, n * n).reshape(n, n)
+    for x in range(n):
+        for y in range(n):
+            want = 0 if x == y else int(oracle.will_collide(ov, poses[x].reshape(3, 4)[:, 3], poses[y].reshape(3, 4)[:, 3], True)[0])
+            assert mat[x, y] == want, (x, y)
+    mids = rd.take(np.uint32, n); moved = rd.take(np.float32, 12 * n).reshape(n, 12)
+    for i, p in enumerate(poses):
+        m, q = oracle.optimize_standoff(ov, K, H, W, p)
+        assert m == mids[i] and np.array_equal(q, moved[i]), i
+    f, sel = rd.ids()
+    sets = [np.sort(oracle.reverse(ov, K, H, W, p, fast=True)["ids"]) for p in poses]
+    assert np.array_equal(sel.astype(np.int64), oracle.greedy_set_cover(sets))
     assert rd.o == len(rd.b)
