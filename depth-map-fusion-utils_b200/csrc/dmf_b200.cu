@@ -40,10 +40,12 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
     VolDev& v = c->vol;
     std::memcpy(c->bounds, bounds, sizeof c->bounds);
     c->voxel_size = delta[0] * delta[1] * delta[2];
-    if ((double)(dim[0] + 1) * (dim[1] + 1) * (dim[2] + 1) >= 4294967296.0) return fail("volume %dx%dx%d too large for the 32-bit linear voxel index", dim[0], dim[1], dim[2]);
+    int pad[3] = {0, 0, 0};
+    if (const char* e = std::getenv("DMF_PAD")) std::sscanf(e, "%d,%d", &pad[1], &pad[2]);      // experiment: extra row / plane padding
+    if ((double)(dim[0] + 1) * (dim[1] + 1 + pad[1]) * (dim[2] + 1 + pad[2]) >= 4294967296.0) return fail("volume %dx%dx%d too large for the 32-bit linear voxel index", dim[0], dim[1], dim[2]);
     for (int a = 0; a < 3; a++) {
         const double vmin = bounds[2 * a], vmax = bounds[2 * a + 1];
-        v.dim[a] = dim[a]; v.pdim[a] = dim[a] + 1; v.mdim[a] = (dim[a] + 1 + 7) / 8;
+        v.dim[a] = dim[a]; v.pdim[a] = dim[a] + 1 + pad[a]; v.mdim[a] = (dim[a] + 1 + 7) / 8;
         v.vmin[a] = vmin; v.delta[a] = delta[a];
         v.inv[a] = 1.0 / delta[a];
         v.c0[a] = -vmin * v.inv[a];
@@ -242,14 +244,19 @@ int ensure_tables(dmf_ctx* c, int z0, int zdelta, int cstride, int rstride, cuda
 }
 
 template <int MODE>
-void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, dim3 grid, cudaStream_t st) {
+void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, bool two_probe, dim3 grid, cudaStream_t st) {
     if (skip) {
         dim3 g((a.Wc + SKIP_TILE_W - 1) / SKIP_TILE_W, (a.Hc + SKIP_TILE_H - 1) / SKIP_TILE_H, grid.z);
         const bool exact = a.vol.err32[0] == 0.0f && a.vol.err32[1] == 0.0f && a.vol.err32[2] == 0.0f;
         if (fmt == DMF_GRID_BYTE) {
             k_view_start<<<(grid.z + 127) / 128, 128, 0, st>>>(a, (int)grid.z, const_cast<int*>(a.kstart));
-            if (exact) k_forward_dist<MODE, true><<<g, SKIP_THREADS, 0, st>>>(a);
-            else k_forward_dist<MODE, false><<<g, SKIP_THREADS, 0, st>>>(a);
+            if (two_probe) {
+                if (exact) k_forward_dist<MODE, true><<<g, SKIP_THREADS, 0, st>>>(a);
+                else k_forward_dist<MODE, false><<<g, SKIP_THREADS, 0, st>>>(a);
+            } else {
+                if (exact) k_forward_line<MODE, true><<<g, SKIP_THREADS, 0, st>>>(a);
+                else k_forward_line<MODE, false><<<g, SKIP_THREADS, 0, st>>>(a);
+            }
         } else k_forward_skip<MODE, 0><<<g, SKIP_THREADS, 0, st>>>(a);
     } else {
         if (fmt == DMF_GRID_BYTE) k_forward<MODE, 1><<<grid, FWD_THREADS, 0, st>>>(a);
@@ -310,11 +317,11 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     dim3 grid((c->Wc + FWD_TILE_W - 1) / FWD_TILE_W, (c->Hc + FWD_TILE_H - 1) / FWD_TILE_H, n_views);
     DMF_CUDA(cudaEventRecord(c->ev_h0, st));
     switch (p->mode) {
-        case 0: launch_forward_fmt<0>(a, p->grid_format, skip, grid, st); break;
-        case 1: launch_forward_fmt<1>(a, p->grid_format, skip, grid, st); break;
-        case 2: launch_forward_fmt<2>(a, p->grid_format, skip, grid, st); break;
-        case 3: launch_forward_fmt<3>(a, p->grid_format, skip, grid, st); break;
-        default: launch_forward_fmt<4>(a, p->grid_format, skip, grid, st); break;
+        case 0: launch_forward_fmt<0>(a, p->grid_format, skip, (p->flags & DMF_FWD_TWO_PROBE) != 0, grid, st); break;
+        case 1: launch_forward_fmt<1>(a, p->grid_format, skip, (p->flags & DMF_FWD_TWO_PROBE) != 0, grid, st); break;
+        case 2: launch_forward_fmt<2>(a, p->grid_format, skip, (p->flags & DMF_FWD_TWO_PROBE) != 0, grid, st); break;
+        case 3: launch_forward_fmt<3>(a, p->grid_format, skip, (p->flags & DMF_FWD_TWO_PROBE) != 0, grid, st); break;
+        default: launch_forward_fmt<4>(a, p->grid_format, skip, (p->flags & DMF_FWD_TWO_PROBE) != 0, grid, st); break;
     }
     DMF_CUDA(cudaEventRecord(c->ev_h1, st));
     c->hot_timed = true;
@@ -610,6 +617,13 @@ int dmf_counters(dmf_ctx* c, uint64_t out[DMF_CNT_COUNT]) {
     DMF_CUDA(cudaMemcpy(all.data(), c->d_counters.p, all.size() * 8, cudaMemcpyDeviceToHost));
     for (int j = 0; j < DMF_CNT_COUNT; j++) { out[j] = 0; for (int s = 0; s < DMF_COUNTER_SLOTS; s++) out[j] += all[(size_t)s * DMF_COUNTER_STRIDE + j]; }
     out[DMF_CNT_LAUNCHES] = c->launches;
+#ifdef DMF_LINE_STATS
+    // diagnostic build: k_forward_line logs blocks / block-cycles / warp-cycles per SM into the unused tail of each slot
+    for (int s = 0; s < 160; s++) {
+        const uint64_t* q = &all[(size_t)s * DMF_COUNTER_STRIDE];
+        if (q[12]) std::fprintf(stderr, "sm %3d blocks %7llu  warp-cycles/warp %8.0f  line %8.0f  exact %8.0f\n", s, (unsigned long long)q[12], q[13] / (4.0 * q[12]), q[14] / (4.0 * q[12]), q[15] / (4.0 * q[12]));
+    }
+#endif
     return 0;
 }
 int dmf_reset_counters(dmf_ctx* c) {

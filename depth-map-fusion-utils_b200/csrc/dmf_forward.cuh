@@ -89,14 +89,16 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
     }
     unsigned ties = 0;
     if (MODE == 4) {
-        if (hit) atomicMin(a.min_depth + view, z_depth);
+        // one atomic per warp at most, and none once the view's minimum is already lower (same-address atomics serialise in L2)
+        const int zw = __reduce_min_sync(0xffffffffu, hit ? z_depth : 0x7fffffff);
+        if (lane == 0 && zw != 0x7fffffff && zw < *((volatile int*)(a.min_depth + view))) atomicMin(a.min_depth + view, zw);
     } else {
         const size_t li = (size_t)view * a.Wc * a.Hc + (size_t)ri * a.Wc + ci;
         bool emit = false;
         int occ = -1;
         if (hit) {
             occ = occupied_ordinal(v, hx, hy, hz);
-            if (a.found_any) a.found_any[view] = 1;
+            if (a.found_any) raise_flag(a.found_any + view);
             bool good = false;
             if (MODE == 1 || MODE == 2) {
                 bool need = (z_depth >= 250 && z_depth <= 600);                       // :363, :429
@@ -140,6 +142,7 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
     const unsigned c358 = __reduce_add_sync(0xffffffffu, n_exact | ties | n_f64);      // almost always 0: reduce individually only then
     unsigned c3 = 0, c5 = 0, c8 = 0;
     if (c358) { c3 = __reduce_add_sync(0xffffffffu, n_exact); c5 = __reduce_add_sync(0xffffffffu, ties); c8 = __reduce_add_sync(0xffffffffu, n_f64); }
+#ifndef DMF_NO_COUNTERS
     if (lane == 0) {
         // one warp, a handful of result-less atomics (RED) into one of the 256 counter replicas: nothing to wait for
         u64* const gcnt = counter_slot(a.counters);
@@ -151,6 +154,7 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
         if (c5) atomicAdd(gcnt + 5, (unsigned long long)c5);
         if (c8) atomicAdd(gcnt + 8, (unsigned long long)c8);
     }
+#endif
     (void)s_cnt;
 }
 
@@ -610,6 +614,180 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
     }
     const unsigned n_samples = active ? (unsigned)min(k, S) : 0u;
     forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23, n_samples, n_inb, n_exact, n_f64, n_skip);
+}
+
+// ---- K1 on distance bytes, line-first: k_forward_line ------------------------------------------------------------
+// Same results as k_forward / k_forward_dist, probe for probe.  The ray is FIRST followed as the straight line
+// Q(k) = QA + k*QB in voxel units (3 FMAs, no table loads): the distance byte d of the line point's voxel decides.
+//   d >= 2: every voxel within d-1 (L-inf) of that voxel is empty and interior.  The reference's sample k lies within
+//           eps_q <= 0.1 voxel of Q(k) (error budget above k_forward_skip), i.e. in that voxel or one next to it: an
+//           in-bounds miss WITHOUT being evaluated; so are the next floor((d - 1.25) / max|QB|) samples.
+//   d <= 1: next to an occupied voxel or to the volume boundary: the sample is evaluated exactly (tables, the
+//           reference's float expression, the exact voxel index), as k_forward does.
+// The line is only consulted for k in [kin, kout], where it is >= 0.25 voxel inside the volume on every axis (slab test,
+// once per ray) so its voxel is addressable; samples that are provably outside (line > 0.25 voxel beyond a face) are
+// dropped without evaluation, and the thin bands in between are evaluated exactly.  Views whose eps_q exceeds 0.1 voxel
+// (or NaN/inf poses) evaluate every sample exactly.  The pose lives in shared memory: the exact path is the rare one, so
+// it re-reads the 12 floats instead of pinning 12 registers through the line loop (12 blocks of 128 threads per SM).
+constexpr int LINE_MIN_BLOCKS = 12;
+
+template <int MODE, bool EXACT>
+__global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(const FwdArgs a) {
+    __shared__ unsigned long long s_cnt[5];
+    __shared__ float s_pose[12];
+    const int view = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
+    const int ri = blockIdx.y * SKIP_TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    const bool active = ci < a.Wc && ri < a.Hc;
+    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldg(a.poses + 12 * (size_t)view + threadIdx.x);
+#ifdef DMF_LINE_STATS
+    const long long t_begin = clock64();
+    long long t_line = 0, t_exact = 0;
+#endif
+    __syncthreads();
+    const volatile float* const sp = s_pose;      // volatile: re-read where used, never hoisted into registers
+    const VolDev& v = a.vol;
+    const float kM = 12582912.0f;
+    const int S = a.S;
+
+    // ---- per ray: the line, the skip rate, and the sample intervals ----
+    float qa0, qa1, qa2, qb0, qb1, qb2, rq, c1;
+    int k = 0, kin = 1, kout = 0, s_end = S;
+    unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
+    {
+        const float m00 = sp[0], m01 = sp[1], m02 = sp[2], m03 = sp[3], m10 = sp[4], m11 = sp[5], m12 = sp[6], m13 = sp[7];
+        const float m20 = sp[8], m21 = sp[9], m22 = sp[10], m23 = sp[11];
+        const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2];
+        const int cic = active ? ci : 0, ric = active ? ri : 0;
+        const float dcx = __ldg(a.dcx + cic), dcy = __ldg(a.dcy + ric);
+        const float g0 = fmaf(m00, dcx, fmaf(m01, dcy, m02)), g1 = fmaf(m10, dcx, fmaf(m11, dcy, m12)), g2 = fmaf(m20, dcx, fmaf(m21, dcy, m22));
+        const float z0m = (float)a.z0 * 0.001f, zdm = (float)a.zdelta * 0.001f;
+        qa0 = fmaf(fmaf(z0m, g0, m03), in0, v.c32[0]); qa1 = fmaf(fmaf(z0m, g1, m13), in1, v.c32[1]); qa2 = fmaf(fmaf(z0m, g2, m23), in2, v.c32[2]);
+        qb0 = zdm * g0 * in0; qb1 = zdm * g1 * in1; qb2 = zdm * g2 * in2;
+        const float qbmax = fmaxf(fabsf(qb0), fmaxf(fabsf(qb1), fabsf(qb2)));
+        rq = 1.0f / fmaxf(qbmax, 1e-3f);          // <= 1000: (d - 1.25) * rq + 1 stays far inside the shifter's range
+        c1 = fmaf(-1.25f, rq, 1.0f);              // floor(d * rq + c1) = 1 + number of samples skipped after a probe with byte d
+        const float kEps = 9.5367431640625e-07f;  // 16 * 2^-24
+        const float e0 = kEps * (fabsf(m00) * a.dcx_max + fabsf(m01) * a.dcy_max + fabsf(m02) + fabsf(m03) + fabsf((float)v.vmin[0])) * fabsf(in0);
+        const float e1 = kEps * (fabsf(m10) * a.dcx_max + fabsf(m11) * a.dcy_max + fabsf(m12) + fabsf(m13) + fabsf((float)v.vmin[1])) * fabsf(in1);
+        const float e2 = kEps * (fabsf(m20) * a.dcx_max + fabsf(m21) * a.dcy_max + fabsf(m22) + fabsf(m23) + fabsf((float)v.vmin[2])) * fabsf(in2);
+        const bool skip_ok = v.bytes != nullptr && fmaxf(e0, fmaxf(e1, e2)) <= 0.1f;   // NaN poses compare false
+        if (skip_ok) {
+            // real-valued k intervals: [ti0, ti1] line >= 0.25 voxel inside on every axis; [to0, to1] line < 0.25 voxel outside
+            float ti0 = -1e30f, ti1 = 1e30f, to0 = -1e30f, to1 = 1e30f;
+            const float qa[3] = {qa0, qa1, qa2}, qb[3] = {qb0, qb1, qb2};
+#pragma unroll
+            for (int ax = 0; ax < 3; ax++) {
+                const float hi_in = v.ext[ax] - 0.25f, hi_out = v.ext[ax] + 0.25f;
+                if (fabsf(qb[ax]) > 1e-12f) {
+                    const float r = 1.0f / qb[ax];
+                    const float ia = (0.25f - qa[ax]) * r, ib = (hi_in - qa[ax]) * r;
+                    const float oa = (-0.25f - qa[ax]) * r, ob = (hi_out - qa[ax]) * r;
+                    ti0 = fmaxf(ti0, fminf(ia, ib)); ti1 = fminf(ti1, fmaxf(ia, ib));
+                    to0 = fmaxf(to0, fminf(oa, ob)); to1 = fminf(to1, fmaxf(oa, ob));
+                } else {
+                    if (!(qa[ax] >= 0.25f && qa[ax] <= hi_in)) ti0 = 1e30f;
+                    if (!(qa[ax] >= -0.25f && qa[ax] <= hi_out)) to0 = 1e30f;
+                }
+            }
+            // the t's carry a few ulps of relative error: one sample of guard on each end (|t| that matter are < 2^20)
+            const float Sf = (float)S;
+            if (!(to0 <= to1)) { k = S; }                                         // never inside: every sample fails validPoints
+            else {
+                k = (int)fminf(fmaxf(floorf(to0) - 1.0f, 0.0f), Sf);
+                s_end = (int)fminf(fmaxf(ceilf(to1) + 2.0f, 0.0f), Sf);
+                if (ti0 <= ti1) {
+                    kin = (int)fminf(fmaxf(ceilf(ti0) + 1.0f, 0.0f), Sf);
+                    kout = (int)fminf(fmaxf(floorf(ti1) - 1.0f, -1.0f), Sf - 1.0f);
+                }
+            }
+            const int ks = min(__ldg(a.kstart + view), S);                        // leading probes no ray of this view can hit (k_view_start)
+            if (ks > k) { k = ks; }
+            n_inb = n_skip = (unsigned)ks;                                        // ks > 0 only when the camera sits inside the volume: to0 < 0
+        }
+    }
+    if (!active) k = s_end = S;
+
+    int hit_k = -1, hx = 0, hy = 0, hz = 0;
+    float hpx = 0.f, hpy = 0.f, hpz = 0.f;
+    const unsigned char* __restrict__ gbytes = v.bytes;
+    const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
+    const unsigned pnyz = pny * pnz;
+    const unsigned bias = 0x4B400000u * (pnyz + pnz + 1u);                          // folds the three "- 0x4B400000" of the shifter into one
+    unsigned iter = 0;
+    bool stop = false;
+    while (k < s_end && !stop) {
+        if (k >= kin && k <= kout) {
+            // ---- follow the line ----
+#ifdef DMF_LINE_STATS
+            const long long tl0 = clock64();
+#endif
+            float kf = (float)k;
+            const float koutf = (float)kout;
+            unsigned d;
+            for (;;) {
+                if (MODE == 4 && (iter++ & 7u) == 0u) {   // rayTraceAndGetMinimum: planes behind the current minimum cannot matter
+                    const int cur = *((volatile int*)(a.min_depth + view));
+                    if (a.z0 + (int)kf * a.zdelta > cur) { stop = true; d = 2u; break; }
+                }
+                const unsigned bx = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb0, qa0), kM));
+                const unsigned by = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb1, qa1), kM));
+                const unsigned bz = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb2, qa2), kM));
+                d = __ldg(gbytes + (bx * pnyz + by * pnz + bz - bias));
+#ifdef DMF_LINE_STATS
+                n_f64++;                                   // diagnostic build: F64_PATH counts line probes, EXACT_DIV exact ones
+#endif
+                if (d < 2u) break;
+                const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;           // (float)d without I2F
+                kf += __fadd_rd(fmaf(df, rq, c1), kM) - kM;                                   // this probe + the skipped ones
+                if (!(kf <= koutf)) break;
+            }
+#ifdef DMF_LINE_STATS
+            t_line += clock64() - tl0;
+#endif
+            const int k2 = min((int)kf, s_end);
+            n_inb += (unsigned)(k2 - k); n_skip += (unsigned)(k2 - k);
+            k = k2;
+            if (d >= 2u) continue;
+        }
+        // ---- exact evaluation of sample k (identical to k_forward) ----
+        if (MODE == 4 && (iter++ & 7u) == 0u) {
+            const int cur = *((volatile int*)(a.min_depth + view));
+            if (a.z0 + k * a.zdelta > cur) break;
+        }
+#ifdef DMF_LINE_STATS
+        n_exact++;
+        const long long te0 = clock64();
+#endif
+        const float xf = __ldg(a.xtab + (size_t)k * a.Wc + ci), yf = __ldg(a.ytab + (size_t)k * a.Hc + ri), zf = __ldg(a.ztab + k);
+        const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp[0], xf), __fmul_rn(sp[1], yf)), __fmul_rn(sp[2], zf)), sp[3]);
+        const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp[4], xf), __fmul_rn(sp[5], yf)), __fmul_rn(sp[6], zf)), sp[7]);
+        const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp[8], xf), __fmul_rn(sp[9], yf)), __fmul_rn(sp[10], zf)), sp[11]);
+        if (!(px > v.lo[0] && px < v.hi[0] && py > v.lo[1] && py < v.hi[1] && pz > v.lo[2] && pz < v.hi[2])) { k++; continue; }   // validPoints failed
+        n_inb++;
+        int ix, iy, iz;
+        const unsigned idx = probe_index<EXACT>(v, px, py, pz, v.inv32[0], v.inv32[1], v.inv32[2], v.c32[0], v.c32[1], v.c32[2],
+                                                v.err32[0], v.err32[1], v.err32[2], pny, pnz, ix, iy, iz, n_f64, n_exact);
+        const unsigned de = __ldg(gbytes + idx);
+#ifdef DMF_LINE_STATS
+        if (de != 77u) t_exact += clock64() - te0;        // (depends on the load: the wait is inside the bracket)
+#endif
+        if (de == 0u) { hit_k = k; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz; k++; break; }
+        k++;
+    }
+    const unsigned n_samples = active ? (unsigned)((hit_k >= 0 || stop || (MODE == 4 && k < s_end)) ? min(k, S) : S) : 0u;
+    forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, sp[3], sp[7], sp[11], n_samples, n_inb, n_exact, n_f64, n_skip);
+#ifdef DMF_LINE_STATS
+    if (lane == 0) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        u64* slot = a.counters + (size_t)smid * DMF_COUNTER_STRIDE;
+        const unsigned long long dt = (unsigned long long)(clock64() - t_begin);
+        atomicAdd(slot + 13, dt); atomicAdd(slot + 14, (unsigned long long)t_line); atomicAdd(slot + 15, (unsigned long long)t_exact);
+        if (warp == 0) atomicAdd(slot + 12, 1ull);
+    }
+#endif
 }
 
 // CLASSIFY: `if(voxel->view==0) voxel->view=view` over a batch of views in call order (:354-355)

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
             const bool collided = march_collides<FMT>(a, cx, cy, cz, vx, vy, vz, chash, FAST ? 50 : 1, n_samples, n_inb, n_exact, n_runaway, n_f64, n_skip);
             if (!collided) {
                 n_hits++;
-                if (a.found_any) a.found_any[view] = 1;
+                if (a.found_any) raise_flag(a.found_any + view);
                 if (a.unocc) atomicOr(a.unocc + (size_t)view * a.vis_words32 + (occ >> 5), 1u << (occ & 31));
                 if (a.viz) a.view_mark[occ] = 1;                                     // :108, :205
                 bool emit = false;

@@ -104,6 +104,9 @@ typedef struct {
  * lists and the samples/inbounds counters are identical either way; DMF_CNT_SKIPPED says how many were skipped).
  * DMF_FWD_NO_SKIP evaluates every probe (the brute-force kernel; used to validate the skipping one). */
 #define DMF_FWD_NO_SKIP 1
+/* DMF_GRID_BYTE only: use the previous generation of the skipping march (every probed sample evaluated exactly, two
+ * per iteration) instead of the line-first one.  Same results; kept as the A/B baseline for profiles/. */
+#define DMF_FWD_TWO_PROBE 2
 
 /* Per-view outputs; any pointer may be NULL.  For the *_dev entry point these are device pointers. */
 typedef struct {

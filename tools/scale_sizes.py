@@ -17,4 +17,4 @@ for name in ("S128d", "S256", "S512", "S1024"):
             ms.append(ctx.last_hot_kernel_ms())
         c = ctx.counters()
         ev = (c["inbounds"] - c["skipped"]) / (128 * 480 * 640)
-        print(f"{name} fmt={fmt} zdelta={sc.zdelta}: {min(ms)/16*1e3:.2f} us/view, exact in-bounds probes per ray {ev:.2f}, samples/ray {c['samples']/(128*480*640):.1f}")
+        print(f"{name} fmt={fmt} zdelta={sc.zdelta}: {min(ms)/128*1e3:.2f} us/view, exact in-bounds probes per ray {ev:.2f}, samples/ray {c['samples']/(128*480*640):.1f}")
