@@ -299,6 +299,9 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     }
     if (first_key) DMF_TRY(fill_u32(c, st, first_key, (size_t)n_views * c->n_occ, 0xFFFFFFFFu));
 
+    // the kernels index pixels, lattice rays and visibility words with 32 bits
+    if ((double)n_views * c->H * c->W >= 4294967296.0 || (double)n_views * (double)vis_words64 * 2.0 >= 4294967296.0)
+        return fail("%d views of %dx%d exceed the 32-bit pixel index of one launch: split the batch", n_views, c->W, c->H);
     FwdArgs a;
     a.vol = c->vol; a.angle = c->angle; a.poses = d_poses;
     a.xtab = c->d_xtab.as<float>(); a.ytab = c->d_ytab.as<float>(); a.ztab = c->d_ztab.as<float>();

@@ -15,8 +15,9 @@ typedef unsigned long long u64;
 #define DMF_COUNTER_SLOTS 256
 #define DMF_COUNTER_STRIDE 16
 __device__ __forceinline__ u64* counter_slot(u64* base) {
-    const unsigned b = (blockIdx.x + blockIdx.y * gridDim.x + blockIdx.z * gridDim.x * gridDim.y) * 32u + (threadIdx.x >> 5);
-    return base + (size_t)((b * 2654435761u) >> 24) * DMF_COUNTER_STRIDE;    // multiplicative hash -> 256 slots
+    // blocks that run at the same time have neighbouring indices: consecutive slots spread their atomics over 256 lines
+    const unsigned b = blockIdx.x * 8u + blockIdx.y * 67u + blockIdx.z * 131u + (threadIdx.x >> 5);
+    return base + (b & (DMF_COUNTER_SLOTS - 1u)) * DMF_COUNTER_STRIDE;
 }
 
 // Thousands of rays of a view raise the same per-view flag.  A plain store per ray funnels ~10^4 same-address writes per

@@ -79,12 +79,14 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
     const bool hit = hit_k >= 0;
     const int z_depth = a.z0 + hit_k * a.zdelta;
     if (active) {
-        const size_t pix = ((size_t)view * a.H + (size_t)ri * a.rstride) * a.W + (size_t)ci * a.cstride;
+        // 32-bit pixel index: the host entry points keep n_views * H * W below 2^32 per launch
+        const unsigned pix = ((unsigned)view * (unsigned)a.H + (unsigned)(ri * a.rstride)) * (unsigned)a.W + (unsigned)(ci * a.cstride);
         if (a.depth) a.depth[pix] = hit ? z_depth : -1;
         if (a.depth16) a.depth16[pix] = hit ? (unsigned short)z_depth : (unsigned short)0xFFFFu;
         if (a.hit_voxel) a.hit_voxel[pix] = hit ? voxel_id(hx, hy, hz) : ~0ull;
         if (a.points) {
-            a.points[3 * pix] = hit ? hpx : 0.f; a.points[3 * pix + 1] = hit ? hpy : 0.f; a.points[3 * pix + 2] = hit ? hpz : 0.f;
+            float* const pp = a.points + 3ull * pix;
+            pp[0] = hit ? hpx : 0.f; pp[1] = hit ? hpy : 0.f; pp[2] = hit ? hpz : 0.f;
         }
     }
     unsigned ties = 0;
@@ -93,7 +95,7 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
         const int zw = __reduce_min_sync(0xffffffffu, hit ? z_depth : 0x7fffffff);
         if (lane == 0 && zw != 0x7fffffff && zw < *((volatile int*)(a.min_depth + view))) atomicMin(a.min_depth + view, zw);
     } else {
-        const size_t li = (size_t)view * a.Wc * a.Hc + (size_t)ri * a.Wc + ci;
+        const unsigned li = ((unsigned)view * (unsigned)a.Hc + (unsigned)ri) * (unsigned)a.Wc + (unsigned)ci;
         bool emit = false;
         int occ = -1;
         if (hit) {
@@ -122,7 +124,7 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
             // (possibly stale, the bits only ever get set) cached read already shows the bit
             const unsigned peers = __match_any_sync(__activemask(), emit ? occ : -1);
             if (emit && (unsigned)(threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
-                unsigned* w = a.vis + (size_t)view * a.vis_words32 + (occ >> 5);
+                unsigned* w = a.vis + ((unsigned)view * (unsigned)a.vis_words32 + ((unsigned)occ >> 5));
                 const unsigned m = 1u << (occ & 31);
                 if (!(*w & m)) atomicOr(w, m);
             }
@@ -459,7 +461,8 @@ __global__ void k_view_start(const FwdArgs a, int n_views, int* __restrict__ kst
             if (zmax_mm >= (float)a.z0) k0 = min(a.S, (int)floorf((zmax_mm - (float)a.z0) / (float)a.zdelta) + 1);
         }
     }
-    kstart[view] = max(k0, 0);
+    // -1: the view's error bound is too large (or the pose is not finite): k_forward_line must evaluate every sample exactly
+    kstart[view] = (emax <= 0.1f && v.bytes != nullptr) ? max(k0, 0) : -1;
 }
 
 // ---- K1 on distance bytes: k_forward_dist ---------------------------------------------------------------------
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
     float hpx = 0.f, hpy = 0.f, hpz = 0.f;
     unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
     const int S = a.S;
-    int k = active ? min(__ldg(a.kstart + view), S) : 0;      // leading probes that no ray of this view can hit (k_view_start)
+    int k = active ? min(max(__ldg(a.kstart + view), 0), S) : 0;      // leading probes that no ray of this view can hit (k_view_start)
     n_inb = (unsigned)k; n_skip = (unsigned)k;
     const float* xt = a.xtab + cic;
     const float* yt = a.ytab + ric;
@@ -627,74 +630,78 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
 // The line is only consulted for k in [kin, kout], where it is >= 0.25 voxel inside the volume on every axis (slab test,
 // once per ray) so its voxel is addressable; samples that are provably outside (line > 0.25 voxel beyond a face) are
 // dropped without evaluation, and the thin bands in between are evaluated exactly.  Views whose eps_q exceeds 0.1 voxel
-// (or NaN/inf poses) evaluate every sample exactly.  The pose lives in shared memory: the exact path is the rare one, so
-// it re-reads the 12 floats instead of pinning 12 registers through the line loop (12 blocks of 128 threads per SM).
+// (or NaN/inf poses; k_view_start flags them with kstart = -1) evaluate every sample exactly.
+// The kernel is issue-bound (ncu: > 80 % issue-active), so the code below counts instructions:
+//   * the pose lives in shared memory and is re-read with vector loads where the (rare) exact path needs it, instead of
+//     pinning 12 registers through the line loop (12 blocks of 128 threads per SM);
+//   * "samples advanced after a probe with byte d" comes from a 256-entry shared table built once per block from the
+//     block's largest |QB| (rays of a 16x8 pixel tile are within ~1 degree, so the common rate costs < 2 % of jump length);
+//     entries 0 and 1 hold 2^20, which ends the loop through the same comparison as running past kout;
+//   * reciprocals are MUFU approximations: they only steer conservative bounds that carry a whole sample of guard.
 constexpr int LINE_MIN_BLOCKS = 12;
+constexpr float LINE_EXACT_FLAG = 1048576.0f;      // 2^20, far above any sample index or jump (<= 254 * 1000 + 1)
+
+__device__ __forceinline__ float4 lds_f4_volatile(unsigned smem_addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem_addr));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 template <int MODE, bool EXACT>
 __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(const FwdArgs a) {
-    __shared__ unsigned long long s_cnt[5];
-    __shared__ float s_pose[12];
+    __shared__ __align__(16) float s_pose[12];
+    __shared__ float s_adv[256];
+    __shared__ int s_qbmax;
     const int view = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
-    const int ri = blockIdx.y * SKIP_TILE_H + (warp >> 1) * 4 + (lane >> 3);
+    int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
+    int ri = blockIdx.y * SKIP_TILE_H + (warp >> 1) * 4 + (lane >> 3);
     const bool active = ci < a.Wc && ri < a.Hc;
-    if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0ull;
-    if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldg(a.poses + 12 * (size_t)view + threadIdx.x);
+    if (!active) { ci = 0; ri = 0; }
+    if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldg(a.poses + 12u * (unsigned)view + threadIdx.x);
+    if (threadIdx.x == 32) s_qbmax = 0;
 #ifdef DMF_LINE_STATS
     const long long t_begin = clock64();
     long long t_line = 0, t_exact = 0;
 #endif
     __syncthreads();
-    const volatile float* const sp = s_pose;      // volatile: re-read where used, never hoisted into registers
+    const unsigned sp = (unsigned)__cvta_generic_to_shared(s_pose);
     const VolDev& v = a.vol;
     const float kM = 12582912.0f;
     const int S = a.S;
 
-    // ---- per ray: the line, the skip rate, and the sample intervals ----
-    float qa0, qa1, qa2, qb0, qb1, qb2, rq, c1;
+    // ---- per ray: the line and the sample intervals ----
+    float qa0, qa1, qa2, qb0, qb1, qb2;
     int k = 0, kin = 1, kout = 0, s_end = S;
     unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
+    const int ks = __ldg(a.kstart + view);            // -1: no skipping for this view; else leading probes no ray can hit
     {
-        const float m00 = sp[0], m01 = sp[1], m02 = sp[2], m03 = sp[3], m10 = sp[4], m11 = sp[5], m12 = sp[6], m13 = sp[7];
-        const float m20 = sp[8], m21 = sp[9], m22 = sp[10], m23 = sp[11];
-        const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2];
-        const int cic = active ? ci : 0, ric = active ? ri : 0;
-        const float dcx = __ldg(a.dcx + cic), dcy = __ldg(a.dcy + ric);
-        const float g0 = fmaf(m00, dcx, fmaf(m01, dcy, m02)), g1 = fmaf(m10, dcx, fmaf(m11, dcy, m12)), g2 = fmaf(m20, dcx, fmaf(m21, dcy, m22));
+        const float4 r0 = lds_f4_volatile(sp), r1 = lds_f4_volatile(sp + 16), r2 = lds_f4_volatile(sp + 32);
+        const float dcx = __ldg(a.dcx + ci), dcy = __ldg(a.dcy + ri);
+        const float g0 = fmaf(r0.x, dcx, fmaf(r0.y, dcy, r0.z)), g1 = fmaf(r1.x, dcx, fmaf(r1.y, dcy, r1.z)), g2 = fmaf(r2.x, dcx, fmaf(r2.y, dcy, r2.z));
         const float z0m = (float)a.z0 * 0.001f, zdm = (float)a.zdelta * 0.001f;
-        qa0 = fmaf(fmaf(z0m, g0, m03), in0, v.c32[0]); qa1 = fmaf(fmaf(z0m, g1, m13), in1, v.c32[1]); qa2 = fmaf(fmaf(z0m, g2, m23), in2, v.c32[2]);
-        qb0 = zdm * g0 * in0; qb1 = zdm * g1 * in1; qb2 = zdm * g2 * in2;
+        qa0 = fmaf(fmaf(z0m, g0, r0.w), v.inv32[0], v.c32[0]); qa1 = fmaf(fmaf(z0m, g1, r1.w), v.inv32[1], v.c32[1]); qa2 = fmaf(fmaf(z0m, g2, r2.w), v.inv32[2], v.c32[2]);
+        qb0 = zdm * g0 * v.inv32[0]; qb1 = zdm * g1 * v.inv32[1]; qb2 = zdm * g2 * v.inv32[2];
         const float qbmax = fmaxf(fabsf(qb0), fmaxf(fabsf(qb1), fabsf(qb2)));
-        rq = 1.0f / fmaxf(qbmax, 1e-3f);          // <= 1000: (d - 1.25) * rq + 1 stays far inside the shifter's range
-        c1 = fmaf(-1.25f, rq, 1.0f);              // floor(d * rq + c1) = 1 + number of samples skipped after a probe with byte d
-        const float kEps = 9.5367431640625e-07f;  // 16 * 2^-24
-        const float e0 = kEps * (fabsf(m00) * a.dcx_max + fabsf(m01) * a.dcy_max + fabsf(m02) + fabsf(m03) + fabsf((float)v.vmin[0])) * fabsf(in0);
-        const float e1 = kEps * (fabsf(m10) * a.dcx_max + fabsf(m11) * a.dcy_max + fabsf(m12) + fabsf(m13) + fabsf((float)v.vmin[1])) * fabsf(in1);
-        const float e2 = kEps * (fabsf(m20) * a.dcx_max + fabsf(m21) * a.dcy_max + fabsf(m22) + fabsf(m23) + fabsf((float)v.vmin[2])) * fabsf(in2);
-        const bool skip_ok = v.bytes != nullptr && fmaxf(e0, fmaxf(e1, e2)) <= 0.1f;   // NaN poses compare false
-        if (skip_ok) {
-            // real-valued k intervals: [ti0, ti1] line >= 0.25 voxel inside on every axis; [to0, to1] line < 0.25 voxel outside
+        if (ks >= 0) {
+            atomicMax(&s_qbmax, __float_as_int(qbmax));                            // non-negative floats order like their bit patterns
+            // real-valued k intervals: [ti0, ti1] line >= 0.25 voxel inside on every axis; [to0, to1] line < 0.25 voxel outside.
+            // Per axis the outer interval is the inner one widened by 0.5 voxel = 0.5 * |1/qb| samples on each side.  An axis the
+            // ray is parallel to gets a huge finite "reciprocal": its interval becomes everything or nothing, as it should.
             float ti0 = -1e30f, ti1 = 1e30f, to0 = -1e30f, to1 = 1e30f;
             const float qa[3] = {qa0, qa1, qa2}, qb[3] = {qb0, qb1, qb2};
 #pragma unroll
             for (int ax = 0; ax < 3; ax++) {
-                const float hi_in = v.ext[ax] - 0.25f, hi_out = v.ext[ax] + 0.25f;
-                if (fabsf(qb[ax]) > 1e-12f) {
-                    const float r = 1.0f / qb[ax];
-                    const float ia = (0.25f - qa[ax]) * r, ib = (hi_in - qa[ax]) * r;
-                    const float oa = (-0.25f - qa[ax]) * r, ob = (hi_out - qa[ax]) * r;
-                    ti0 = fmaxf(ti0, fminf(ia, ib)); ti1 = fminf(ti1, fmaxf(ia, ib));
-                    to0 = fmaxf(to0, fminf(oa, ob)); to1 = fminf(to1, fmaxf(oa, ob));
-                } else {
-                    if (!(qa[ax] >= 0.25f && qa[ax] <= hi_in)) ti0 = 1e30f;
-                    if (!(qa[ax] >= -0.25f && qa[ax] <= hi_out)) to0 = 1e30f;
-                }
+                const float r = fabsf(qb[ax]) > 1e-12f ? rcp_approx(qb[ax]) : 1e30f;
+                const float ta = (0.25f - qa[ax]) * r, tb = (v.ext[ax] - 0.25f - qa[ax]) * r, w = 0.5f * fabsf(r);
+                const float lo = fminf(ta, tb), hi = fmaxf(ta, tb);
+                ti0 = fmaxf(ti0, lo); ti1 = fminf(ti1, hi);
+                to0 = fmaxf(to0, lo - w); to1 = fminf(to1, hi + w);
             }
             // the t's carry a few ulps of relative error: one sample of guard on each end (|t| that matter are < 2^20)
             const float Sf = (float)S;
-            if (!(to0 <= to1)) { k = S; }                                         // never inside: every sample fails validPoints
+            if (!(to0 <= to1)) k = S;                                                // never inside: every sample fails validPoints
             else {
                 k = (int)fminf(fmaxf(floorf(to0) - 1.0f, 0.0f), Sf);
                 s_end = (int)fminf(fmaxf(ceilf(to1) + 2.0f, 0.0f), Sf);
@@ -703,19 +710,33 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
                     kout = (int)fminf(fmaxf(floorf(ti1) - 1.0f, -1.0f), Sf - 1.0f);
                 }
             }
-            const int ks = min(__ldg(a.kstart + view), S);                        // leading probes no ray of this view can hit (k_view_start)
-            if (ks > k) { k = ks; }
-            n_inb = n_skip = (unsigned)ks;                                        // ks > 0 only when the camera sits inside the volume: to0 < 0
+            const int k0 = min(ks, S);
+            k = max(k, k0);
+            n_inb = n_skip = (unsigned)k0;                                            // k0 > 0 only when the camera sits inside the volume
         }
     }
     if (!active) k = s_end = S;
+    __syncthreads();
+    {
+        // s_adv[d] = 1 + number of samples skipped after a line probe with byte d, at the block's largest |QB|
+        const float rq = rcp_approx(fmaxf(__int_as_float(s_qbmax), 1e-3f)) * 0.999999f;     // <= 1000
+        const float c1 = fmaf(-1.25f, rq, 1.0f);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int d = threadIdx.x + j * SKIP_THREADS;
+            s_adv[d] = d < 2 ? LINE_EXACT_FLAG : __fadd_rd(fmaf((float)d, rq, c1), kM) - kM;
+        }
+    }
+    __syncthreads();
+    // opaque register copies: otherwise the compiler re-derives the pixel from %tid / %ctaid on every exact evaluation
+    asm volatile("" : "+r"(ci), "+r"(ri));
 
     int hit_k = -1, hx = 0, hy = 0, hz = 0;
     float hpx = 0.f, hpy = 0.f, hpz = 0.f;
     const unsigned char* __restrict__ gbytes = v.bytes;
     const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
     const unsigned pnyz = pny * pnz;
-    const unsigned bias = 0x4B400000u * (pnyz + pnz + 1u);                          // folds the three "- 0x4B400000" of the shifter into one
+    const unsigned bias = 0x4B400000u * (pnyz + pnz + 1u);                          // the three "- 0x4B400000" of the shifter, folded
     unsigned iter = 0;
     bool stop = false;
     while (k < s_end && !stop) {
@@ -726,31 +747,30 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
 #endif
             float kf = (float)k;
             const float koutf = (float)kout;
-            unsigned d;
             for (;;) {
                 if (MODE == 4 && (iter++ & 7u) == 0u) {   // rayTraceAndGetMinimum: planes behind the current minimum cannot matter
                     const int cur = *((volatile int*)(a.min_depth + view));
-                    if (a.z0 + (int)kf * a.zdelta > cur) { stop = true; d = 2u; break; }
+                    if (a.z0 + (int)kf * a.zdelta > cur) { stop = true; break; }
                 }
                 const unsigned bx = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb0, qa0), kM));
                 const unsigned by = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb1, qa1), kM));
                 const unsigned bz = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb2, qa2), kM));
-                d = __ldg(gbytes + (bx * pnyz + by * pnz + bz - bias));
+                const unsigned d = __ldg(gbytes + (bx * pnyz + (by * pnz + (bz - bias))));
 #ifdef DMF_LINE_STATS
                 n_f64++;                                   // diagnostic build: F64_PATH counts line probes, EXACT_DIV exact ones
 #endif
-                if (d < 2u) break;
-                const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;           // (float)d without I2F
-                kf += __fadd_rd(fmaf(df, rq, c1), kM) - kM;                                   // this probe + the skipped ones
+                kf += s_adv[d];                            // this probe + the skipped ones; 2^20 when the probe must be evaluated exactly
                 if (!(kf <= koutf)) break;
             }
 #ifdef DMF_LINE_STATS
             t_line += clock64() - tl0;
 #endif
+            const bool need_exact = kf >= LINE_EXACT_FLAG;
+            if (need_exact) kf -= LINE_EXACT_FLAG;
             const int k2 = min((int)kf, s_end);
             n_inb += (unsigned)(k2 - k); n_skip += (unsigned)(k2 - k);
             k = k2;
-            if (d >= 2u) continue;
+            if (!need_exact) continue;
         }
         // ---- exact evaluation of sample k (identical to k_forward) ----
         if (MODE == 4 && (iter++ & 7u) == 0u) {
@@ -761,10 +781,12 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
         n_exact++;
         const long long te0 = clock64();
 #endif
-        const float xf = __ldg(a.xtab + (size_t)k * a.Wc + ci), yf = __ldg(a.ytab + (size_t)k * a.Hc + ri), zf = __ldg(a.ztab + k);
-        const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp[0], xf), __fmul_rn(sp[1], yf)), __fmul_rn(sp[2], zf)), sp[3]);
-        const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp[4], xf), __fmul_rn(sp[5], yf)), __fmul_rn(sp[6], zf)), sp[7]);
-        const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp[8], xf), __fmul_rn(sp[9], yf)), __fmul_rn(sp[10], zf)), sp[11]);
+        const float xf = __ldg(a.xtab + ((unsigned)k * (unsigned)a.Wc + (unsigned)ci)), yf = __ldg(a.ytab + ((unsigned)k * (unsigned)a.Hc + (unsigned)ri));
+        const float zf = __ldg(a.ztab + k);
+        const float4 r0 = lds_f4_volatile(sp), r1 = lds_f4_volatile(sp + 16), r2 = lds_f4_volatile(sp + 32);
+        const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, xf), __fmul_rn(r0.y, yf)), __fmul_rn(r0.z, zf)), r0.w);
+        const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, xf), __fmul_rn(r1.y, yf)), __fmul_rn(r1.z, zf)), r1.w);
+        const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, xf), __fmul_rn(r2.y, yf)), __fmul_rn(r2.z, zf)), r2.w);
         if (!(px > v.lo[0] && px < v.hi[0] && py > v.lo[1] && py < v.hi[1] && pz > v.lo[2] && pz < v.hi[2])) { k++; continue; }   // validPoints failed
         n_inb++;
         int ix, iy, iz;
@@ -778,7 +800,9 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
         k++;
     }
     const unsigned n_samples = active ? (unsigned)((hit_k >= 0 || stop || (MODE == 4 && k < s_end)) ? min(k, S) : S) : 0u;
-    forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, sp[3], sp[7], sp[11], n_samples, n_inb, n_exact, n_f64, n_skip);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    if (MODE == 1 || MODE == 2) { t0 = s_pose[3]; t1 = s_pose[7]; t2 = s_pose[11]; }
+    forward_epilogue<MODE>(a, nullptr, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, t0, t1, t2, n_samples, n_inb, n_exact, n_f64, n_skip);
 #ifdef DMF_LINE_STATS
     if (lane == 0) {
         unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
