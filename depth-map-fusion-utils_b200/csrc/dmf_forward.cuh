@@ -13,6 +13,7 @@ struct FwdArgs {
     VolDev vol;
     AngleTest angle;
     const float* __restrict__ poses;   // [n_views][12]
+    int view0;                         // first view of this launch (a batch may be marched as several launches, blockIdx.z = view - view0)
     // projectPoint tables (Camera.hpp:24-31), built once per (K, H, W, z0, zdelta, stride) by k_build_tables:
     const float* __restrict__ xtab;    // [S][Wc]  (float)(z_k*((double)c-cx)/fx)
     const float* __restrict__ ytab;    // [S][Hc]  (float)(z_k*((double)r-cy)/fy)
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
     __shared__ __align__(16) float sz[FWD_CHUNK][4];   // m02*z, m12*z, m22*z
     __shared__ unsigned long long s_cnt[5];
 
-    const int view = blockIdx.z;
+    const int view = blockIdx.z + a.view0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lc = (warp & 3) * 8 + (lane & 7);   // column within the tile
     const int lr = (warp >> 2) * 4 + (lane >> 3); // row within the tile
@@ -285,7 +286,7 @@ constexpr int SKIP_TILE_W = 16, SKIP_TILE_H = 8;
 template <int MODE, int FMT>
 __global__ void __launch_bounds__(SKIP_THREADS, 8) k_forward_skip(const FwdArgs a) {
     __shared__ unsigned long long s_cnt[5];
-    const int view = blockIdx.z;
+    const int view = blockIdx.z + a.view0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
     const int ri = blockIdx.y * SKIP_TILE_H + (warp >> 1) * 4 + (lane >> 3);
@@ -499,7 +500,7 @@ __device__ __forceinline__ unsigned probe_index(const VolDev& v, float px, float
 template <int MODE, bool EXACT>
 __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs a) {
     __shared__ unsigned long long s_cnt[5];
-    const int view = blockIdx.z;
+    const int view = blockIdx.z + a.view0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
     const int ri = blockIdx.y * SKIP_TILE_H + (warp >> 1) * 4 + (lane >> 3);
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
     __shared__ __align__(16) float s_pose[12];
     __shared__ float s_adv[256];
     __shared__ int s_qbmax;
-    const int view = blockIdx.z;
+    const int view = blockIdx.z + a.view0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
     int ri = blockIdx.y * SKIP_TILE_H + (warp >> 1) * 4 + (lane >> 3);

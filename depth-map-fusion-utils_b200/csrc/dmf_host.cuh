@@ -121,7 +121,8 @@ struct TableKey {
 
 struct dmf_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, aux_stream = nullptr;   // aux: every other sub-launch of a split march
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;     // bracket the kernels of the last call
     cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;     // bracket the dominant march kernel of the last call
