@@ -176,14 +176,30 @@ __device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float
     }
 }
 
+// Warp-reduce the per-thread tallies (REDUX) and add the non-zero ones to one of the 256 counter replicas with result-less
+// atomics.  Must be called by all 32 lanes.  The rarely non-zero tallies are reduced only if any lane has one.
 __device__ __forceinline__ void flush_counters(u64* counters, unsigned n_samples, unsigned n_inb, unsigned n_hits, unsigned n_exact,
                                                unsigned n_oob, unsigned n_ties, unsigned n_runaway, unsigned n_f64 = 0, unsigned n_skip = 0) {
-    unsigned long long c[9] = {n_samples, n_inb, n_hits, n_exact, n_oob, n_ties, n_runaway, n_f64, n_skip};
-    const int slot[9] = {0, 1, 2, 3, 4, 5, 7, 8, 9};
-#pragma unroll
-    for (int j = 0; j < 9; j++) {
-        for (int o = 16; o; o >>= 1) c[j] += __shfl_down_sync(0xffffffffu, c[j], o);
-        if ((threadIdx.x & 31) == 0 && c[j]) atomicAdd(counter_slot(counters) + slot[j], c[j]);
+    const unsigned full = 0xffffffffu;
+    const unsigned c0 = __reduce_add_sync(full, n_samples), c1 = __reduce_add_sync(full, n_inb), c2 = __reduce_add_sync(full, n_hits);
+    const unsigned c9 = __reduce_add_sync(full, n_skip);
+    const unsigned rare = __reduce_or_sync(full, n_exact | n_oob | n_ties | n_runaway | n_f64);
+    unsigned c3 = 0, c4 = 0, c5 = 0, c7 = 0, c8 = 0;
+    if (rare) {
+        c3 = __reduce_add_sync(full, n_exact); c4 = __reduce_add_sync(full, n_oob); c5 = __reduce_add_sync(full, n_ties);
+        c7 = __reduce_add_sync(full, n_runaway); c8 = __reduce_add_sync(full, n_f64);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        u64* const g = counter_slot(counters);
+        if (c0) atomicAdd(g + 0, (unsigned long long)c0);
+        if (c1) atomicAdd(g + 1, (unsigned long long)c1);
+        if (c2) atomicAdd(g + 2, (unsigned long long)c2);
+        if (c9) atomicAdd(g + 9, (unsigned long long)c9);
+        if (c3) atomicAdd(g + 3, (unsigned long long)c3);
+        if (c4) atomicAdd(g + 4, (unsigned long long)c4);
+        if (c5) atomicAdd(g + 5, (unsigned long long)c5);
+        if (c7) atomicAdd(g + 7, (unsigned long long)c7);
+        if (c8) atomicAdd(g + 8, (unsigned long long)c8);
     }
 }
 
@@ -197,7 +213,7 @@ __global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
     unsigned n_samples = 0, n_inb = 0, n_hits = 0, n_exact = 0, n_oob = 0, n_ties = 0, n_runaway = 0, n_f64 = 0, n_skip = 0;
     const float* T = a.poses + 12 * (size_t)view;
     const float* I = a.inv_poses + 12 * (size_t)view;
-    bool live = true;
+    bool live = true, f_unocc = false, f_emit = false;
     int occ = -1; float cx = 0, cy = 0, cz = 0; u64 chash = 0;
     if (FAST) {
         live = t < (size_t)v.n_occ;
@@ -241,17 +257,21 @@ __global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
             const bool collided = march_collides<FMT>(a, cx, cy, cz, vx, vy, vz, chash, FAST ? 50 : 1, n_samples, n_inb, n_exact, n_runaway, n_f64, n_skip);
             if (!collided) {
                 n_hits++;
-                if (a.found_any) raise_flag(a.found_any + view);
-                if (a.unocc) atomicOr(a.unocc + (size_t)view * a.vis_words32 + (occ >> 5), 1u << (occ & 31));
+                f_unocc = true;
+                if (!FAST) {
+                    if (a.found_any) raise_flag(a.found_any + view);
+                    if (a.unocc) atomicOr(a.unocc + (size_t)view * a.vis_words32 + (occ >> 5), 1u << (occ & 31));
+                }
                 if (a.viz) a.view_mark[occ] = 1;                                     // :108, :205
                 bool emit = false;
                 if ((double)zz >= 0.20 && (double)zz <= 1.0) {                       // k_ZMin, k_ZMax (:109, :206)
                     emit = FAST ? any_normal_faces(v, a.angle, occ, vx, vy, vz, n_ties) : true;
                 }
-                if (emit) {
+                f_emit = emit;
+                if (emit && !FAST) {
                     if (a.viz) atomicOr(a.good_bits + (occ >> 5), 1u << (occ & 31)); // :112, :215
                     if (a.vis) atomicOr(a.vis + (size_t)view * a.vis_words32 + (occ >> 5), 1u << (occ & 31));
-                    if (!FAST && a.emit_count) {
+                    if (a.emit_count) {
                         unsigned slot = atomicAdd(a.emit_count + view, 1u);
                         if (a.emit_list && slot < a.emit_cap) {
                             a.emit_list[2 * ((size_t)view * a.emit_cap + slot)] = (u64)t;
@@ -259,6 +279,20 @@ __global__ void __launch_bounds__(128) k_reverse(const RevArgs a) {
                         }
                     }
                 }
+            }
+        }
+    }
+    if (FAST) {
+        // thread t <-> occupied ordinal t: the 32 lanes of a warp own exactly one word of every per-voxel bitset, so the warp
+        // publishes its results with one atomic per bitset instead of one per voxel
+        const unsigned mu = __ballot_sync(0xffffffffu, f_unocc), me = __ballot_sync(0xffffffffu, f_emit);
+        if ((threadIdx.x & 31) == 0 && mu) {
+            const size_t w = (size_t)view * a.vis_words32 + (size_t)(t >> 5);
+            if (a.found_any) raise_flag(a.found_any + view);
+            if (a.unocc) atomicOr(a.unocc + w, mu);
+            if (me) {
+                if (a.viz) atomicOr(a.good_bits + (t >> 5), me);                     // :112, :215
+                if (a.vis) atomicOr(a.vis + w, me);
             }
         }
     }
