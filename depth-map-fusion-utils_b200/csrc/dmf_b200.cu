@@ -321,8 +321,8 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     a.counters = c->d_counters.as<u64>();
     a.dcx = c->d_dcx.as<float>(); a.dcy = c->d_dcy.as<float>(); a.clearance = c->d_clearance.as<float>();
     a.dcx_max = c->dcx_max; a.dcy_max = c->dcy_max;
-    DMF_TRY(c->d_kstart.reserve((size_t)n_views * 4));
-    a.kstart = c->d_kstart.as<int>();
+    DMF_TRY(c->d_kstart.reserve((size_t)n_views * 8));
+    a.kstart = c->d_kstart.as<int>(); a.veps = c->d_kstart.as<float>() + n_views;
     const bool skip = !(p->flags & DMF_FWD_NO_SKIP);
     const bool byte_skip = skip && p->grid_format == DMF_GRID_BYTE;
     const bool two_probe = (p->flags & DMF_FWD_TWO_PROBE) != 0;

@@ -25,7 +25,8 @@ struct FwdArgs {
     const float* __restrict__ clearance; // [mdim_x][mdim_y][mdim_z] voxels that can be crossed (L-inf) from anywhere in the cell
                                        //  while provably staying in empty, in-bounds macro cells (0 = evaluate exactly)
     float dcx_max, dcy_max;            // max |dcx|, |dcy| (for the per-view error bound)
-    const int* __restrict__ kstart;    // [n_views] probes 0..kstart-1 of EVERY ray of the view are provably in-bounds misses (k_view_start)
+    const int* __restrict__ kstart;    // [n_views] probes 0..kstart-1 of EVERY ray of the view are provably in-bounds misses (k_view_start); -1 = view must not skip
+    float* veps;                       // [n_views] the view's bound on |reference sample - line point| in voxels (k_view_start)
     // outputs (may be null)
     int* depth;                        // [n_views][H][W]
     unsigned short* depth16;           // [n_views][H][W]  same, 0xFFFF = none
@@ -464,6 +465,7 @@ __global__ void k_view_start(const FwdArgs a, int n_views, int* __restrict__ kst
     }
     // -1: the view's error bound is too large (or the pose is not finite): k_forward_line must evaluate every sample exactly
     kstart[view] = (emax <= 0.1f && v.bytes != nullptr) ? max(k0, 0) : -1;
+    if (a.veps) a.veps[view] = emax;
 }
 
 // ---- K1 on distance bytes: k_forward_dist ---------------------------------------------------------------------
@@ -654,6 +656,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
     __shared__ __align__(16) float s_pose[12];
     __shared__ float s_adv[256];
     __shared__ int s_qbmax;
+    __shared__ float s_esafe;
     const int view = blockIdx.z + a.view0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
@@ -661,7 +664,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
     const bool active = ci < a.Wc && ri < a.Hc;
     if (!active) { ci = 0; ri = 0; }
     if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldg(a.poses + 12u * (unsigned)view + threadIdx.x);
-    if (threadIdx.x == 32) s_qbmax = 0;
+    if (threadIdx.x == 32) { s_qbmax = 0; s_esafe = __ldg(a.veps + view) + 0.0009765625f; }   // eps_q of the view + 2^-10 voxel of slack
 #ifdef DMF_LINE_STATS
     const long long t_begin = clock64();
     long long t_line = 0, t_exact = 0;
@@ -760,7 +763,17 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
 #ifdef DMF_LINE_STATS
                 n_f64++;                                   // diagnostic build: F64_PATH counts line probes, EXACT_DIV exact ones
 #endif
-                kf += s_adv[d];                            // this probe + the skipped ones; 2^20 when the probe must be evaluated exactly
+                float adv = s_adv[d];                      // this probe + the skipped ones; 2^20 when the probe must be evaluated exactly
+                if (d == 1u) {
+                    // Next to an occupied voxel or in the boundary layer, but this voxel itself is empty.  If the line point is
+                    // at least e_safe (> eps_q) away from every face of its voxel, the reference's sample is in the same voxel:
+                    // an in-bounds miss (the line is >= 0.25 voxel inside the volume here).  Otherwise evaluate exactly.
+                    const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
+                    const float f0 = q0 - (__fadd_rd(q0, kM) - kM), f1 = q1 - (__fadd_rd(q1, kM) - kM), f2 = q2 - (__fadd_rd(q2, kM) - kM);
+                    const float e = s_esafe;
+                    if (fminf(f0, fminf(f1, f2)) >= e && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e) adv = 1.0f;
+                }
+                kf += adv;
                 if (!(kf <= koutf)) break;
             }
 #ifdef DMF_LINE_STATS
