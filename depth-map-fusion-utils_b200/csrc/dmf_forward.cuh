@@ -446,11 +446,15 @@ __global__ void k_view_start(const FwdArgs a, int n_views, int* __restrict__ kst
     const float tx = m[0][3], ty = m[1][3], tz = m[2][3];
     const float kEps = 9.5367431640625e-07f;   // 16 * 2^-24
     float emax = 0.f, G = 0.f;
+    bool finite = true;                                   // fmaxf drops NaN operands, so non-finite poses are tested explicitly
     for (int i = 0; i < 3; i++) {
         const float reach = fabsf(m[i][0]) * a.dcx_max + fabsf(m[i][1]) * a.dcy_max + fabsf(m[i][2]);
-        emax = fmaxf(emax, kEps * (reach + fabsf(m[i][3]) + fabsf((float)v.vmin[i])) * fabsf(v.inv32[i]));
+        const float e = kEps * (reach + fabsf(m[i][3]) + fabsf((float)v.vmin[i])) * fabsf(v.inv32[i]);
+        finite = finite && (e <= 3.0e38f);                // false for NaN and +inf
+        emax = fmaxf(emax, e);
         G = fmaxf(G, reach * fabsf(v.inv32[i]) * 1.00001f);
     }
+    if (!finite) emax = __int_as_float(0x7fc00000);       // NaN: every "<= bound" test downstream fails
     if (emax <= 0.1f && in_bounds(v, tx, ty, tz) && v.bytes != nullptr) {       // NaN poses fail the comparisons
         unsigned ne = 0;
         const int ix = voxel_index(tx, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], ne);
@@ -636,12 +640,12 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
 // (or NaN/inf poses; k_view_start flags them with kstart = -1) evaluate every sample exactly.
 // The kernel is issue-bound (ncu: > 80 % issue-active), so the code below counts instructions:
 //   * the pose lives in shared memory and is re-read with vector loads where the (rare) exact path needs it, instead of
-//     pinning 12 registers through the line loop (12 blocks of 128 threads per SM);
+//     pinning 12 registers through the line loop (16 blocks of 128 threads = all 64 warp slots of an SM; measured 9 % faster than 12 blocks / 40 registers);
 //   * "samples advanced after a probe with byte d" comes from a 256-entry shared table built once per block from the
 //     block's largest |QB| (rays of a 16x8 pixel tile are within ~1 degree, so the common rate costs < 2 % of jump length);
 //     entries 0 and 1 hold 2^20, which ends the loop through the same comparison as running past kout;
 //   * reciprocals are MUFU approximations: they only steer conservative bounds that carry a whole sample of guard.
-constexpr int LINE_MIN_BLOCKS = 12;
+constexpr int LINE_MIN_BLOCKS = 16;
 constexpr float LINE_EXACT_FLAG = 1048576.0f;      // 2^20, far above any sample index or jump (<= 254 * 1000 + 1)
 
 __device__ __forceinline__ float4 lds_f4_volatile(unsigned smem_addr) {
@@ -741,6 +745,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
     const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
     const unsigned pnyz = pny * pnz;
     const unsigned bias = 0x4B400000u * (pnyz + pnz + 1u);                          // the three "- 0x4B400000" of the shifter, folded
+    const unsigned last = pnyz * (unsigned)v.pdim[0] - 1u;
     unsigned iter = 0;
     bool stop = false;
     while (k < s_end && !stop) {
@@ -759,7 +764,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
                 const unsigned bx = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb0, qa0), kM));
                 const unsigned by = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb1, qa1), kM));
                 const unsigned bz = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb2, qa2), kM));
-                const unsigned d = __ldg(gbytes + (bx * pnyz + (by * pnz + (bz - bias))));
+                const unsigned d = __ldg(gbytes + min(bx * pnyz + (by * pnz + (bz - bias)), last));   // (the clamp is a seat belt, never active)
 #ifdef DMF_LINE_STATS
                 n_f64++;                                   // diagnostic build: F64_PATH counts line probes, EXACT_DIV exact ones
 #endif

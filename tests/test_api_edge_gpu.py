@@ -88,6 +88,28 @@ def test_nan_and_degenerate_poses_do_not_crash(dmf, ctx):
     ctx.synchronize()
 
 
+def test_partially_non_finite_poses_match_oracle(dmf, oracle, ctx):
+    """one NaN / inf entry in an otherwise sane pose: fmaxf-style bounds drop NaNs, so the line-first march must be
+    told explicitly not to follow such a view (regression: garbage line addresses); results still equal the oracle's"""
+    sc, gv = _vol(dmf, ctx)
+    ov = oracle.volume_from_scene(sc, flat=True)
+    K = dmf.scenes.REFERENCE_K
+    eng = dmf.RayTracingEngine(dmf.Camera(K), ctx)
+    base = dmf.scenes.pose_p1(float(sc.bounds[1]))[0]
+    poses = [base.copy()]
+    for idx, val in ((3, np.nan), (0, np.nan), (10, np.inf), (7, -np.inf), (5, np.nan)):
+        p = base.copy(); p[idx] = val; poses.append(p)
+    poses = np.stack(poses)
+    for fmt in (dmf.GRID_BYTE, dmf.GRID_BIT):
+        eng.grid_format = fmt
+        r = eng.forward_views(gv, poses, 0, sc.zdelta, False, want=("depth", "visibility"))
+        for i, p in enumerate(poses):
+            o = oracle.forward(ov, K, 480, 640, p, oracle.MODE_POINTS, sc.zdelta, False)
+            assert np.array_equal(r["depth"][i], o["depth"]), (fmt, i)
+            assert bool(r["found_any"][i]) == o["found_any"]
+    ctx.synchronize()
+
+
 def test_two_contexts_and_reupload(dmf, oracle, ctx):
     sc_a, gv_a = _vol(dmf, ctx, "S64")
     c2 = dmf.Context(0)
