@@ -211,7 +211,7 @@ int dmf_reset_counters(dmf_ctx* ctx);
 /* duration in ms of the kernels of the most recent *_dev/host call on this context, measured with CUDA
  * events on the launching stream (synchronises) */
 int dmf_last_kernel_ms(dmf_ctx* ctx, float* ms);
-/* same, for the dominant march kernel alone (k_forward / k_reverse of the last chunk launched) */
+/* same, for the dominant march kernel(s) alone (the k_forward* / k_reverse launches of the last call or pass) */
 int dmf_last_hot_kernel_ms(dmf_ctx* ctx, float* ms);
 int dmf_synchronize(dmf_ctx* ctx);
 
