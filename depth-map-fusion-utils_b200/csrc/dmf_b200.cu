@@ -76,6 +76,12 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
         v.rev_eps[a] = (float)(std::ldexp(8.0, -24) * std::max(std::fabs(vmin), std::fabs(vmax)) * v.inv[a] * 2.0);
         v.ext[a] = next_up((float)((vmax - vmin) * v.inv[a] * (1.0 + 1e-7)));
     }
+    {
+        // 2 * rev_eps covers the reference sample's and the float line's distance from the ideal line; the dim-scaled term the
+        // slope's rounding over a whole march (~4 ulp at the largest voxel coordinate); 2^-12 is plain slack
+        const float re = std::max(v.rev_eps[0], std::max(v.rev_eps[1], v.rev_eps[2]));
+        v.rev_esafe = 2.0f * re + (float)std::ldexp((double)std::max(dim[0], std::max(dim[1], dim[2])) + 2.0, -21) + (float)std::ldexp(1.0, -12);
+    }
     const size_t nbits = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
     const size_t nwords = ((nbits + 31) / 32 + 7) / 8 * 8;           // whole 8-word (256-bit) rank blocks
     const size_t nmacro = (size_t)v.mdim[0] * v.mdim[1] * v.mdim[2];

@@ -64,6 +64,7 @@ struct VolDev {
     float lo[3];     // largest float <= vmin   (validPoints: x<=xmin_  <=>  !(x > lo))
     float hi[3];     // smallest float >= vmax  (validPoints: x>=xmax_  <=>  !(x < hi))
     float rev_eps[3]; // bound (voxel units) on |reverse-march sample - its line point|; > 0.1 disables skipping there
+    float rev_esafe;  // a line point at least this far from every face of its voxel shares the voxel with the reference's sample
     float ext[3];    // >= (vmax-vmin)/delta: the volume's extent in voxel units (dim <= ext < dim+1, constructVolume truncates)
 };
 
