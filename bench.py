@@ -196,6 +196,8 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
+    from dmf_b200.sweep import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local)        # before any pinned allocation: host buffers on the GPU's own socket
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -214,10 +216,10 @@ def run_b200(args):
     eng._prepare(vol)
     n_occ = len(vol.occupied_cells_)
     vw = (n_occ + 63) // 64
-    from dmf_b200.sweep import shard_range
+    from dmf_b200.sweep import shard_indices
     all_poses = D.scenes.bench_poses(float(sc.bounds[1]), V * world)
-    lo, hi = shard_range(V * world, rank, world)
-    poses = np.ascontiguousarray(all_poses[lo:hi])                        # this rank's contiguous shard of the sweep
+    # this rank's share of the sweep, interleaved: neighbouring views cost about the same, so every rank gets the same mix
+    poses = np.ascontiguousarray(all_poses[shard_indices(V * world, rank, world, "strided")])
     dev = torch.device("cuda", local)
 
     # device-resident buffers for `value`
@@ -239,16 +241,49 @@ def run_b200(args):
     bench_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(bench_stream)
 
+    # N > 1: the all-gather of step i runs on its own stream while step i+1 is marched (two visibility buffers); a step's
+    # end event waits for the PREVIOUS step's gather, and the last gather is timed on its own and added, so every
+    # gather is inside the timed total exactly once.
+    d_vis2 = [d_vis, torch.zeros_like(d_vis)] if world > 1 else [d_vis]
+    d_vis_all2 = [d_vis_all, torch.zeros_like(d_vis_all)] if world > 1 else [None]
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    gather_done = [None, None]
+    state = {"i": 0}
+
     def step_dev():
         st = torch.cuda.current_stream().cuda_stream
         assert st != 0
+        j = state["i"] & 1 if world > 1 else 0
+        if world > 1 and gather_done[j] is not None:
+            torch.cuda.current_stream().wait_event(gather_done[j])        # buffer j is free again
+        o.visibility = d_vis2[j].data_ptr()
         check(ctx.lib.dmf_forward_dev(ctx.h, C.byref(params), C.c_void_p(d_poses.data_ptr()), V, C.byref(o), C.c_void_p(st)))
         if world > 1:
-            dist.all_gather_into_tensor(d_vis_all, d_vis)
+            marched = torch.cuda.Event(); marched.record()
+            if gather_done[j ^ 1] is not None:
+                torch.cuda.current_stream().wait_event(gather_done[j ^ 1])   # the previous step's gather ends inside this step
+            gather_stream.wait_event(marched)
+            with torch.cuda.stream(gather_stream):
+                dist.all_gather_into_tensor(d_vis_all2[j], d_vis2[j])
+                gather_done[j] = torch.cuda.Event(enable_timing=True); gather_done[j].record()
+            state["i"] += 1
+
+    def join_gathers():
+        """ms from now (on the bench stream) until the last gather has finished; 0 at N = 1"""
+        if world == 1:
+            return 0.0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for e in gather_done:
+            if e is not None:
+                torch.cuda.current_stream().wait_event(e)
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b)
 
     # ---- value: device-resident, CUDA events on torch's current stream --------------------------------------
     for _ in range(args.warmup):
         step_dev()
+    join_gathers()
     torch.cuda.synchronize()
     ctx.reset_counters()
     sampler = ClockSampler(local)
@@ -266,9 +301,12 @@ def run_b200(args):
         b.record()
         if rank == 0 and len(hot_ms) < 4:
             hot_ms.append(ctx.last_hot_kernel_ms())   # synchronises; cheap, outside the event pair's GPU time
+    tail_ms = join_gathers()
     torch.cuda.synchronize(); barrier()
     wall = time.perf_counter() - t_wall
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    d_vis = d_vis2[(state["i"] - 1) & 1] if world > 1 else d_vis          # the buffer the last step wrote
+    o.visibility = d_vis.data_ptr()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs) + tail_ms
     clocks = sampler.stop() if rank == 0 else None
     cnt = ctx.counters()
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -395,7 +433,8 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "views_per_step_per_gpu": V, "mode": "rayTraceAndGetPoints", "grid_format": args.grid,
                        "outputs": "depth_mm+points+hit_voxel+visibility", "n_occupied": n_occ,
                        "l2": "flushed between timed iterations (256 MiB fill, untimed)" if flush is not None else "not flushed",
-                       "parallelism": f"views sharded over {world} GPU(s), grid replicated" + (", visibility all-gather (NCCL) per step" if world > 1 else "")},
+                       "parallelism": f"views interleaved over {world} GPU(s) (rank, rank+N, ...), grid replicated" + (", visibility all-gather (NCCL) per step, overlapped with the next step's march" if world > 1 else ""),
+                       "host": numa},
             "voxel_updates_per_s": inbounds_total / (dev_ms * 1e-3),
             "samples_per_s": samples_total / (dev_ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -20,9 +20,23 @@ def shard_range(n_views: int, rank: int, world: int) -> Tuple[int, int]:
     return (rank * n_views) // world, ((rank + 1) * n_views) // world
 
 
-def gather_rows(local, n_total: int, group=None):
-    """All-gather row blocks produced under shard_range into the full [n_total, words] array (torch tensor in,
-    torch tensor out, on the same device).  Ragged blocks are padded to the largest block for the collective."""
+def shard_indices(n_views: int, rank: int, world: int, layout: str = "block") -> np.ndarray:
+    """View indices of rank `rank`.  "block": the contiguous block of shard_range.  "strided": rank, rank+world, ... --
+    neighbouring views of a sweep cost about the same, so interleaving them evens out the per-rank work (a step is as
+    slow as its slowest rank) at no cost: views are independent."""
+    if layout == "block":
+        a, b = shard_range(n_views, rank, world)
+        return np.arange(a, b)
+    if layout != "strided":
+        raise ValueError(f"unknown layout {layout!r}")
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    return np.arange(rank, n_views, world)
+
+
+def gather_rows(local, n_total: int, group=None, layout: str = "block"):
+    """All-gather the rows each rank produced for shard_indices(..., layout) into the full [n_total, words] array in VIEW
+    order (torch tensor in, torch tensor out, on the same device).  Ragged shards are padded for the collective."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -30,6 +44,17 @@ def gather_rows(local, n_total: int, group=None):
     if world == 1:
         assert local.shape[0] == n_total
         return local
+    if layout == "strided":
+        counts = [len(range(r, n_total, world)) for r in range(world)]
+        mx = max(counts)
+        assert local.shape[0] == counts[rank], "local rows do not match shard_indices"
+        pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, pad, group=group)
+        # row i of rank r is view i*world + r: transposing (rank, i) -> (i, rank) restores view order; padding rows fall at the end
+        out = out.reshape((world, mx) + tuple(local.shape[1:])).transpose(0, 1).reshape((world * mx,) + tuple(local.shape[1:]))
+        return out[:n_total].contiguous()
     sizes = [shard_range(n_total, r, world) for r in range(world)]
     mx = max(b - a for a, b in sizes)
     assert local.shape[0] == sizes[rank][1] - sizes[rank][0], "local block does not match shard_range"
@@ -48,22 +73,50 @@ def or_rows(bitsets) -> np.ndarray:
     return np.bitwise_or.reduce(b, axis=0) if len(b) else np.zeros(b.shape[1:], b.dtype)
 
 
-def sweep_visibility(engine, volume, poses, mode: int, zdelta: int, sparse: bool = False, reverse: bool = False, group=None) -> np.ndarray:
-    """Visibility bitsets [n_views, words] of the whole pose list, computed on this rank's shard and all-gathered.
-    Every rank returns the full array."""
+def sweep_visibility(engine, volume, poses, mode: int, zdelta: int, sparse: bool = False, reverse: bool = False, group=None,
+                     layout: str = "strided") -> np.ndarray:
+    """Visibility bitsets [n_views, words] of the whole pose list in view order, computed on this rank's shard and
+    all-gathered.  Every rank returns the full array."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
-    a, b = shard_range(len(poses), rank, world)
+    mine = poses[shard_indices(len(poses), rank, world, layout)]
     if reverse:
-        local = engine.reverse_views(volume, poses[a:b], fast=True, want=("visibility",))["visibility"]
+        local = engine.reverse_views(volume, mine, fast=True, want=("visibility",))["visibility"]
     else:
-        local = engine.forward_views(volume, poses[a:b], mode, zdelta, sparse, want=("visibility",))["visibility"]
+        local = engine.forward_views(volume, mine, mode, zdelta, sparse, want=("visibility",))["visibility"]
     if world == 1:
         return local
     t = torch.from_numpy(local.view(np.int64))
     if dist.get_backend(group) == "nccl":
         t = t.cuda()
-    return gather_rows(t, len(poses), group).cpu().numpy().view(np.uint64)
+    return gather_rows(t, len(poses), group, layout).cpu().numpy().view(np.uint64)
+
+
+def bind_to_gpu_numa_node(device: int) -> str:
+    """Pin the calling process to the CPUs that are local to GPU `device` (sysfs local_cpulist of its PCI function), so
+    that pinned host buffers allocated afterwards land on that socket's memory: with one rank per GPU, device-to-host
+    copies then do not cross the inter-socket link.  Returns a description; a no-op when the topology cannot be read."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return f"gpu {device} ({bdf}): local cpus {txt or '?'} = current affinity, nothing to do"
+        os.sched_setaffinity(0, cpus)
+        return f"gpu {device} ({bdf}): bound to its {len(cpus)} local cpus ({txt})"
+    except Exception as e:                                             # noqa: BLE001 - topology is best effort
+        return f"gpu {device}: not bound ({type(e).__name__}: {e})"

@@ -29,13 +29,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_views, q):
+def _worker(rank, world, port, n_views, q, layout="block"):
     sys.path.insert(0, os.path.join(ROOT, "depth-map-fusion-utils_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import torch.distributed as dist
     import oracle_py as O
     from dmf_b200 import scenes
-    from dmf_b200.sweep import gather_rows, or_rows, shard_range
+    from dmf_b200.sweep import gather_rows, or_rows, shard_indices
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     sc = scenes.scene("S64")
     vol = O.volume_from_scene(sc)
@@ -43,26 +43,39 @@ def _worker(rank, world, port, n_views, q):
     index = {int(h): i for i, h in enumerate(occ)}
     K = scenes.REFERENCE_K.copy(); K[[0, 2, 4, 5]] *= 0.125
     poses = scenes.poses_sphere_lookat(1.024, 200)[:: 200 // n_views][:n_views]
-    a, b = shard_range(n_views, rank, world)
+    mine = shard_indices(n_views, rank, world, layout)
     words = (len(occ) + 63) // 64
-    local = np.zeros((b - a, words), np.uint64)
-    for j, p in enumerate(poses[a:b]):
+    local = np.zeros((len(mine), words), np.uint64)
+    for j, p in enumerate(poses[mine]):
         for h in O.forward(vol, K, 60, 80, p, O.MODE_POINTS, 8, False, want_pixels=False)["ids"]:
             i = index[int(h)]
             local[j, i >> 6] |= np.uint64(1) << np.uint64(i & 63)
-    full = gather_rows(torch.from_numpy(local.view(np.int64)), n_views).numpy().view(np.uint64)
+    full = gather_rows(torch.from_numpy(local.view(np.int64)), n_views, layout=layout).numpy().view(np.uint64)
     q.put((rank, full, or_rows(full)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_views", [6, 7])   # even and ragged split over 2 ranks
-def test_two_rank_sweep_equals_single_process(dmf, oracle, n_views):
+def test_shard_indices_partition_the_views(dmf):
+    from dmf_b200.sweep import shard_indices
+    for layout in ("block", "strided"):
+        for n in (0, 1, 7, 8, 1000):
+            for world in (1, 2, 3, 8):
+                parts = [shard_indices(n, r, world, layout) for r in range(world)]
+                assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+                assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert shard_indices(10, 1, 4, "strided").tolist() == [1, 5, 9]
+    with pytest.raises(ValueError):
+        shard_indices(10, 0, 2, "diagonal")
+
+
+@pytest.mark.parametrize("n_views,layout", [(6, "block"), (7, "block"), (6, "strided"), (7, "strided")])   # even and ragged splits over 2 ranks
+def test_two_rank_sweep_equals_single_process(dmf, oracle, n_views, layout):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_views, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_views, q, layout)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict()
