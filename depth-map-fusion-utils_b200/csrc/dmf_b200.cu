@@ -42,12 +42,10 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
     VolDev& v = c->vol;
     std::memcpy(c->bounds, bounds, sizeof c->bounds);
     c->voxel_size = delta[0] * delta[1] * delta[2];
-    int pad[3] = {0, 0, 0};
-    if (const char* e = std::getenv("DMF_PAD")) std::sscanf(e, "%d,%d", &pad[1], &pad[2]);      // experiment: extra row / plane padding
-    if ((double)(dim[0] + 1) * (dim[1] + 1 + pad[1]) * (dim[2] + 1 + pad[2]) >= 4294967296.0) return fail("volume %dx%dx%d too large for the 32-bit linear voxel index", dim[0], dim[1], dim[2]);
+    if ((double)(dim[0] + 1) * (dim[1] + 1) * (dim[2] + 1) >= 4294967296.0) return fail("volume %dx%dx%d too large for the 32-bit linear voxel index", dim[0], dim[1], dim[2]);
     for (int a = 0; a < 3; a++) {
         const double vmin = bounds[2 * a], vmax = bounds[2 * a + 1];
-        v.dim[a] = dim[a]; v.pdim[a] = dim[a] + 1 + pad[a]; v.mdim[a] = (dim[a] + 1 + 7) / 8;
+        v.dim[a] = dim[a]; v.pdim[a] = dim[a] + 1; v.mdim[a] = (dim[a] + 1 + 7) / 8;
         v.vmin[a] = vmin; v.delta[a] = delta[a];
         v.inv[a] = 1.0 / delta[a];
         v.c0[a] = -vmin * v.inv[a];

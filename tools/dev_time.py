@@ -43,4 +43,4 @@ for _ in range(steps):
     a.record(); step(); b.record(); torch.cuda.synchronize()
     ms.append(a.elapsed_time(b))
 ms.sort()
-print(f"{name} V={V} outs={outs} flags={flags} pad={os.environ.get('DMF_PAD','')}: median {ms[len(ms)//2]:.3f} ms/step  min {ms[0]:.3f}  = {ms[len(ms)//2]/V*1e3:.2f} us/view")
+print(f"{name} V={V} outs={outs} flags={flags}: median {ms[len(ms)//2]:.3f} ms/step  min {ms[0]:.3f}  = {ms[len(ms)//2]/V*1e3:.2f} us/view")
