@@ -11,8 +11,8 @@ box-shell grid (scene S512 of SURVEY 8d), zdelta = 2 mm, sparse = false, rayTrac
              and D2H of depth + points + visibility inside the timed region).
     N > 1  : one process per GPU (torchrun), views sharded by rank, grid replicated, per-view visibility
              bitsets all-gathered over NCCL every step (the exchange the set-cover consumer needs).
---impl reference times the CPU oracle port of the reference (the reference itself cannot be built here:
-no Eigen/PCL) on the host cores, same workload, bounded sample.
+--impl reference times the reference's own hot-path headers compiled against oracle/ref_shim (oracle/_ref; the
+oracle port only if that prebuilt library is missing) on the host cores, same workload, bounded sample.
 """
 from __future__ import annotations
 
@@ -400,6 +400,46 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     rv_s = float(t.item())
 
+    # ---- secondary: carve mode (DMF_FWD_CARVE, "occupied/free voxel marking"): every in-bounds sample of every ray really
+    # updates the observed-voxel bit grid, so nothing is skipped.  Device-resident, CUDA events on the bench stream.
+    # "first pass" = right after dmf_clear_observed (every new voxel costs an atomicOr), "steady" = the same views again
+    # (every sample still locates its voxel and tests its bit; a long sweep over one scene converges to this).
+    carve = None
+    if not (args.no_skip or args.two_probe) and fmt == D.GRID_BYTE:
+        cparams = ForwardParams(D.MODE_POINTS, sc.zdelta, 0, 1, fmt, D.FWD_CARVE)
+        o.visibility = d_vis.data_ptr()
+
+        def carve_step():
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            check(ctx.lib.dmf_forward_dev(ctx.h, C.byref(cparams), C.c_void_p(d_poses.data_ptr()), V, C.byref(o), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b), ctx.last_hot_kernel_ms()
+
+        carve_step()                                  # warm-up (allocates and zeroes the observed grid)
+        ctx.clear_observed(); ctx.reset_counters()
+        first_ms, first_hot = carve_step()
+        inb_per_step = ctx.counters()["inbounds"]
+        n_c = max(3, min(args.steps, 10))
+        steady = [carve_step() for _ in range(n_c)]
+        steady_ms, steady_hot = float(np.mean([x[0] for x in steady])), float(np.mean([x[1] for x in steady]))
+        oc = ctx.observed_counts()
+        tt = torch.tensor([first_ms, steady_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        first_ms, steady_ms = (float(x) for x in tt.tolist())
+        # algorithmic bytes per launch (carve mode): 1 B occupancy read + 1/8 B observed-bit write per in-bounds
+        # sample, + the per-ray and per-view outputs as above
+        c_bytes = inb_per_step * 1.125 + V * H * W * 24 + V * (vw * 8 + 48)
+        carve = {"what": "same views with DMF_FWD_CARVE: k_forward_line finds the hit, carve_on_line marks the voxel of every visited in-bounds sample in the observed bit grid",
+                 "voxel_updates_per_step": inb_per_step, "first_pass_ms": first_ms, "steady_ms_per_step": steady_ms,
+                 "voxel_updates_per_s_first_pass": inb_per_step * world / (first_ms * 1e-3), "voxel_updates_per_s": inb_per_step * world / (steady_ms * 1e-3),
+                 "rays_per_s": V * H * W * world / (steady_ms * 1e-3), "kernel_ms_first_pass": first_hot, "kernel_ms": steady_hot,
+                 "observed_voxels": oc["observed"], "free_voxels": oc["free"], "hit_voxels": oc["hit"],
+                 "roofline": {"bound": "hbm", "algorithmic_bytes_per_launch": c_bytes, "achieved": c_bytes / (steady_hot * 1e-3) / 1e9,
+                              "frac": c_bytes / (steady_hot * 1e-3) / 1e9 / measured_peak()[0], "unit": "GB/s",
+                              "note": "1 B occupancy read + 1/8 B observed-bit write per in-bounds sample + 24 B per ray + bitset/pose per view"}}
+
     # ---- single-view calls, the way the reference's drivers use the engine (one pose per call, id list returned) ----
     single = None
     if rank == 0:
@@ -442,7 +482,7 @@ def run_b200(args):
                          "traffic_source": None if not traffic else traffic.get("source"),
                          "peak_source": peak_src, "kernel": "k_forward" if args.no_skip else (("k_forward_dist" if args.two_probe else "k_forward_line") if fmt == D.GRID_BYTE else "k_forward_skip"),
                          "achieved_dram": None if not traffic else traffic.get("dram_bytes_per_view", 0) * V / (hot * 1e-3) / 1e9, "kernel_ms": hot, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "algorithmic bytes are SURVEY 8(d)'s reference-equivalent ones (1 B per in-bounds sample of the reference + the per-ray and per-view outputs); the kernel proves ~98 % of those samples empty from one distance byte each without touching memory, so frac can exceed 1 and is not an HBM utilisation: achieved_dram (measured DRAM bytes / kernel time) is. The kernel is issue-bound (ncu issue-active ~77 %), see DESIGN.md section 5"},
+                         "note": "algorithmic bytes are SURVEY 8(d)'s reference-equivalent ones (1 B per in-bounds sample of the reference + the per-ray and per-view outputs); the kernel proves ~98 % of those samples empty from one distance byte each without touching memory, so frac can exceed 1 and is not an HBM utilisation: achieved_dram (measured DRAM bytes / kernel time) is. The kernel is issue-bound (ncu issue-active ~86 %), see DESIGN.md section 5"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_run": same, "result": "depth_mm + visibility + found_any per view",
                     "with_points": {"value": e2e_pts_value, "d2h_bytes_per_step": d2h + V * H * W * 12, "ms_per_step": 1e3 * e2e_pts_s / e2e_pts_steps},
@@ -453,6 +493,7 @@ def run_b200(args):
             "reverse_sweep": {"what": "reverseRayTraceFast over the same views via dmf_reverse (host poses in, visibility bitsets out)",
                               "views_per_s": rv_steps * V * world / rv_s, "voxel_rays_per_s": rv_steps * V * world * n_occ / rv_s,
                               "ms_per_step": 1e3 * rv_s / rv_steps, "kernel_ms_per_step": rv_hot},
+            "carve": carve,
             "single_view_calls": single,
             "clocks": clocks,
             "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,

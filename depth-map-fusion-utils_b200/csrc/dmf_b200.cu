@@ -182,6 +182,7 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
     v.noff = c->d_noff.as<unsigned>(); v.normals = c->d_normals.as<float>(); v.occ_ids = c->d_occ_ids.as<u64>();
     v.bytes = nullptr; v.n_occ = (int)n_occ;
     c->bytes_built = false;
+    c->n_grid_words = nwords; c->observed_ready = false;     // a new volume starts unobserved
     c->vol_set = true;
     // float-accumulated axes of the whole-grid loops (RayTracingEngine.hpp:54-56, :509-511)
     for (int a = 0; a < 3; a++) {
@@ -201,6 +202,25 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
         DMF_CUDA(cudaStreamSynchronize(st));
     }
     return 0;
+}
+
+// carve mode: the observed-voxel bit grid, allocated and zeroed on first use (and again after every volume upload)
+int ensure_observed(dmf_ctx* c, cudaStream_t st) {
+    if (c->observed_ready) return 0;
+    DMF_TRY(c->d_observed.reserve(std::max<size_t>(c->n_grid_words, 8) * 4));
+    DMF_CUDA(cudaMemsetAsync(c->d_observed.p, 0, std::max<size_t>(c->n_grid_words, 8) * 4, st));
+    c->observed_ready = true;
+    return 0;
+}
+
+__global__ void k_observed_counts(const unsigned* __restrict__ obs, const unsigned* __restrict__ occ, size_t n_words, u64* out) {
+    unsigned long long n_obs = 0, n_hit = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned o = obs[i];
+        n_obs += (unsigned)__popc(o); n_hit += (unsigned)__popc(o & __ldg(occ + i));
+    }
+    for (int s = 16; s > 0; s >>= 1) { n_obs += __shfl_down_sync(0xffffffffu, n_obs, s); n_hit += __shfl_down_sync(0xffffffffu, n_hit, s); }
+    if ((threadIdx.x & 31) == 0) { if (n_obs) atomicAdd(out, n_obs); if (n_hit) atomicAdd(out + 1, n_hit); }
 }
 
 // DMF_GRID_BYTE: the per-voxel Chebyshev distance bytes (dmf_distance.cuh), built on first use
@@ -251,7 +271,19 @@ int ensure_tables(dmf_ctx* c, int z0, int zdelta, int cstride, int rstride, cuda
 
 template <int MODE>
 void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, bool two_probe, dim3 grid, cudaStream_t st) {
-    if (skip) {
+    if (a.observed) {
+        // carve mode: every sample has to be located, so none can be skipped; with the distance bytes the line-first kernel
+        // finds the hit and then locates the samples on the line (carve_on_line), otherwise the brute-force march records them
+        if constexpr (MODE != 4) {
+            if (skip && fmt == DMF_GRID_BYTE && !two_probe) {
+                dim3 g((a.Wc + SKIP_TILE_W - 1) / SKIP_TILE_W, (a.Hc + SKIP_TILE_H - 1) / SKIP_TILE_H, grid.z);
+                const bool exact = a.vol.err32[0] == 0.0f && a.vol.err32[1] == 0.0f && a.vol.err32[2] == 0.0f;
+                if (exact) k_forward_line<MODE, true, true><<<g, SKIP_THREADS, 0, st>>>(a);
+                else k_forward_line<MODE, false, true><<<g, SKIP_THREADS, 0, st>>>(a);
+            } else if (fmt == DMF_GRID_BYTE) k_forward<MODE, 1, true><<<grid, FWD_THREADS, 0, st>>>(a);
+            else k_forward<MODE, 0, true><<<grid, FWD_THREADS, 0, st>>>(a);
+        }
+    } else if (skip) {
         dim3 g((a.Wc + SKIP_TILE_W - 1) / SKIP_TILE_W, (a.Hc + SKIP_TILE_H - 1) / SKIP_TILE_H, grid.z);
         const bool exact = a.vol.err32[0] == 0.0f && a.vol.err32[1] == 0.0f && a.vol.err32[2] == 0.0f;
         if (fmt == DMF_GRID_BYTE) {
@@ -259,13 +291,13 @@ void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, bool two_probe, di
                 if (exact) k_forward_dist<MODE, true><<<g, SKIP_THREADS, 0, st>>>(a);
                 else k_forward_dist<MODE, false><<<g, SKIP_THREADS, 0, st>>>(a);
             } else {
-                if (exact) k_forward_line<MODE, true><<<g, SKIP_THREADS, 0, st>>>(a);
-                else k_forward_line<MODE, false><<<g, SKIP_THREADS, 0, st>>>(a);
+                if (exact) k_forward_line<MODE, true, false><<<g, SKIP_THREADS, 0, st>>>(a);
+                else k_forward_line<MODE, false, false><<<g, SKIP_THREADS, 0, st>>>(a);
             }
         } else k_forward_skip<MODE, 0><<<g, SKIP_THREADS, 0, st>>>(a);
     } else {
-        if (fmt == DMF_GRID_BYTE) k_forward<MODE, 1><<<grid, FWD_THREADS, 0, st>>>(a);
-        else k_forward<MODE, 0><<<grid, FWD_THREADS, 0, st>>>(a);
+        if (fmt == DMF_GRID_BYTE) k_forward<MODE, 1, false><<<grid, FWD_THREADS, 0, st>>>(a);
+        else k_forward<MODE, 0, false><<<grid, FWD_THREADS, 0, st>>>(a);
     }
 }
 
@@ -276,6 +308,8 @@ int plan_forward(dmf_ctx* c, const dmf_forward_params* p, FwdPlan& pl) {
     if (p->mode < 0 || p->mode > 4) return fail("bad mode %d", p->mode);
     if (p->zdelta < 1) return fail("zdelta must be >= 1 (the reference loops forever on zdelta <= 0)");
     if (p->grid_format != DMF_GRID_BIT && p->grid_format != DMF_GRID_BYTE) return fail("bad grid_format %d", p->grid_format);
+    if ((p->flags & DMF_FWD_CARVE) && p->mode == DMF_MODE_MINIMUM)
+        return fail("DMF_FWD_CARVE is not defined for MINIMUM mode (rayTraceAndGetMinimum returns mid-plane: the samples it visits depend on the pixel order)");
     pl.z0 = p->mode == DMF_MODE_MINIMUM ? 5 : 10;                                        // :239 vs :280,:327,:396,:461
     pl.cstride = pl.rstride = p->sparse ? (p->mode == DMF_MODE_MINIMUM ? 10 : 5) : 1;    // :236-237 vs :277-278
     return 0;
@@ -295,6 +329,8 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     if (n_views > 65535) return fail("at most 65535 views per launch (got %d)", n_views);
     DMF_TRY(ensure_tables(c, pl.z0, p->zdelta, pl.cstride, pl.rstride, st));
     if (p->grid_format == DMF_GRID_BYTE) DMF_TRY(ensure_bytes(c, st));
+    const bool carve = (p->flags & DMF_FWD_CARVE) != 0;
+    if (carve) DMF_TRY(ensure_observed(c, st));
     const size_t HW = (size_t)c->H * c->W;
     const size_t vis_words64 = (c->n_occ + 63) / 64;
     const bool sparse_lattice = pl.cstride > 1;
@@ -323,6 +359,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     a.first_key = first_key; a.ray_key = ray_key; a.ray_occ = ray_occ;
     a.first_view = c->d_first_view.as<int>(); a.good_bits = c->d_good_bits.as<unsigned>(); a.view_mark = c->d_view_mark.as<int>();
     a.counters = c->d_counters.as<u64>();
+    a.observed = carve ? c->d_observed.as<unsigned>() : nullptr;
     a.dcx = c->d_dcx.as<float>(); a.dcy = c->d_dcy.as<float>(); a.clearance = c->d_clearance.as<float>();
     a.dcx_max = c->dcx_max; a.dcy_max = c->dcy_max;
     DMF_TRY(c->d_kstart.reserve((size_t)n_views * 8));
@@ -432,7 +469,7 @@ void dmf_destroy(dmf_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->d_bricks, &c->d_macro, &c->d_clearance, &c->d_dcx, &c->d_dcy, &c->d_prefix, &c->d_rank2occ, &c->d_bytes, &c->d_noff, &c->d_normals, &c->d_occ_ids, &c->d_centroid_hash,
-                      &c->d_view_mark, &c->d_good_bits, &c->d_first_view, &c->d_axis[0], &c->d_axis[1], &c->d_axis[2], &c->d_xtab, &c->d_ytab, &c->d_ztab, &c->d_kstart,
+                      &c->d_view_mark, &c->d_good_bits, &c->d_first_view, &c->d_observed, &c->d_axis[0], &c->d_axis[1], &c->d_axis[2], &c->d_xtab, &c->d_ytab, &c->d_ztab, &c->d_kstart,
                       &c->d_poses[0], &c->d_poses[1], &c->d_inv_poses, &c->d_first_key, &c->d_ray_key, &c->d_ray_occ, &c->d_tmp_a, &c->d_tmp_b,
                       &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters};
     for (auto* b : bufs) b->release();
@@ -533,6 +570,57 @@ int dmf_upload_marks(dmf_ctx* c, const int32_t* view, const uint8_t* good) {
     for (size_t i = 0; i < c->n_occ; i++) if (good[i]) bits[i >> 5] |= 1u << (i & 31);
     DMF_CUDA(cudaMemcpy(c->d_view_mark.p, view, c->n_occ * 4, cudaMemcpyHostToDevice));
     DMF_CUDA(cudaMemcpy(c->d_good_bits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ---- carve mode: the observed-voxel bit grid ------------------------------------------------------------------
+size_t dmf_observed_words(dmf_ctx* c) { return c && c->vol_set ? c->n_grid_words : 0; }
+
+int dmf_clear_observed(dmf_ctx* c) {
+    if (!c || !c->vol_set) return fail("no volume uploaded");
+    DMF_CUDA(cudaSetDevice(c->device));
+    DMF_CUDA(cudaDeviceSynchronize());
+    c->observed_ready = false;
+    DMF_TRY(ensure_observed(c, c->stream));
+    DMF_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int dmf_download_observed(dmf_ctx* c, uint32_t* words) {
+    if (!c || !c->vol_set) return fail("no volume uploaded");
+    if (!words) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    DMF_TRY(ensure_observed(c, c->stream));
+    DMF_CUDA(cudaDeviceSynchronize());
+    DMF_CUDA(cudaMemcpy(words, c->d_observed.p, c->n_grid_words * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dmf_observed_dev(dmf_ctx* c, void** d_words) {
+    if (!c || !c->vol_set) return fail("no volume uploaded");
+    if (!d_words) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    DMF_TRY(ensure_observed(c, c->stream));
+    DMF_CUDA(cudaStreamSynchronize(c->stream));
+    *d_words = c->d_observed.p;
+    return 0;
+}
+
+int dmf_observed_counts(dmf_ctx* c, uint64_t out[3]) {
+    if (!c || !c->vol_set) return fail("no volume uploaded");
+    if (!out) return fail("null argument");
+    DMF_CUDA(cudaSetDevice(c->device));
+    DMF_TRY(ensure_observed(c, c->stream));
+    DMF_CUDA(cudaDeviceSynchronize());
+    DMF_TRY(c->d_misc[3].reserve(16));
+    DMF_CUDA(cudaMemsetAsync(c->d_misc[3].p, 0, 16, c->stream));
+    k_observed_counts<<<blocks_for(c->n_grid_words, 256), 256, 0, c->stream>>>(c->d_observed.as<unsigned>(), c->d_bricks.as<unsigned>(), c->n_grid_words, c->d_misc[3].as<u64>());
+    c->launches++;
+    DMF_CUDA(cudaGetLastError());
+    uint64_t h[2];
+    DMF_CUDA(cudaMemcpyAsync(h, c->d_misc[3].p, 16, cudaMemcpyDeviceToHost, c->stream));
+    DMF_CUDA(cudaStreamSynchronize(c->stream));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[0] - h[1];
     return 0;
 }
 

@@ -44,6 +44,9 @@ struct FwdArgs {
     int* first_view;                   // [n_occ] min batch-local view index that hit the voxel (INT_MAX-initialised)
     unsigned* good_bits;               // [ceil(n_occ/32)]
     int* view_mark;                    // [n_occ]
+    // carve mode (DMF_FWD_CARVE): bit grid over the padded index space, same layout as vol.bits; every in-bounds sample a ray
+    // visits up to and including its first hit sets the bit of the voxel it falls in ("observed": free where not occupied)
+    unsigned* observed;
     u64* counters;                     // DMF_CNT_*
 };
 
@@ -167,8 +170,8 @@ constexpr int FWD_THREADS = 256;      // 8 warps: 4 across x 2 down, each warp a
 constexpr int FWD_TILE_W = 32, FWD_TILE_H = 8;
 constexpr int FWD_CHUNK = 32;         // z-steps staged in shared memory per round
 
-// MODE: DMF_MODE_*, FMT: DMF_GRID_*
-template <int MODE, int FMT>
+// MODE: DMF_MODE_*, FMT: DMF_GRID_*, CARVE: also record every visited in-bounds sample's voxel in a.observed
+template <int MODE, int FMT, bool CARVE>
 __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
     __shared__ float sx[FWD_CHUNK][FWD_TILE_W];
     __shared__ float sy[FWD_CHUNK][FWD_TILE_H];
@@ -254,6 +257,13 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
                 }
                 // voxels_[xid][yid][zid] != nullptr: indices are in [0,dim] here, the padded grid covers index == dim
                 const unsigned idx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+                if (CARVE) {
+                    // read first: after the first few views of a sweep nearly every bit is already set, the word sits in
+                    // L1/L2, and a stale 0 only costs a redundant (idempotent) atomicOr
+                    unsigned* const ow = a.observed + (idx >> 5);
+                    const unsigned om = 1u << (idx & 31);
+                    if (!(*ow & om)) atomicOr(ow, om);
+                }
                 const bool occ_here = FMT == 0 ? ((__ldg(gbits + (idx >> 5)) >> (idx & 31)) & 1u) != 0u : __ldg(gbytes + idx) == 0;
                 if (occ_here) {
                     hit_k = k0 + kk; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz;
@@ -655,8 +665,62 @@ __device__ __forceinline__ float4 lds_f4_volatile(unsigned smem_addr) {
 }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-template <int MODE, bool EXACT>
-__global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(const FwdArgs a) {
+// ---- carve mode on the line (DMF_FWD_CARVE) -----------------------------------------------------------------------
+// Every in-bounds sample a ray visits, up to and including its first hit, sets the bit of its voxel in a.observed.  Which
+// voxel that is has to be known for EVERY sample, so nothing can be skipped -- but almost nothing has to be evaluated the
+// reference's way either: for k in [kin, kout] the sample is in bounds (the line is >= 0.25 voxel inside, eps_q <= 0.1) and
+// lies within eps_q(view) of the line point Q(k); if Q(k) is at least e_safe = eps_q(view) + 2^-10 away from every face of
+// its voxel, the sample is in that same voxel (the argument k_forward_line uses for its d == 1 probes).  Only samples whose
+// line point is closer than that to a face, and those in the thin bands around the volume boundary, take the exact path
+// (tables, the reference's float expression, validPoints, exact index).  Runs after the march, when hit_k is known.
+__device__ __forceinline__ void observe_voxel(unsigned* __restrict__ obs, unsigned idx) {
+    // read first: after the first few views of a sweep nearly every bit is already set and the word sits in L1/L2; a stale 0
+    // only costs a redundant (idempotent) atomicOr
+    unsigned* const w = obs + (idx >> 5);
+    const unsigned m = 1u << (idx & 31);
+    if (!(*w & m)) atomicOr(w, m);
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void carve_on_line(const FwdArgs& a, unsigned sp, int ci, int ri, int k_first, int k_last, int kin, int kout,
+                                           float qa0, float qa1, float qa2, float qb0, float qb1, float qb2, float esafe) {
+    const VolDev& v = a.vol;
+    const float kM = 12582912.0f;
+    const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
+    const unsigned pnyz = pny * pnz;
+    const unsigned bias = 0x4B400000u * (pnyz + pnz + 1u);
+    const unsigned last = pnyz * (unsigned)v.pdim[0] - 1u;
+    const float hi_safe = 1.0f - esafe;
+    unsigned* const obs = a.observed;
+    unsigned dummy0 = 0, dummy1 = 0;
+    for (int k = k_first; k <= k_last; k++) {
+        if (k >= kin && k <= kout) {
+            const float kf = (float)k;
+            const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
+            const float s0 = __fadd_rd(q0, kM), s1 = __fadd_rd(q1, kM), s2 = __fadd_rd(q2, kM);
+            const float f0 = q0 - (s0 - kM), f1 = q1 - (s1 - kM), f2 = q2 - (s2 - kM);
+            if (fminf(f0, fminf(f1, f2)) >= esafe && fmaxf(f0, fmaxf(f1, f2)) <= hi_safe) {
+                const unsigned idx = (unsigned)__float_as_int(s0) * pnyz + ((unsigned)__float_as_int(s1) * pnz + ((unsigned)__float_as_int(s2) - bias));
+                observe_voxel(obs, min(idx, last));
+                continue;
+            }
+        }
+        const float xf = __ldg(a.xtab + ((unsigned)k * (unsigned)a.Wc + (unsigned)ci)), yf = __ldg(a.ytab + ((unsigned)k * (unsigned)a.Hc + (unsigned)ri));
+        const float zf = __ldg(a.ztab + k);
+        const float4 r0 = lds_f4_volatile(sp), r1 = lds_f4_volatile(sp + 16), r2 = lds_f4_volatile(sp + 32);
+        const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, xf), __fmul_rn(r0.y, yf)), __fmul_rn(r0.z, zf)), r0.w);
+        const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, xf), __fmul_rn(r1.y, yf)), __fmul_rn(r1.z, zf)), r1.w);
+        const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, xf), __fmul_rn(r2.y, yf)), __fmul_rn(r2.z, zf)), r2.w);
+        if (!(px > v.lo[0] && px < v.hi[0] && py > v.lo[1] && py < v.hi[1] && pz > v.lo[2] && pz < v.hi[2])) continue;   // validPoints failed
+        int ix, iy, iz;
+        const unsigned idx = probe_index<EXACT>(v, px, py, pz, v.inv32[0], v.inv32[1], v.inv32[2], v.c32[0], v.c32[1], v.c32[2],
+                                                v.err32[0], v.err32[1], v.err32[2], pny, pnz, ix, iy, iz, dummy0, dummy1);
+        observe_voxel(obs, idx);
+    }
+}
+
+template <int MODE, bool EXACT, bool CARVE>
+__global__ void __launch_bounds__(SKIP_THREADS, CARVE ? 8 : LINE_MIN_BLOCKS) k_forward_line(const FwdArgs a) {
     __shared__ __align__(16) float s_pose[12];
     __shared__ float s_adv[256];
     __shared__ int s_qbmax;
@@ -682,6 +746,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
     // ---- per ray: the line and the sample intervals ----
     float qa0, qa1, qa2, qb0, qb1, qb2;
     int k = 0, kin = 1, kout = 0, s_end = S;
+    int k_slab = 0;                                   // CARVE: first sample that can be in bounds (before the view-wide k0 skip)
     unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
     const int ks = __ldg(a.kstart + view);            // -1: no skipping for this view; else leading probes no ray can hit
     {
@@ -709,9 +774,10 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
             }
             // the t's carry a few ulps of relative error: one sample of guard on each end (|t| that matter are < 2^20)
             const float Sf = (float)S;
-            if (!(to0 <= to1)) k = S;                                                // never inside: every sample fails validPoints
+            if (!(to0 <= to1)) { k = S; if (CARVE) k_slab = S; }                     // never inside: every sample fails validPoints
             else {
                 k = (int)fminf(fmaxf(floorf(to0) - 1.0f, 0.0f), Sf);
+                if (CARVE) k_slab = k;
                 s_end = (int)fminf(fmaxf(ceilf(to1) + 2.0f, 0.0f), Sf);
                 if (ti0 <= ti1) {
                     kin = (int)fminf(fmaxf(ceilf(ti0) + 1.0f, 0.0f), Sf);
@@ -817,6 +883,10 @@ __global__ void __launch_bounds__(SKIP_THREADS, LINE_MIN_BLOCKS) k_forward_line(
 #endif
         if (de == 0u) { hit_k = k; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz; k++; break; }
         k++;
+    }
+    if (CARVE && MODE != 4 && active) {
+        const int k_last = hit_k >= 0 ? hit_k : s_end - 1;                          // samples >= s_end are provably outside the volume
+        carve_on_line<EXACT>(a, sp, ci, ri, k_slab, k_last, kin, kout, qa0, qa1, qa2, qb0, qb1, qb2, s_esafe);
     }
     const unsigned n_samples = active ? (unsigned)((hit_k >= 0 || stop || (MODE == 4 && k < s_end)) ? min(k, S) : S) : 0u;
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;

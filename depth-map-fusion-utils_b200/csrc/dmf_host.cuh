@@ -138,6 +138,8 @@ struct dmf_ctx {
     bool bytes_built = false;
     int reverse_format = DMF_GRID_BYTE;   // grid the reverse march probes (dmf_set_reverse_format)
     dmf::DevBuf d_view_mark, d_good_bits, d_first_view;
+    // carve mode (DMF_FWD_CARVE): observed-voxel bit grid, same layout and word count as the occupancy bit grid; zeroed on first use
+    dmf::DevBuf d_observed; size_t n_grid_words = 0; bool observed_ready = false;
     // reverseRayTrace / rayTraceVolume float-accumulated axes
     dmf::DevBuf d_axis[3]; int n_axis[3] = {0, 0, 0};
     // projectPoint tables

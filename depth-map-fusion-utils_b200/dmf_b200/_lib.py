@@ -57,6 +57,11 @@ SYMBOLS = {
     "dmf_download_marks": (C.c_int, [vp, i32p, u8p]),
     "dmf_upload_marks": (C.c_int, [vp, i32p, u8p]),
     "dmf_visibility_words": (C.c_size_t, [vp]),
+    "dmf_observed_words": (C.c_size_t, [vp]),
+    "dmf_clear_observed": (C.c_int, [vp]),
+    "dmf_download_observed": (C.c_int, [vp, u32p]),
+    "dmf_observed_dev": (C.c_int, [vp, C.POINTER(vp)]),
+    "dmf_observed_counts": (C.c_int, [vp, u64p]),
     "dmf_forward": (C.c_int, [vp, C.POINTER(ForwardParams), fp, C.c_int, C.POINTER(ForwardOut)]),
     "dmf_forward_dev": (C.c_int, [vp, C.POINTER(ForwardParams), vp, C.c_int, C.POINTER(ForwardOut), vp]),
     "dmf_reverse": (C.c_int, [vp, C.c_int, C.c_int, fp, C.c_int, C.POINTER(ReverseOut)]),

@@ -24,6 +24,7 @@ from ._lib import DmfError, ForwardOut, ForwardParams, ReverseOut, check
 
 MODE_POINTS, MODE_GOOD_POINTS, MODE_CLASSIFY, MODE_MARK, MODE_MINIMUM = range(5)
 GRID_BIT, GRID_BYTE = 0, 1
+FWD_NO_SKIP, FWD_TWO_PROBE, FWD_CARVE = 1, 2, 4
 NO_VOXEL = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
@@ -95,6 +96,26 @@ class Context:
 
     def synchronize(self):
         check(self.lib.dmf_synchronize(self.h))
+
+    # ---- carve mode (DMF_FWD_CARVE): the observed-voxel bit grid -------------------------------------------
+    def clear_observed(self):
+        check(self.lib.dmf_clear_observed(self.h))
+
+    def observed_words(self) -> np.ndarray:
+        """uint32 words over the padded index space (bit index = (x*(dim_y+1) + y)*(dim_z+1) + z)."""
+        out = np.zeros(self.lib.dmf_observed_words(self.h), np.uint32)
+        check(self.lib.dmf_download_observed(self.h, _ptr(out, C.c_uint32)))
+        return out
+
+    def observed_dev_ptr(self) -> int:
+        p = C.c_void_p()
+        check(self.lib.dmf_observed_dev(self.h, C.byref(p)))
+        return int(p.value)
+
+    def observed_counts(self) -> dict:
+        out = np.zeros(3, np.uint64)
+        check(self.lib.dmf_observed_counts(self.h, _ptr(out, C.c_uint64)))
+        return dict(observed=int(out[0]), hit=int(out[1]), free=int(out[2]))
 
 
 class Camera:
@@ -231,7 +252,9 @@ class RayTracingEngine:
 
     # ---- batched forward: n views in one call ---------------------------------------------------------------
     def forward_views(self, volume: VoxelVolume, poses, mode: int, zdelta: int, sparse: bool, view_id0: int = 1,
-                      want=("depth", "points", "voxel", "visibility", "ids")) -> dict:
+                      want=("depth", "points", "voxel", "visibility", "ids"), carve: bool = False) -> dict:
+        """carve=True (DMF_FWD_CARVE): every visited in-bounds sample also marks its voxel in the context's observed grid
+        (Context.observed_words / observed_counts)."""
         self._prepare(volume)
         poses = _poses12(poses)
         n = len(poses)
@@ -257,7 +280,7 @@ class RayTracingEngine:
             cap = n * min(len(volume.occupied_cells_), H * W) + 1
             ids, offs = np.zeros(cap, np.uint64), np.zeros(n + 1, np.int64)
             o.ids, o.ids_offsets, o.ids_capacity = _vptr(ids), _vptr(offs), cap
-        p = ForwardParams(mode, int(zdelta), int(bool(sparse)), int(view_id0), self.grid_format, 0 if self.skip_empty else 1)
+        p = ForwardParams(mode, int(zdelta), int(bool(sparse)), int(view_id0), self.grid_format, (0 if self.skip_empty else FWD_NO_SKIP) | (FWD_CARVE if carve else 0))
         check(self.ctx.lib.dmf_forward(self.ctx.h, C.byref(p), _ptr(poses, C.c_float), n, C.byref(o)))
         if ids is not None:
             res["ids"] = [ids[offs[i]:offs[i + 1]].copy() for i in range(n)]

@@ -108,6 +108,16 @@ typedef struct {
  * per iteration) instead of the line-first one.  Same results; kept as the A/B baseline for profiles/. */
 #define DMF_FWD_TWO_PROBE 2
 
+/* Carve mode -- "occupied/free voxel marking".  NOT in the reference (it never records free space); defined by and pinned to
+ * oracle/dmf_oracle.hpp only (PixelOut::observed): every sample that passes validPoints (Volume.hpp:230-233) and is visited
+ * by its ray up to and including the ray's first hit -- exactly the samples DMF_CNT_INBOUNDS counts -- sets the bit of the
+ * voxel getVoxel (Volume.hpp:150-156) puts it in, in a per-context "observed" bit grid that accumulates over views and calls
+ * until dmf_clear_observed / a new volume.  observed & ~occupied = voxels seen free; observed & occupied = voxels hit.
+ * Every sample has to be located, so none is skipped: with DMF_GRID_BYTE the line-first kernel finds the hit and then places
+ * the samples on the line (exact evaluation only near voxel faces and the volume boundary); DMF_FWD_NO_SKIP or DMF_GRID_BIT
+ * select the brute-force march that evaluates every sample the reference's way.  Not available in MINIMUM mode. */
+#define DMF_FWD_CARVE 4
+
 /* Per-view outputs; any pointer may be NULL.  For the *_dev entry point these are device pointers. */
 typedef struct {
     int32_t*  depth_mm;    /* [n_views][H][W]    z_depth (mm) of each pixel's first occupied sample, -1 = none/not cast */
@@ -124,6 +134,14 @@ typedef struct {
 } dmf_forward_out;
 
 size_t dmf_visibility_words(dmf_ctx* ctx);   /* ceil(n_occ/64) */
+
+/* The observed bit grid of carve mode: uint32 words over the PADDED index space [0,dim_x] x [0,dim_y] x [0,dim_z]
+ * (z fastest, like voxels_[x][y][z]): bit index = (x*(dim_y+1) + y)*(dim_z+1) + z, bit i of word w = index 32w+i. */
+size_t dmf_observed_words(dmf_ctx* ctx);                       /* number of uint32 words (a multiple of 8)                  */
+int dmf_clear_observed(dmf_ctx* ctx);
+int dmf_download_observed(dmf_ctx* ctx, uint32_t* words /* dmf_observed_words */);
+int dmf_observed_dev(dmf_ctx* ctx, void** d_words);           /* device pointer (for OR-reducing the grids of several GPUs) */
+int dmf_observed_counts(dmf_ctx* ctx, uint64_t out[3]);       /* observed, observed & occupied (hit), observed & ~occupied (free) */
 
 /* Host-buffer call: copies poses H2D, casts all views, copies the requested outputs D2H, synchronises.
  * Replaces n_views consecutive calls of one forward routine (RayTracingEngine.hpp:229,268,311,377,447). */

@@ -292,6 +292,11 @@ struct PixelOut {                  // optional per-pixel outputs (size H*W each)
     int32_t* depth = nullptr;      // first-hit z_depth in mm, -1 = no hit / not cast
     float* point = nullptr;        // world-space sample point of the first hit (x,y,z), untouched if none
     u64* voxel = nullptr;          // voxel id of the first hit
+    // Carve mode -- an EXTENSION, not in the reference (which never records free space); this restatement is its only
+    // definition: every sample that passes validPoints and is visited by its ray up to and including the first hit (the
+    // samples `Counters::inbounds` counts) sets the bit of the voxel getVoxel (Volume.hpp:150-156) puts it in.  uint32 words
+    // over the padded index space [0,xdim] x [0,ydim] x [0,zdim], bit index = (x*(ydim+1) + y)*(zdim+1) + z; OR-accumulated.
+    uint32_t* observed = nullptr;
 };
 
 using IdList = std::pair<bool, std::vector<u64>>;
@@ -356,6 +361,10 @@ public:
                     double x,y,z; int xid,yid,zid;
                     if (!probe(vol,T,r,c,z_depth,x,y,z,xid,yid,zid)) continue;
                     if (cnt) cnt->inbounds++;
+                    if (po && po->observed && mode != MINIMUM) {
+                        size_t idx = ((size_t)xid*(size_t)(vol.ydim_+1) + (size_t)yid)*(size_t)(vol.zdim_+1) + (size_t)zid;
+                        po->observed[idx >> 5] |= 1u << (idx & 31);
+                    }
                     Voxel* voxel = vol.at(xid,yid,zid);
                     if (voxel == nullptr) continue;
                     if (mode == MINIMUM) {                                   // :256-259

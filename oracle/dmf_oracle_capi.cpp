@@ -80,6 +80,23 @@ long orc_forward(void* h, const float* K, int H, int W, const float* pose12, int
     return n;
 }
 
+// Carve-mode extension (PixelOut::observed; not in the reference): runs one forward routine and ORs the voxels of all visited
+// in-bounds samples into `observed` (uint32 words over the padded index space, caller-zeroed or accumulated across calls).
+// Returns the number of words the grid needs; with observed == NULL nothing is run.
+long orc_forward_observed(void* h, const float* K, int H, int W, const float* pose12, int mode, int zdelta, int sparse, int view,
+                          unsigned* observed, long long* counters) {
+    auto* vol = (VoxelVolume*)h;
+    size_t nbits = (size_t)(vol->xdim_+1)*(size_t)(vol->ydim_+1)*(size_t)(vol->zdim_+1);
+    long nwords = (long)(((nbits + 31) / 32 + 7) / 8 * 8);
+    if (!observed) return nwords;
+    RayTracingEngine eng(cam_from(K,H,W));
+    Counters c; PixelOut po; po.observed = observed;
+    int md = -1;
+    eng.forward((RayTracingEngine::Mode)mode, *vol, pose_from12(pose12), zdelta, sparse != 0, view, &md, counters ? &c : nullptr, &po);
+    put_counters(c, counters);
+    return nwords;
+}
+
 // reverseRayTraceFast (fast=1) / reverseRayTrace (fast=0).  visible_flags (n_occ bytes, fast only):
 // bit0 = not occluded, bit1 = emitted as good.
 long orc_reverse(void* h, const float* K, int H, int W, const float* pose12, int fast, int viz, int dead_work,

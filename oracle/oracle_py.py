@@ -53,6 +53,8 @@ def lib():
         L.orc_forward.restype = C.c_long
         L.orc_forward.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                   ip, fp, u64p, u64p, C.c_long, ip, ip, llp]
+        L.orc_forward_observed.restype = C.c_long
+        L.orc_forward_observed.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint), llp]
         L.orc_reverse.restype = C.c_long
         L.orc_reverse.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int,
                                   u64p, C.c_long, ip, ucp, llp]
@@ -152,6 +154,21 @@ def forward(vol: Volume, K, H, W, pose12, mode, zdelta, sparse, view=1, want_pix
                           _p(ids, C.c_ulonglong), len(ids), C.byref(found), C.byref(md), _p(cnt, C.c_longlong))
     return dict(found_any=bool(found.value), ids=ids[:n].copy(), min_depth=md.value, depth=depth, points=points,
                 voxel=voxel, counters=None if cnt is None else dict(zip(("samples", "inbounds", "hits", "oob", "runaway"), cnt.tolist())))
+
+
+def forward_observed(vol: Volume, K, H, W, pose12, mode, zdelta, sparse, view=1, observed=None):
+    """Carve-mode extension (PixelOut::observed): returns (observed uint32 words over the padded index space, counters);
+    pass the previous `observed` to accumulate over views."""
+    K = np.ascontiguousarray(K, np.float32)
+    pose = np.ascontiguousarray(pose12, np.float32).reshape(12)
+    f = lib().orc_forward_observed
+    n = f(vol.h, _p(K, C.c_float), H, W, _p(pose, C.c_float), mode, zdelta, int(sparse), view, None, None)
+    if observed is None:
+        observed = np.zeros(n, np.uint32)
+    assert observed.dtype == np.uint32 and len(observed) == n
+    cnt = np.zeros(5, np.int64)
+    f(vol.h, _p(K, C.c_float), H, W, _p(pose, C.c_float), mode, zdelta, int(sparse), view, _p(observed, C.c_uint), _p(cnt, C.c_longlong))
+    return observed, dict(zip(("samples", "inbounds", "hits", "oob", "runaway"), cnt.tolist()))
 
 
 def reverse(vol: Volume, K, H, W, pose12, fast=True, viz=False, dead_work=False):

@@ -47,3 +47,25 @@ def test_gpu_reproduces_golden(dmf, ctx, name):
     view, good = gv.marks()
     assert np.array_equal(view, g[f"{name}/classify/view"]) and np.array_equal(good, g[f"{name}/classify/good"])
     assert np.array_equal(dmf.greedySetCover(rv["visibility"], ctx), g[f"{name}/setcover"])
+
+
+@pytest.mark.parametrize("name", ["S64", "S128-odd", "S128-clutter"])
+def test_gpu_reproduces_carve_golden(dmf, ctx, name):
+    """carve mode (DMF_FWD_CARVE) against tests/golden/golden_carve_v1.npz: the observed-voxel bit grid, both device paths"""
+    g = np.load(GOLDEN)
+    gc = np.load(os.path.join(os.path.dirname(GOLDEN), "golden_carve_v1.npz"))
+    K = g["K"]; H, W = (int(v) for v in g["HW"])
+    sc = dmf.scenes.scene(name)
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+    poses = g[f"{name}/poses"]; zd = int(g[f"{name}/zdelta"])
+    for fmt, skip in ((dmf.GRID_BYTE, True), (dmf.GRID_BYTE, False), (dmf.GRID_BIT, True)):
+        eng = dmf.RayTracingEngine(dmf.Camera(K, H, W), ctx, fmt, skip_empty=skip)
+        for sparse in (0, 1):
+            gv._commit(ctx)
+            ctx.clear_observed(); ctx.reset_counters()
+            eng.forward_views(gv, poses[:1], dmf.MODE_POINTS, zd, bool(sparse), want=(), carve=True)
+            assert np.array_equal(ctx.observed_words(), gc[f"{name}/s{sparse}/view0"])
+            eng.forward_views(gv, poses[1:], dmf.MODE_POINTS, zd, bool(sparse), want=(), carve=True)
+            assert np.array_equal(ctx.observed_words(), gc[f"{name}/s{sparse}/all_views"])
+            assert ctx.counters()["inbounds"] == int(gc[f"{name}/s{sparse}/inbounds"])

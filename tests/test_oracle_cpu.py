@@ -121,3 +121,44 @@ def test_set_cover_known_answer(oracle):
     sets = [np.arange(0, 10), np.arange(5, 30), np.arange(28, 40), np.arange(0, 3)]
     sel = oracle.greedy_set_cover([s.astype(np.uint64) for s in sets])
     assert list(sel) == [1, 2, 0]    # gains 25, 10 (30..39), 5 (0..4); set 3 adds nothing
+
+
+# ---- carve mode (PixelOut::observed): an extension defined by the oracle, see oracle/dmf_oracle.hpp ------------------
+GOLDEN_CARVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_carve_v1.npz")
+
+
+def _bits(words):
+    return np.unpackbits(words.view(np.uint8), bitorder="little")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_observed_matches_golden_and_is_consistent(oracle, dmf, golden, name):
+    """the observed grid of carve mode: golden vectors, both storages, and what it must mean -- observed & occupied is the
+    set of first-hit voxels, observed popcount <= in-bounds samples, accumulation over views is a plain OR"""
+    g, gc = golden, np.load(GOLDEN_CARVE)
+    K = g["K"]; H, W = (int(v) for v in g["HW"])
+    sc = dmf.scenes.scene(name)
+    poses = g[f"{name}/poses"]; zd = int(g[f"{name}/zdelta"])
+    dims = np.asarray(sc.dims, np.int64) + 1
+    for flat in (True, False):
+        vol = oracle.volume_from_scene(sc, flat=flat)
+        occ = vol.occupied()
+        occ_idx = ((occ >> np.uint64(40)).astype(np.int64) * dims[1] + ((occ >> np.uint64(20)) & np.uint64(0xFFFFF)).astype(np.int64)) * dims[2] + (occ & np.uint64(0xFFFFF)).astype(np.int64)
+        for sparse in (0, 1):
+            obs, inb, hit_ids, singles = None, 0, set(), []
+            for i, p in enumerate(poses):
+                obs, c = oracle.forward_observed(vol, K, H, W, p, oracle.MODE_POINTS, zd, bool(sparse), observed=obs)
+                one, c1 = oracle.forward_observed(vol, K, H, W, p, oracle.MODE_POINTS, zd, bool(sparse))
+                assert c1 == c and c["inbounds"] == int(g[f"{name}/{i}/counters/s{sparse}"][1])
+                assert int(_bits(one).sum()) <= c["inbounds"]
+                singles.append(one)
+                inb += c["inbounds"]
+                hit_ids.update(int(v) for v in g[f"{name}/{i}/points/s{sparse}/ids"])
+                if i == 0:
+                    assert np.array_equal(obs, gc[f"{name}/s{sparse}/view0"])
+            assert np.array_equal(obs, gc[f"{name}/s{sparse}/all_views"]) and inb == int(gc[f"{name}/s{sparse}/inbounds"])
+            assert np.array_equal(obs, np.bitwise_or.reduce(np.stack(singles), axis=0))
+            b = _bits(obs)
+            seen_occ = occ[b[occ_idx] == 1]
+            assert set(int(v) for v in seen_occ) == hit_ids
+            assert b.sum() > len(hit_ids)           # free voxels were recorded too
