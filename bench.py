@@ -424,6 +424,18 @@ def run_b200(args):
         steady = [carve_step() for _ in range(n_c)]
         steady_ms, steady_hot = float(np.mean([x[0] for x in steady])), float(np.mean([x[1] for x in steady]))
         oc = ctx.observed_counts()
+        fused = None
+        if world > 1:
+            # every rank's grid covers its own views: OR all-reduce (all-gather over NCCL + k_or_reduce) leaves the union everywhere
+            try:
+                from dmf_b200.sweep import fuse_observed
+                barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+                oc_f = fuse_observed(ctx)
+                torch.cuda.synchronize(); barrier()
+                fused = {"observed_voxels": oc_f["observed"], "free_voxels": oc_f["free"], "hit_voxels": oc_f["hit"], "ms": 1e3 * (time.perf_counter() - t0),
+                         "bytes_gathered_per_rank": int(ctx.lib.dmf_observed_words(ctx.h)) * 4 * world}
+            except Exception as e:                                           # noqa: BLE001 - secondary measurement: report, do not lose the line
+                fused = {"error": f"{type(e).__name__}: {e}"}
         tt = torch.tensor([first_ms, steady_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -435,7 +447,7 @@ def run_b200(args):
                  "voxel_updates_per_step": inb_per_step, "first_pass_ms": first_ms, "steady_ms_per_step": steady_ms,
                  "voxel_updates_per_s_first_pass": inb_per_step * world / (first_ms * 1e-3), "voxel_updates_per_s": inb_per_step * world / (steady_ms * 1e-3),
                  "rays_per_s": V * H * W * world / (steady_ms * 1e-3), "kernel_ms_first_pass": first_hot, "kernel_ms": steady_hot,
-                 "observed_voxels": oc["observed"], "free_voxels": oc["free"], "hit_voxels": oc["hit"],
+                 "observed_voxels": oc["observed"], "free_voxels": oc["free"], "hit_voxels": oc["hit"], "fused_over_ranks": fused,
                  "roofline": {"bound": "hbm", "algorithmic_bytes_per_launch": c_bytes, "achieved": c_bytes / (steady_hot * 1e-3) / 1e9,
                               "frac": c_bytes / (steady_hot * 1e-3) / 1e9 / measured_peak()[0], "unit": "GB/s",
                               "note": "1 B occupancy read + 1/8 B observed-bit write per in-bounds sample + 24 B per ray + bitset/pose per view"}}

@@ -73,6 +73,50 @@ def or_rows(bitsets) -> np.ndarray:
     return np.bitwise_or.reduce(b, axis=0) if len(b) else np.zeros(b.shape[1:], b.dtype)
 
 
+def or_allreduce(t, group=None, or_rows_dev=None):
+    """Bitwise-OR all-reduce of a packed bit grid (integer torch tensor, same shape on every rank), in place.
+    gloo reduces with BOR directly.  NCCL has no bitwise-OR: the grids are all-gathered (NVSwitch: every rank receives the
+    others' rows at full link rate) and OR-ed locally by `or_rows_dev(dst, rows)` -- K5 k_or_reduce via dmf_or_reduce_dev."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return t
+    if dist.get_backend(group) != "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.BOR, group=group)
+        return t
+    rows = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(rows, t.contiguous(), group=group)
+    if or_rows_dev is None:
+        raise ValueError("or_allreduce over NCCL needs or_rows_dev (the device OR kernel)")
+    or_rows_dev(t, rows)
+    return t
+
+
+def fuse_observed(ctx, group=None) -> dict:
+    """Carve mode over several GPUs: every rank has marched its share of the views into its own observed-voxel bit grid;
+    afterwards every rank's grid is the union (the fused free/occupied map of the whole sweep).  Returns observed_counts()."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from ._lib import check
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        n64 = ctx.lib.dmf_observed_words(ctx.h) // 2                     # the grid is a whole number of 256-bit blocks
+        ptr = ctx.observed_dev_ptr()                                     # synchronises the context's stream
+        ctx.synchronize()
+        dev = torch.device("cuda", ctx.device)
+        mine = torch.zeros(n64, dtype=torch.int64, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        check(ctx.lib.dmf_or_reduce_dev(ctx.h, C.c_void_p(mine.data_ptr()), C.c_void_p(ptr), 1, n64, st))        # export: 0 | grid
+
+        def or_rows_dev(dst, rows):
+            check(ctx.lib.dmf_or_reduce_dev(ctx.h, C.c_void_p(ptr), C.c_void_p(rows.data_ptr()), world, n64, st))  # merge into the context
+        or_allreduce(mine, group, or_rows_dev)
+        torch.cuda.current_stream(dev).synchronize()
+    return ctx.observed_counts()
+
+
 def sweep_visibility(engine, volume, poses, mode: int, zdelta: int, sparse: bool = False, reverse: bool = False, group=None,
                      layout: str = "strided") -> np.ndarray:
     """Visibility bitsets [n_views, words] of the whole pose list in view order, computed on this rank's shard and

@@ -107,3 +107,54 @@ def test_two_rank_sweep_equals_single_process(dmf, oracle, n_views, layout):
     sel = oracle.greedy_set_cover(sets)
     pop = [int(np.unpackbits(r.view(np.uint8)).sum()) for r in want]
     assert pop == [len(s) for s in sets] and len(sel) >= 1
+
+
+def _carve_worker(rank, world, port, n_views, q):
+    sys.path.insert(0, os.path.join(ROOT, "depth-map-fusion-utils_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch.distributed as dist
+    import oracle_py as O
+    from dmf_b200 import scenes
+    from dmf_b200.sweep import or_allreduce, shard_indices
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    sc = scenes.scene("S64")
+    vol = O.volume_from_scene(sc)
+    K = scenes.REFERENCE_K.copy(); K[[0, 2, 4, 5]] *= 0.125
+    poses = scenes.poses_sphere_lookat(1.024, 200)[:: 200 // n_views][:n_views]
+    obs, _ = O.forward_observed(vol, K, 60, 80, poses[0], O.MODE_POINTS, 8, False)
+    obs[:] = 0
+    for p in poses[shard_indices(n_views, rank, world, "strided")]:
+        obs, _ = O.forward_observed(vol, K, 60, 80, p, O.MODE_POINTS, 8, False, observed=obs)
+    fused = or_allreduce(torch.from_numpy(obs.view(np.int32).copy())).numpy().view(np.uint32)
+    q.put((rank, obs, fused))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_observed_grids_fuse_to_the_single_process_grid(dmf, oracle):
+    """carve mode over 2 ranks: each rank's observed-voxel grid covers its share of the views; the OR all-reduce leaves the
+    union on both -- equal to the grid one process builds from all views"""
+    import torch.multiprocessing as mp
+    n_views = 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_carve_worker, args=(r, 2, port, n_views, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        r, own, fused = q.get(timeout=240)
+        got[r] = (own, fused)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sc = dmf.scenes.scene("S64")
+    vol = oracle.volume_from_scene(sc)
+    K = dmf.scenes.REFERENCE_K.copy(); K[[0, 2, 4, 5]] *= 0.125
+    poses = dmf.scenes.poses_sphere_lookat(1.024, 200)[:: 200 // n_views][:n_views]
+    want = None
+    for p in poses:
+        want, _ = oracle.forward_observed(vol, K, 60, 80, p, oracle.MODE_POINTS, 8, False, observed=want)
+    assert np.array_equal(got[0][1], want) and np.array_equal(got[1][1], want)
+    assert not np.array_equal(got[0][0], want) and np.array_equal(got[0][0] | got[1][0], want)
