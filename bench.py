@@ -424,6 +424,15 @@ def run_b200(args):
         steady = [carve_step() for _ in range(n_c)]
         steady_ms, steady_hot = float(np.mean([x[0] for x in steady])), float(np.mean([x[1] for x in steady]))
         oc = ctx.observed_counts()
+        # the brute-force carve (k_forward<.., CARVE>: every sample evaluated the reference's way) for comparison, 2 launches
+        bparams = ForwardParams(D.MODE_POINTS, sc.zdelta, 0, 1, fmt, D.FWD_CARVE | D.FWD_NO_SKIP)
+        brute_ms = []
+        for _ in range(2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            check(ctx.lib.dmf_forward_dev(ctx.h, C.byref(bparams), C.c_void_p(d_poses.data_ptr()), V, C.byref(o), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            b.record(); torch.cuda.synchronize()
+            brute_ms.append(a.elapsed_time(b))
         fused = None
         if world > 1:
             # every rank's grid covers its own views: OR all-reduce (all-gather over NCCL + k_or_reduce) leaves the union everywhere
@@ -448,6 +457,7 @@ def run_b200(args):
                  "voxel_updates_per_s_first_pass": inb_per_step * world / (first_ms * 1e-3), "voxel_updates_per_s": inb_per_step * world / (steady_ms * 1e-3),
                  "rays_per_s": V * H * W * world / (steady_ms * 1e-3), "kernel_ms_first_pass": first_hot, "kernel_ms": steady_hot,
                  "observed_voxels": oc["observed"], "free_voxels": oc["free"], "hit_voxels": oc["hit"], "fused_over_ranks": fused,
+                 "brute_force_ms_per_step": min(brute_ms),
                  "roofline": {"bound": "hbm", "algorithmic_bytes_per_launch": c_bytes, "achieved": c_bytes / (steady_hot * 1e-3) / 1e9,
                               "frac": c_bytes / (steady_hot * 1e-3) / 1e9 / measured_peak()[0], "unit": "GB/s",
                               "note": "1 B occupancy read + 1/8 B observed-bit write per in-bounds sample + 24 B per ray + bitset/pose per view"}}

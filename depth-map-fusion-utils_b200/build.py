@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libdmf_b200.so")
+OUT = os.environ.get("DMF_B200_OUT") or os.path.join(HERE, "libdmf_b200.so")       # DMF_B200_OUT: build a variant next to the default
 SOURCES = ["dmf_b200.cu"]
 DEPS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(HERE, "..", "include", "dmf_b200.h")]
 

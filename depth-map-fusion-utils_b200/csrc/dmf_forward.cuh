@@ -677,50 +677,114 @@ __device__ __forceinline__ void observe_voxel(unsigned* __restrict__ obs, unsign
     // read first: after the first few views of a sweep nearly every bit is already set and the word sits in L1/L2; a stale 0
     // only costs a redundant (idempotent) atomicOr
     unsigned* const w = obs + (idx >> 5);
-    const unsigned m = 1u << (idx & 31);
+    unsigned m;
+    asm("shf.l.wrap.b32 %0, 0, 1, %1;" : "=r"(m) : "r"(idx));      // 1u << (idx & 31) in one instruction, opaque to strength "reduction"
     if (!(*w & m)) atomicOr(w, m);
 }
 
+// sample k of pixel (ci, ri) evaluated the reference's way (as k_forward does); marks its voxel if it passes validPoints
+template <bool EXACT>
+__device__ __forceinline__ void carve_exact_sample(const FwdArgs& a, unsigned sp, int ci, int ri, int k) {
+    const VolDev& v = a.vol;
+    const float xf = __ldg(a.xtab + ((unsigned)k * (unsigned)a.Wc + (unsigned)ci)), yf = __ldg(a.ytab + ((unsigned)k * (unsigned)a.Hc + (unsigned)ri));
+    const float zf = __ldg(a.ztab + k);
+    const float4 r0 = lds_f4_volatile(sp), r1 = lds_f4_volatile(sp + 16), r2 = lds_f4_volatile(sp + 32);
+    const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, xf), __fmul_rn(r0.y, yf)), __fmul_rn(r0.z, zf)), r0.w);
+    const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, xf), __fmul_rn(r1.y, yf)), __fmul_rn(r1.z, zf)), r1.w);
+    const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, xf), __fmul_rn(r2.y, yf)), __fmul_rn(r2.z, zf)), r2.w);
+    if (!(px > v.lo[0] && px < v.hi[0] && py > v.lo[1] && py < v.hi[1] && pz > v.lo[2] && pz < v.hi[2])) return;   // validPoints failed
+    int ix, iy, iz;
+    unsigned dummy0 = 0, dummy1 = 0;
+    const unsigned idx = probe_index<EXACT>(v, px, py, pz, v.inv32[0], v.inv32[1], v.inv32[2], v.c32[0], v.c32[1], v.c32[2],
+                                            v.err32[0], v.err32[1], v.err32[2], (unsigned)v.pdim[1], (unsigned)v.pdim[2], ix, iy, iz, dummy0, dummy1);
+    observe_voxel(a.observed, idx);
+}
+
+// The loop is issue-bound and, within that, bound by the half-rate integer (ALU) pipe -- a 12.20 fixed-point version of the
+// line (integer add / mask / compare per axis) measured no faster than the float one because every one of its instructions
+// went down that pipe (ncu: ALU 63 % busy, FMA 13 %).  So the line stays in float, on the full-rate FMA pipe:
+//   t = Q(k) - 0.5;  s = t + 1.5*2^23 (round to nearest) -> low mantissa bits = rint(t) = n;  h = t - n in [-0.5, 0.5]
+//   => Q(k) = n + 0.5 + h: the voxel is n and the distance to its nearer face is 0.5 - |h|;  safe <=> max|h| <= 0.5 - e_safe.
+// Four FMA-pipe instructions per axis, then one 3-input max and one compare.  Samples that fail the face test are only
+// remembered (one bit each) and evaluated exactly after their chunk of 32, so a warp runs the long exact path a couple of
+// times per 32 samples instead of whenever any of its 32 lanes needs it.
+#ifndef DMF_CARVE_MLP
+#define DMF_CARVE_MLP 8
+#endif
+#ifndef DMF_CARVE_MIN_BLOCKS
+#define DMF_CARVE_MIN_BLOCKS 7
+#endif
+constexpr int CARVE_MLP = DMF_CARVE_MLP;          // samples whose observed-word loads are in flight together
+constexpr int CARVE_MIN_BLOCKS = DMF_CARVE_MIN_BLOCKS;
+
 template <bool EXACT>
 __device__ __forceinline__ void carve_on_line(const FwdArgs& a, unsigned sp, int ci, int ri, int k_first, int k_last, int kin, int kout,
-                                           float qa0, float qa1, float qa2, float qb0, float qb1, float qb2, float esafe) {
+                                              float qa0, float qa1, float qa2, float qb0, float qb1, float qb2, float esafe) {
     const VolDev& v = a.vol;
-    const float kM = 12582912.0f;
-    const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
-    const unsigned pnyz = pny * pnz;
-    const unsigned bias = 0x4B400000u * (pnyz + pnz + 1u);
-    const unsigned last = pnyz * (unsigned)v.pdim[0] - 1u;
-    const float hi_safe = 1.0f - esafe;
-    unsigned* const obs = a.observed;
-    unsigned dummy0 = 0, dummy1 = 0;
-    for (int k = k_first; k <= k_last; k++) {
-        if (k >= kin && k <= kout) {
-            const float kf = (float)k;
-            const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
-            const float s0 = __fadd_rd(q0, kM), s1 = __fadd_rd(q1, kM), s2 = __fadd_rd(q2, kM);
-            const float f0 = q0 - (s0 - kM), f1 = q1 - (s1 - kM), f2 = q2 - (s2 - kM);
-            if (fminf(f0, fminf(f1, f2)) >= esafe && fmaxf(f0, fmaxf(f1, f2)) <= hi_safe) {
-                const unsigned idx = (unsigned)__float_as_int(s0) * pnyz + ((unsigned)__float_as_int(s1) * pnz + ((unsigned)__float_as_int(s2) - bias));
-                observe_voxel(obs, min(idx, last));
-                continue;
+    const int b0 = max(kin, k_first), b1 = min(kout, k_last);
+    if (b0 > b1) {                                           // the line is never safely inside within the visited range
+        for (int k = k_first; k <= k_last; k++) carve_exact_sample<EXACT>(a, sp, ci, ri, k);
+        return;
+    }
+    for (int k = k_first; k < b0; k++) carve_exact_sample<EXACT>(a, sp, ci, ri, k);          // entry band around the boundary
+    {
+        const float kM = 12582912.0f;                                                        // 1.5 * 2^23
+        unsigned pnz = (unsigned)v.pdim[2], pnyz = (unsigned)v.pdim[1] * pnz;
+        unsigned last = pnyz * (unsigned)v.pdim[0] - 1u;
+        unsigned bias = 0x4B400000u * (pnyz + pnz + 1u);                                     // the three "- 0x4B400000" of the shifter, folded
+        asm volatile("" : "+r"(pnz), "+r"(pnyz), "+r"(last), "+r"(bias));                    // registers, not re-derived from the constant bank per sample
+        const float ta0 = qa0 - 0.5f, ta1 = qa1 - 0.5f, ta2 = qa2 - 0.5f;
+        const float hmax = 0.5f - esafe;
+        unsigned* const obs = a.observed;
+        for (int kb = b0; kb <= b1; kb += 32) {
+            const int n = min(32, b1 - kb + 1);
+            unsigned unsafe = 0u;
+            // CARVE_MLP samples at a time: all their voxels are located first, then all their observed words are loaded (back to
+            // back, so the loads overlap), then tested.  With one load -> test -> branch per sample the loop was latency-bound
+            // (ncu: 41 % of the stall samples on the instruction consuming the load, issue-active 56 %).
+            for (int j = 0; j < n; j += CARVE_MLP) {
+                unsigned idx[CARVE_MLP], word[CARVE_MLP], bit[CARVE_MLP];
+                unsigned okm = 0u;
+                const float kfb = (float)(kb + j);
+#pragma unroll
+                for (int u = 0; u < CARVE_MLP; u++) {
+                    const float kf = kfb + (float)u;                                     // exact: small integers
+                    const float t0 = fmaf(kf, qb0, ta0), t1 = fmaf(kf, qb1, ta1), t2 = fmaf(kf, qb2, ta2);
+                    const float s0 = __fadd_rn(t0, kM), s1 = __fadd_rn(t1, kM), s2 = __fadd_rn(t2, kM);
+                    const float h0 = __fsub_rn(t0, __fsub_rn(s0, kM)), h1 = __fsub_rn(t1, __fsub_rn(s1, kM)), h2 = __fsub_rn(t2, __fsub_rn(s2, kM));
+                    if (fmaxf(fabsf(h0), fmaxf(fabsf(h1), fabsf(h2))) <= hmax) okm |= 1u << u;
+                    idx[u] = min((unsigned)__float_as_int(s0) * pnyz + ((unsigned)__float_as_int(s1) * pnz + ((unsigned)__float_as_int(s2) - bias)), last);
+                }
+                const unsigned live = (j + CARVE_MLP <= n) ? ((1u << CARVE_MLP) - 1u) : ((1u << (n - j)) - 1u);   // samples of this group inside the chunk
+                unsafe |= (~okm & live) << j;
+#pragma unroll
+                for (int u = 0; u < CARVE_MLP; u++) word[u] = obs[idx[u] >> 5];         // (a clamped, in-grid address even when the sample is not used)
+                // one branch per group, not per sample: after the first views of a sweep no bit is missing any more
+                unsigned need = 0u;
+#pragma unroll
+                for (int u = 0; u < CARVE_MLP; u++) {
+                    asm("shf.l.wrap.b32 %0, 0, 1, %1;" : "=r"(bit[u]) : "r"(idx[u]));   // 1u << (idx & 31)
+                    if (!(word[u] & bit[u])) need |= 1u << u;
+                }
+                need &= okm & live;
+                if (need) {
+#pragma unroll
+                    for (int u = 0; u < CARVE_MLP; u++)
+                        if ((need >> u) & 1u) atomicOr(obs + (idx[u] >> 5), bit[u]);
+                }
+            }
+            while (unsafe) {
+                const int j = __ffs(unsafe) - 1;
+                unsafe &= unsafe - 1u;
+                carve_exact_sample<EXACT>(a, sp, ci, ri, kb + j);
             }
         }
-        const float xf = __ldg(a.xtab + ((unsigned)k * (unsigned)a.Wc + (unsigned)ci)), yf = __ldg(a.ytab + ((unsigned)k * (unsigned)a.Hc + (unsigned)ri));
-        const float zf = __ldg(a.ztab + k);
-        const float4 r0 = lds_f4_volatile(sp), r1 = lds_f4_volatile(sp + 16), r2 = lds_f4_volatile(sp + 32);
-        const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, xf), __fmul_rn(r0.y, yf)), __fmul_rn(r0.z, zf)), r0.w);
-        const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, xf), __fmul_rn(r1.y, yf)), __fmul_rn(r1.z, zf)), r1.w);
-        const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, xf), __fmul_rn(r2.y, yf)), __fmul_rn(r2.z, zf)), r2.w);
-        if (!(px > v.lo[0] && px < v.hi[0] && py > v.lo[1] && py < v.hi[1] && pz > v.lo[2] && pz < v.hi[2])) continue;   // validPoints failed
-        int ix, iy, iz;
-        const unsigned idx = probe_index<EXACT>(v, px, py, pz, v.inv32[0], v.inv32[1], v.inv32[2], v.c32[0], v.c32[1], v.c32[2],
-                                                v.err32[0], v.err32[1], v.err32[2], pny, pnz, ix, iy, iz, dummy0, dummy1);
-        observe_voxel(obs, idx);
     }
+    for (int k = b1 + 1; k <= k_last; k++) carve_exact_sample<EXACT>(a, sp, ci, ri, k);      // exit band
 }
 
 template <int MODE, bool EXACT, bool CARVE>
-__global__ void __launch_bounds__(SKIP_THREADS, CARVE ? 8 : LINE_MIN_BLOCKS) k_forward_line(const FwdArgs a) {
+__global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_MIN_BLOCKS) k_forward_line(const FwdArgs a) {
     __shared__ __align__(16) float s_pose[12];
     __shared__ float s_adv[256];
     __shared__ int s_qbmax;
@@ -789,7 +853,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? 8 : LINE_MIN_BLOCKS) k_f
             n_inb = n_skip = (unsigned)k0;                                            // k0 > 0 only when the camera sits inside the volume
         }
     }
-    if (!active) k = s_end = S;
+    if (!active) { k = s_end = S; n_inb = n_skip = 0u; }      // (lanes outside a ragged lattice must not count the view-wide k0 either)
     __syncthreads();
     {
         // s_adv[d] = 1 + number of samples skipped after a line probe with byte d, at the block's largest |QB|

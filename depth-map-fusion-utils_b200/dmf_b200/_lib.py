@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(HERE), "libdmf_b200.so")
+# DMF_B200_LIB: another build of the same library (A/B timing of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("DMF_B200_LIB") or os.path.join(os.path.dirname(HERE), "libdmf_b200.so")
 
 
 class DmfError(RuntimeError):

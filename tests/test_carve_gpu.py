@@ -151,3 +151,34 @@ def test_full_size_properties(dmf, ctx):
     x, y, z = (ids >> np.uint64(40)).astype(np.int64), ((ids >> np.uint64(20)) & np.uint64(0xFFFFF)).astype(np.int64), (ids & np.uint64(0xFFFFF)).astype(np.int64)
     idx = (x * dims[1] + y) * dims[2] + z
     assert np.all((line[idx >> 5] >> (idx & 31).astype(np.uint32)) & 1), "a first-hit voxel is not marked observed"
+
+
+def test_anisotropic_offset_volume(dmf, oracle, ctx):
+    """non-cubic voxels, bounds off the origin, non-dyadic sizes: the fixed-point line and the face test scale per axis"""
+    from tests.test_forward_gpu import _aniso_scene
+    sc = _aniso_scene(dmf)
+    ov = oracle.volume_from_scene(sc, flat=True)
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+    K = dmf.scenes.REFERENCE_K
+    centre = np.array([0.08, 0.2, 0.52])
+    poses = np.stack([dmf.scenes.look_at(centre + 0.45 * v, centre) for v in dmf.scenes.sphere_directions(6.0)[3::9][:5]]
+                     + [dmf.scenes.look_at([0.9, 0.9, 1.4], centre), dmf.scenes.look_at([-0.30, -0.21, 0.12], centre), dmf.scenes.look_at(centre, centre + [0.3, 0.1, 0.2])])
+    for zd, sparse in ((5, False), (3, True)):
+        want, tot = _oracle_observed(oracle, ov, K, K_H, K_W, poses, 0, zd, sparse)
+        for fmt, skip in ((dmf.GRID_BYTE, True), (dmf.GRID_BYTE, False)):
+            got, cnt, _ = _gpu_observed(dmf, ctx, gv, K, K_H, K_W, poses, 0, zd, sparse, fmt, skip)
+            assert np.array_equal(got, want), f"zd={zd} sparse={sparse} fmt={fmt} skip={skip}: {_popcount(got ^ want)} voxels differ"
+            assert cnt["samples"] == tot["samples"] and cnt["inbounds"] == tot["inbounds"] and cnt["hits"] == tot["hits"], (cnt, tot)
+    assert _popcount(want) > 1000
+
+
+def test_config3_1024_grid_observed(dmf, oracle, ctx):
+    """BASELINE.json configs[3] grid: 1024^3 (0.977 mm voxels, zdelta = 1 mm, 990 samples per ray), 320x240 camera for the oracle"""
+    sc, ov, gv = _scene_pair(dmf, oracle, ctx, "S1024")
+    K = dmf.scenes.REFERENCE_K.copy(); K[[0, 2, 4, 5]] *= 0.5
+    poses = np.stack([dmf.scenes.pose_p1(1.0)[0], dmf.scenes.poses_helix(1.0, 40)[17]])
+    want, tot = _oracle_observed(oracle, ov, K, 240, 320, poses, 0, 1, False)
+    got, cnt, _ = _gpu_observed(dmf, ctx, gv, K, 240, 320, poses, 0, 1, False, dmf.GRID_BYTE, True)
+    assert np.array_equal(got, want), f"{_popcount(got ^ want)} voxels differ"
+    assert cnt["inbounds"] == tot["inbounds"] and cnt["hits"] == tot["hits"]
