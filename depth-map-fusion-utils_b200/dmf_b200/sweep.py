@@ -107,13 +107,17 @@ def fuse_observed(ctx, group=None) -> dict:
         ctx.synchronize()
         dev = torch.device("cuda", ctx.device)
         mine = torch.zeros(n64, dtype=torch.int64, device=dev)
-        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        check(ctx.lib.dmf_or_reduce_dev(ctx.h, C.c_void_p(mine.data_ptr()), C.c_void_p(ptr), 1, n64, st))        # export: 0 | grid
+        torch.cuda.synchronize(dev)                                       # `mine` is zeroed before the context's stream touches it
+        # both kernels run on the context's own stream (NULL = that stream in the C ABI); the collective runs on torch's.
+        # A one-off step at the end of a sweep: plain synchronisation between the three, no event plumbing.
+        check(ctx.lib.dmf_or_reduce_dev(ctx.h, C.c_void_p(mine.data_ptr()), C.c_void_p(ptr), 1, n64, None))           # export: 0 | grid
+        ctx.synchronize()
 
         def or_rows_dev(dst, rows):
-            check(ctx.lib.dmf_or_reduce_dev(ctx.h, C.c_void_p(ptr), C.c_void_p(rows.data_ptr()), world, n64, st))  # merge into the context
+            torch.cuda.synchronize(dev)                                   # the all-gather has landed
+            check(ctx.lib.dmf_or_reduce_dev(ctx.h, C.c_void_p(ptr), C.c_void_p(rows.data_ptr()), world, n64, None))   # merge into the context
+            ctx.synchronize()
         or_allreduce(mine, group, or_rows_dev)
-        torch.cuda.current_stream(dev).synchronize()
     return ctx.observed_counts()
 
 
