@@ -28,6 +28,16 @@ __device__ __forceinline__ void raise_flag(int* p) {
     if (*p == 0) *p = 1;
 }
 
+// Packed FP32 pairs (sm_100 FFMA2 / FADD2): two independent IEEE round-to-nearest operations per issued instruction,
+// each half bit-identical to the scalar fmaf / __fadd_rn / __fsub_rn.  For loops that are bound by instruction issue,
+// not by the FMA pipe.  A pair lives in one 64-bit register (lo = .x, hi = .y); pack/unpack are register-pair renames.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // HBM layout of a VoxelVolume (reference include/Volume.hpp:50-78):
 //   bits     uint32 words of a linear bit grid over the PADDED index space [0,dim_x] x [0,dim_y] x [0,dim_z]
 //            (pdim = dim + 1 per axis, z fastest like voxels_[x][y][z]); bit index = (x*pdim_y + y)*pdim_z + z.

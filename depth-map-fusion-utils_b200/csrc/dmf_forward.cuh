@@ -711,8 +711,23 @@ __device__ __forceinline__ void carve_exact_sample(const FwdArgs& a, unsigned sp
 #ifndef DMF_CARVE_MLP
 #define DMF_CARVE_MLP 8
 #endif
+#ifndef DMF_CARVE_X2
+#define DMF_CARVE_X2 1                            // 1: locate two samples per FFMA2 / FADD2 (sm_100 packed FP32)
+#endif
+#if DMF_CARVE_X2 && (DMF_CARVE_MLP % 2)
+#error "DMF_CARVE_X2 needs an even DMF_CARVE_MLP"
+#endif
+#ifndef DMF_CARVE_SIGN
+#define DMF_CARVE_SIGN 1                          // 1: carve_on_line_sign (face test collected as sign bits, OR tree for the missing bits, full groups only)
+#endif
+#ifndef DMF_CARVE_CLAMP
+#define DMF_CARVE_CLAMP 0                         // carve_on_line_sign: 1 = clamp the located voxel index (never active, see the proof there; costs 3.5 %)
+#endif
+#if DMF_CARVE_SIGN && (!DMF_CARVE_X2 || (DMF_CARVE_MLP & (DMF_CARVE_MLP - 1)) || DMF_CARVE_MLP > 32)
+#error "DMF_CARVE_SIGN needs DMF_CARVE_X2 and a power-of-two DMF_CARVE_MLP <= 32"
+#endif
 #ifndef DMF_CARVE_MIN_BLOCKS
-#define DMF_CARVE_MIN_BLOCKS 7
+#define DMF_CARVE_MIN_BLOCKS 8
 #endif
 constexpr int CARVE_MLP = DMF_CARVE_MLP;          // samples whose observed-word loads are in flight together
 constexpr int CARVE_MIN_BLOCKS = DMF_CARVE_MIN_BLOCKS;
@@ -735,6 +750,10 @@ __device__ __forceinline__ void carve_on_line(const FwdArgs& a, unsigned sp, int
         asm volatile("" : "+r"(pnz), "+r"(pnyz), "+r"(last), "+r"(bias));                    // registers, not re-derived from the constant bank per sample
         const float ta0 = qa0 - 0.5f, ta1 = qa1 - 0.5f, ta2 = qa2 - 0.5f;
         const float hmax = 0.5f - esafe;
+#if DMF_CARVE_X2
+        const f32x2 qb0p = f2_pack(qb0, qb0), qb1p = f2_pack(qb1, qb1), qb2p = f2_pack(qb2, qb2);
+        const f32x2 ta0p = f2_pack(ta0, ta0), ta1p = f2_pack(ta1, ta1), ta2p = f2_pack(ta2, ta2), kMp = f2_pack(kM, kM);
+#endif
         unsigned* const obs = a.observed;
         for (int kb = b0; kb <= b1; kb += 32) {
             const int n = min(32, b1 - kb + 1);
@@ -743,19 +762,43 @@ __device__ __forceinline__ void carve_on_line(const FwdArgs& a, unsigned sp, int
             // back, so the loads overlap), then tested.  With one load -> test -> branch per sample the loop was latency-bound
             // (ncu: 41 % of the stall samples on the instruction consuming the load, issue-active 56 %).
             for (int j = 0; j < n; j += CARVE_MLP) {
-                unsigned idx[CARVE_MLP], word[CARVE_MLP], bit[CARVE_MLP];
-                unsigned okm = 0u;
+                unsigned idx[CARVE_MLP], word[CARVE_MLP];
+                float hm[CARVE_MLP];                                                     // max |h| over the three axes
                 const float kfb = (float)(kb + j);
+#if DMF_CARVE_X2
+                // two samples per instruction (FFMA2 / FADD2): the same fmaf / add / sub sequence as below, each half
+                // rounded exactly like the scalar op, at half the issue slots
+                const f32x2 kp = f2_pack(kfb, kfb + 1.0f);
+#pragma unroll
+                for (int u = 0; u < CARVE_MLP; u += 2) {
+                    const f32x2 kf = f2_add(kp, f2_pack((float)u, (float)u));            // exact: small integers
+                    const f32x2 t0 = f2_fma(kf, qb0p, ta0p), t1 = f2_fma(kf, qb1p, ta1p), t2 = f2_fma(kf, qb2p, ta2p);
+                    const f32x2 s0 = f2_add(t0, kMp), s1 = f2_add(t1, kMp), s2 = f2_add(t2, kMp);
+                    const f32x2 h0 = f2_sub(t0, f2_sub(s0, kMp)), h1 = f2_sub(t1, f2_sub(s1, kMp)), h2 = f2_sub(t2, f2_sub(s2, kMp));
+                    float h0a, h0b, h1a, h1b, h2a, h2b, s0a, s0b, s1a, s1b, s2a, s2b;
+                    f2_unpack(h0, h0a, h0b); f2_unpack(h1, h1a, h1b); f2_unpack(h2, h2a, h2b);
+                    f2_unpack(s0, s0a, s0b); f2_unpack(s1, s1a, s1b); f2_unpack(s2, s2a, s2b);
+                    hm[u] = fmaxf(fabsf(h0a), fmaxf(fabsf(h1a), fabsf(h2a)));
+                    hm[u + 1] = fmaxf(fabsf(h0b), fmaxf(fabsf(h1b), fabsf(h2b)));
+                    idx[u] = min((unsigned)__float_as_int(s0a) * pnyz + ((unsigned)__float_as_int(s1a) * pnz + ((unsigned)__float_as_int(s2a) - bias)), last);
+                    idx[u + 1] = min((unsigned)__float_as_int(s0b) * pnyz + ((unsigned)__float_as_int(s1b) * pnz + ((unsigned)__float_as_int(s2b) - bias)), last);
+                }
+#else
 #pragma unroll
                 for (int u = 0; u < CARVE_MLP; u++) {
                     const float kf = kfb + (float)u;                                     // exact: small integers
                     const float t0 = fmaf(kf, qb0, ta0), t1 = fmaf(kf, qb1, ta1), t2 = fmaf(kf, qb2, ta2);
                     const float s0 = __fadd_rn(t0, kM), s1 = __fadd_rn(t1, kM), s2 = __fadd_rn(t2, kM);
                     const float h0 = __fsub_rn(t0, __fsub_rn(s0, kM)), h1 = __fsub_rn(t1, __fsub_rn(s1, kM)), h2 = __fsub_rn(t2, __fsub_rn(s2, kM));
-                    if (fmaxf(fabsf(h0), fmaxf(fabsf(h1), fabsf(h2))) <= hmax) okm |= 1u << u;
+                    hm[u] = fmaxf(fabsf(h0), fmaxf(fabsf(h1), fabsf(h2)));
                     idx[u] = min((unsigned)__float_as_int(s0) * pnyz + ((unsigned)__float_as_int(s1) * pnz + ((unsigned)__float_as_int(s2) - bias)), last);
                 }
+#endif
                 const unsigned live = (j + CARVE_MLP <= n) ? ((1u << CARVE_MLP) - 1u) : ((1u << (n - j)) - 1u);   // samples of this group inside the chunk
+                unsigned okm = 0u, bit[CARVE_MLP];
+#pragma unroll
+                for (int u = 0; u < CARVE_MLP; u++)
+                    if (hm[u] <= hmax) okm |= 1u << u;
                 unsafe |= (~okm & live) << j;
 #pragma unroll
                 for (int u = 0; u < CARVE_MLP; u++) word[u] = obs[idx[u] >> 5];         // (a clamped, in-grid address even when the sample is not used)
@@ -782,6 +825,102 @@ __device__ __forceinline__ void carve_on_line(const FwdArgs& a, unsigned sp, int
     }
     for (int k = b1 + 1; k <= k_last; k++) carve_exact_sample<EXACT>(a, sp, ci, ri, k);      // exit band
 }
+
+#if DMF_CARVE_SIGN
+// carve_on_line with fewer instructions on the half-rate integer pipe (ncu on the packed-FP32 build: ALU pipe 65 % busy, issue
+// 72 %): the same samples located by the same arithmetic, but
+//  * the face test "max|h| <= hmax" is taken from the SIGN of hmax - max|h| (the sign of a rounded float difference is the sign
+//    of the exact one; equal operands give +0) and funnel-shifted into a per-group bit string: one SHF per sample instead of
+//    compare + select + add.  The newest sample sits in bit 0, so bit b of a group is its sample b ^ (CARVE_MLP - 1);
+//  * the missing observed bits are collected as words (bit & ~word, one LOP3) and OR-ed into one "anything missing?" test;
+//  * groups are always full: a range whose length is not a multiple of CARVE_MLP starts with one group at b0 and continues
+//    at b0 + (length % CARVE_MLP), so a few samples are located twice (marking is idempotent) and no per-sample "inside the
+//    chunk" mask exists.  A safe range shorter than one group is evaluated exactly.
+// (Branching on "a face test failed" per group does NOT pay: 1.2 % of the samples fail, i.e. some lane of nearly every warp --
+// measured 10.3 ms against 9.5 ms.  The failures stay deferred to the end of the chunk as in carve_on_line.)
+template <bool EXACT>
+__device__ __forceinline__ void carve_on_line_sign(const FwdArgs& a, unsigned sp, int ci, int ri, int k_first, int k_last, int kin, int kout,
+                                                   float qa0, float qa1, float qa2, float qb0, float qb1, float qb2, float esafe) {
+    const VolDev& v = a.vol;
+    const int b0 = max(kin, k_first), b1 = min(kout, k_last);
+    const int len = b1 - b0 + 1;
+    if (len < CARVE_MLP) {                                   // no (or a very short) safely-inside range: everything exactly
+        for (int k = k_first; k <= k_last; k++) carve_exact_sample<EXACT>(a, sp, ci, ri, k);
+        return;
+    }
+    for (int k = k_first; k < b0; k++) carve_exact_sample<EXACT>(a, sp, ci, ri, k);          // entry band around the boundary
+    {
+        const float kM = 12582912.0f;                                                        // 1.5 * 2^23
+        unsigned pnz = (unsigned)v.pdim[2], pnyz = (unsigned)v.pdim[1] * pnz;
+        unsigned bias = 0x4B400000u * (pnyz + pnz + 1u);                                     // the three "- 0x4B400000" of the shifter, folded
+#if DMF_CARVE_CLAMP
+        unsigned last = pnyz * (unsigned)v.pdim[0] - 1u;
+        asm volatile("" : "+r"(last));
+#endif
+        asm volatile("" : "+r"(pnz), "+r"(pnyz), "+r"(bias));                                // registers, not re-derived from the constant bank per sample
+        const float ta0 = qa0 - 0.5f, ta1 = qa1 - 0.5f, ta2 = qa2 - 0.5f;
+        const float hmax = 0.5f - esafe;
+        const f32x2 qb0p = f2_pack(qb0, qb0), qb1p = f2_pack(qb1, qb1), qb2p = f2_pack(qb2, qb2);
+        const f32x2 ta0p = f2_pack(ta0, ta0), ta1p = f2_pack(ta1, ta1), ta2p = f2_pack(ta2, ta2), kMp = f2_pack(kM, kM);
+        unsigned* const obs = a.observed;
+        const int head = len % CARVE_MLP;                    // != 0: one group at b0 first, the aligned rest starts at b0 + head
+        int kb = b0, n = head ? CARVE_MLP : min(32, len), next = head ? b0 + head : b0 + n;
+        for (;;) {
+            unsigned unsafe = 0u;                            // bit j + b: sample kb + j + (b ^ (CARVE_MLP - 1)) failed the face test
+            for (int j = 0; j < n; j += CARVE_MLP) {         // n is a multiple of CARVE_MLP
+                unsigned idx[CARVE_MLP], word[CARVE_MLP], miss[CARVE_MLP];
+                unsigned fail = 0u;
+                const float kfb = (float)(kb + j);
+                const f32x2 kp = f2_pack(kfb, kfb + 1.0f);
+#pragma unroll
+                for (int u = 0; u < CARVE_MLP; u += 2) {
+                    const f32x2 kf = f2_add(kp, f2_pack((float)u, (float)u));            // exact: small integers
+                    const f32x2 t0 = f2_fma(kf, qb0p, ta0p), t1 = f2_fma(kf, qb1p, ta1p), t2 = f2_fma(kf, qb2p, ta2p);
+                    const f32x2 s0 = f2_add(t0, kMp), s1 = f2_add(t1, kMp), s2 = f2_add(t2, kMp);
+                    const f32x2 h0 = f2_sub(t0, f2_sub(s0, kMp)), h1 = f2_sub(t1, f2_sub(s1, kMp)), h2 = f2_sub(t2, f2_sub(s2, kMp));
+                    float h0a, h0b, h1a, h1b, h2a, h2b, s0a, s0b, s1a, s1b, s2a, s2b;
+                    f2_unpack(h0, h0a, h0b); f2_unpack(h1, h1a, h1b); f2_unpack(h2, h2a, h2b);
+                    f2_unpack(s0, s0a, s0b); f2_unpack(s1, s1a, s1b); f2_unpack(s2, s2a, s2b);
+                    const float da = __fsub_rn(hmax, fmaxf(fabsf(h0a), fmaxf(fabsf(h1a), fabsf(h2a))));   // < 0  <=>  face test failed
+                    const float db = __fsub_rn(hmax, fmaxf(fabsf(h0b), fmaxf(fabsf(h1b), fabsf(h2b))));
+                    fail = __funnelshift_l(__float_as_uint(da), fail, 1);                // (fail << 1) | sign(da)
+                    fail = __funnelshift_l(__float_as_uint(db), fail, 1);
+                    idx[u] = (unsigned)__float_as_int(s0a) * pnyz + ((unsigned)__float_as_int(s1a) * pnz + ((unsigned)__float_as_int(s2a) - bias));
+                    idx[u + 1] = (unsigned)__float_as_int(s0b) * pnyz + ((unsigned)__float_as_int(s1b) * pnz + ((unsigned)__float_as_int(s2b) - bias));
+#if DMF_CARVE_CLAMP
+                    idx[u] = min(idx[u], last); idx[u + 1] = min(idx[u + 1], last);      // a seat belt, never active: the samples are inside
+#endif
+                }
+                unsafe |= fail << j;
+#pragma unroll
+                for (int u = 0; u < CARVE_MLP; u++) word[u] = obs[idx[u] >> 5];
+                unsigned missing = 0u;
+#pragma unroll
+                for (int u = 0; u < CARVE_MLP; u++) {
+                    unsigned bit;
+                    asm("shf.l.wrap.b32 %0, 0, 1, %1;" : "=r"(bit) : "r"(idx[u]));      // 1u << (idx & 31)
+                    miss[u] = bit & ~word[u];                                            // the bit if it is not set yet, else 0
+                    missing |= miss[u];
+                }
+                if (missing) {                                                           // rare once the sweep has seen the voxels
+#pragma unroll
+                    for (int u = 0; u < CARVE_MLP; u++)
+                        if (miss[u] && !((fail >> (CARVE_MLP - 1 - u)) & 1u)) atomicOr(obs + (idx[u] >> 5), miss[u]);
+                }
+            }
+            while (unsafe) {
+                const int b = __ffs(unsafe) - 1;
+                unsafe &= unsafe - 1u;
+                carve_exact_sample<EXACT>(a, sp, ci, ri, kb + (b ^ (CARVE_MLP - 1)));
+            }
+            kb = next;
+            if (kb > b1) break;
+            n = min(32, b1 - kb + 1); next = kb + n;
+        }
+    }
+    for (int k = b1 + 1; k <= k_last; k++) carve_exact_sample<EXACT>(a, sp, ci, ri, k);      // exit band
+}
+#endif
 
 template <int MODE, bool EXACT, bool CARVE>
 __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_MIN_BLOCKS) k_forward_line(const FwdArgs a) {
@@ -950,7 +1089,11 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
     }
     if (CARVE && MODE != 4 && active) {
         const int k_last = hit_k >= 0 ? hit_k : s_end - 1;                          // samples >= s_end are provably outside the volume
+#if DMF_CARVE_SIGN
+        carve_on_line_sign<EXACT>(a, sp, ci, ri, k_slab, k_last, kin, kout, qa0, qa1, qa2, qb0, qb1, qb2, s_esafe);
+#else
         carve_on_line<EXACT>(a, sp, ci, ri, k_slab, k_last, kin, kout, qa0, qa1, qa2, qb0, qb1, qb2, s_esafe);
+#endif
     }
     const unsigned n_samples = active ? (unsigned)((hit_k >= 0 || stop || (MODE == 4 && k < s_end)) ? min(k, S) : S) : 0u;
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
