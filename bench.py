@@ -452,7 +452,7 @@ def run_b200(args):
         # algorithmic bytes per launch (carve mode): 1 B occupancy read + 1/8 B observed-bit write per in-bounds
         # sample, + the per-ray and per-view outputs as above
         c_bytes = inb_per_step * 1.125 + V * H * W * 24 + V * (vw * 8 + 48)
-        carve = {"what": "same views with DMF_FWD_CARVE: k_forward_line finds the hit, carve_on_line marks the voxel of every visited in-bounds sample in the observed bit grid",
+        carve = {"what": "same views with DMF_FWD_CARVE: k_forward_line finds the hit, carve_on_line_sign marks the voxel of every visited in-bounds sample in the observed bit grid",
                  "voxel_updates_per_step": inb_per_step, "first_pass_ms": first_ms, "steady_ms_per_step": steady_ms,
                  "voxel_updates_per_s_first_pass": inb_per_step * world / (first_ms * 1e-3), "voxel_updates_per_s": inb_per_step * world / (steady_ms * 1e-3),
                  "rays_per_s": V * H * W * world / (steady_ms * 1e-3), "kernel_ms_first_pass": first_hot, "kernel_ms": steady_hot,
