@@ -1,7 +1,7 @@
-"""Ad-hoc timing of reverseRayTraceFast batches (kernel ms from CUDA events) vs the CPU oracle."""
+"""Ad-hoc timing of reverseRayTraceFast batches (kernel ms from CUDA events).  (The CPU side is timed by bench.py only.)"""
 import sys, time, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "depth-map-fusion-utils_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "depth-map-fusion-utils_b200"))
 import numpy as np
 import dmf_b200 as D
 name = sys.argv[1] if len(sys.argv) > 1 else "S512"
@@ -19,9 +19,3 @@ for fmt in (D.GRID_BYTE, D.GRID_BIT):
         t = time.time(); r = eng.reverse_views(gv, poses, fast=True, want=("visibility",)); wall = time.time() - t
         ms = ctx.last_hot_kernel_ms(); c = ctx.counters()
         print(f"{name} reverse fmt={fmt} views={nv} n_occ={len(gv.occupied_cells_)} hot_ms={ms:.3f} wall_ms={wall*1e3:.1f} voxel-rays/s={nv*len(gv.occupied_cells_)/ms*1e3:.3e} steps/s={c['samples']/ms*1e3:.3e} skipped={c['skipped']/max(c['samples'],1):.3f} visible={c['hits']}")
-if len(sys.argv) > 3:
-    import oracle_py as O
-    ov = O.volume_from_scene(sc, flat=False)
-    for dead in (0, 1):
-        t = time.time(); o = O.reverse(ov, D.scenes.REFERENCE_K, 480, 640, poses[0], fast=True, dead_work=bool(dead)); dt = time.time() - t
-        print(f"oracle reverseRayTraceFast 1 view dead_work={dead}: {dt:.3f} s, {len(o['ids'])} ids")
