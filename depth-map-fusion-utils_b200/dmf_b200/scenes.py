@@ -218,6 +218,25 @@ def poses_position_camera(L: float, n: int, standoff: float = 0.5, factor: float
     return np.stack(out)
 
 
+def position_cameras(points, normals, distance: int = 300) -> np.ndarray:
+    """Algorithms::positionCameras(locations, distance) (Algorithms.hpp:282-298 -> positionCamera :190-236), float for float:
+    normals with z <= 0 are flipped (:286-292); x = (0,-1,0), y = (1,0,0) (the fixed columns of :223-225), z = -normal;
+    translation = point + Vector3f(normal) * float(distance / 1000.0) evaluated like movePointAway (:114-122): the product in
+    float, the sum in double, stored to float.  points, normals: (n, 3) -> (n, 12) float32 poses."""
+    f32 = np.float32
+    pts = np.ascontiguousarray(points, f32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals, f32).reshape(-1, 3).copy()
+    nrm[nrm[:, 2] <= 0] *= f32(-1)
+    d = f32(float(distance) / 1000.0)                                  # double(distance)/1000.0 narrowed to float by Vector3f * double
+    moved = (nrm * d).astype(np.float64) + pts.astype(np.float64)      # n(i) + pi[i]: float product, double sum
+    out = np.zeros((len(pts), 3, 4), f32)
+    out[:, :, 0] = (0, -1, 0)
+    out[:, :, 1] = (1, 0, 0)
+    out[:, :, 2] = nrm * f32(-1)
+    out[:, :, 3] = moved.astype(f32)
+    return out.reshape(-1, 12)
+
+
 def poses_helix(L: float, n: int, radius: float = 0.48, seed: int = 0xC0FFEE) -> np.ndarray:
     """P10k: helix around the cube centre with +-1 mm / +-0.2 deg jitter."""
     g = splitmix64(seed)

@@ -23,6 +23,14 @@ using namespace Eigen;   // the reference's CommonUtilities.hpp names Vector3f u
 #include <Volume.hpp>
 #pragma GCC pop_options
 #include <RayTracingEngine.hpp>
+// The consumers next to the hot path: greedySetCover, positionCamera(s), generateSphere, repositionCamera,
+// optimizeCameraPosition -- the reference's Algorithms.hpp, unmodified.  Its PCL I/O / viewer includes resolve to empty
+// stand-ins and its TransformationUtilities.hpp to a one-function stand-in (oracle/ref_shim); it relies on its drivers
+// having included <numeric> / <iterator> / <iostream> and the engine headers before it.
+#include <numeric>
+#include <iterator>
+#include <iostream>
+#include <Algorithms.hpp>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -165,6 +173,60 @@ double ref_time_views(void* h, const float* K, int H, int W, const float* poses,
     auto t1 = std::chrono::steady_clock::now();
     if (total_out) *total_out = total;
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- Algorithms.hpp -------------------------------------------------------------------------------------------------
+// greedySetCover(candidate_sets) over CSR sets (sorted ids, Algorithms.hpp:38-86).  Returns the number selected.
+long ref_greedy_set_cover(const unsigned long long* ids, const long long* offsets, long n_sets, unsigned long long* selected_out) {
+    Quiet q;
+    std::vector<std::vector<unsigned long long int>> sets(n_sets);
+    for (long i = 0; i < n_sets; i++) sets[i].assign(ids + offsets[i], ids + offsets[i + 1]);
+    auto sel = Algorithms::greedySetCover(sets);
+    std::copy(sel.begin(), sel.end(), selected_out);
+    return (long)sel.size();
+}
+
+// positionCameras(locations, distance) (Algorithms.hpp:282-298 -> positionCamera :190-236): n surface points + normals
+// -> n poses (12 floats each, row-major 3x4).  The normal flip of :286-292 is applied to a private copy.
+void ref_position_cameras(const float* xyz, const float* normals, long n, unsigned distance, float* poses12) {
+    Quiet q;
+    pcl::PointCloud<pcl::PointXYZRGBNormal>::Ptr loc(new pcl::PointCloud<pcl::PointXYZRGBNormal>);
+    for (long i = 0; i < n; i++) {
+        pcl::PointXYZRGBNormal p;
+        p.x = xyz[3 * i]; p.y = xyz[3 * i + 1]; p.z = xyz[3 * i + 2];
+        p.normal[0] = normals[3 * i]; p.normal[1] = normals[3 * i + 1]; p.normal[2] = normals[3 * i + 2];
+        loc->points.push_back(p);
+    }
+    auto cams = Algorithms::positionCameras(loc, distance);
+    for (long i = 0; i < n; i++) for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) poses12[12 * i + 4 * r + c] = cams[i](r, c);
+}
+
+// generateSphere(radius, sphere, transformation, z_threshold, factor) (Algorithms.hpp:88-112).  Returns the number of
+// points generated; writes at most cap of them.
+long ref_generate_sphere(double radius, const float* T12, double z_threshold, double factor, float* xyz_out, long cap) {
+    Quiet q;
+    pcl::PointCloud<pcl::PointXYZRGB>::Ptr sphere(new pcl::PointCloud<pcl::PointXYZRGB>);
+    Algorithms::generateSphere(radius, sphere, pose_from12(T12), z_threshold, factor);
+    const long n = (long)sphere->points.size();
+    for (long i = 0; i < n && i < cap; i++) { xyz_out[3 * i] = sphere->points[i].x; xyz_out[3 * i + 1] = sphere->points[i].y; xyz_out[3 * i + 2] = sphere->points[i].z; }
+    return n;
+}
+
+// repositionCamera(camera, distance) (Algorithms.hpp:180-188 -> moveCamera :170-178)
+void ref_reposition_camera(const float* pose12, unsigned distance, float* out12) {
+    Eigen::Affine3f r = Algorithms::repositionCamera(pose_from12(pose12), distance);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) out12[4 * i + j] = r(i, j);
+}
+
+// optimizeCameraPosition(volume, engine, resolution, camera) (Algorithms.hpp:394-421): the binary search over the stand-off
+// with two reverseRayTrace casts per step.  out12 = the repositioned camera it returns.
+void ref_optimize_camera_position(void* h, const float* K, int H, int W, const float* pose12, float* out12) {
+    Quiet q;
+    std::vector<float> Kv(K, K + 9);
+    Camera cam(Kv, H, W);
+    RayTracingEngine engine(cam);
+    Eigen::Affine3f r = Algorithms::optimizeCameraPosition(*(VoxelVolume*)h, engine, 1, pose_from12(pose12));
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) out12[4 * i + j] = r(i, j);
 }
 
 int ref_max_threads() {

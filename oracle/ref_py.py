@@ -52,6 +52,13 @@ def lib():
         L.ref_time_views.restype = C.c_double
         L.ref_time_views.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, llp]
         L.ref_max_threads.restype = C.c_int
+        L.ref_greedy_set_cover.restype = C.c_long
+        L.ref_greedy_set_cover.argtypes = [u64p, llp, C.c_long, u64p]
+        L.ref_position_cameras.argtypes = [fp, fp, C.c_long, C.c_uint, fp]
+        L.ref_generate_sphere.restype = C.c_long
+        L.ref_generate_sphere.argtypes = [C.c_double, fp, C.c_double, C.c_double, fp, C.c_long]
+        L.ref_reposition_camera.argtypes = [fp, C.c_uint, fp]
+        L.ref_optimize_camera_position.argtypes = [vp, fp, C.c_int, C.c_int, fp, fp]
         _lib = L
     return _lib
 
@@ -128,3 +135,45 @@ def time_views(vol, K, H, W, poses, kind, zdelta, sparse, threads=1):
 
 def max_threads():
     return lib().ref_max_threads()
+
+
+# ---- the reference's Algorithms.hpp (compiled unmodified, see ref_capi.cpp) -------------------------------------------
+def greedy_set_cover(sets):
+    """Algorithms::greedySetCover (Algorithms.hpp:38-86).  sets: list of sorted uint64 arrays -> selected indices in order."""
+    off = np.zeros(len(sets) + 1, np.int64)
+    off[1:] = np.cumsum([len(s) for s in sets])
+    ids = np.concatenate([np.asarray(s, np.uint64) for s in sets]) if len(sets) and off[-1] else np.zeros(1, np.uint64)
+    sel = np.zeros(max(len(sets), 1), np.uint64)
+    n = lib().ref_greedy_set_cover(_p(ids, C.c_ulonglong), _p(off, C.c_longlong), len(sets), _p(sel, C.c_ulonglong))
+    return sel[:n].astype(np.int64)
+
+
+def position_cameras(points, normals, distance=300):
+    """Algorithms::positionCameras(locations, distance) (Algorithms.hpp:282-298) -> (n, 12) float32 poses."""
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3); nrm = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    out = np.zeros((len(pts), 12), np.float32)
+    lib().ref_position_cameras(_p(pts, C.c_float), _p(nrm, C.c_float), len(pts), int(distance), _p(out, C.c_float))
+    return out
+
+
+def generate_sphere(radius, transformation12=None, z_threshold=0.1, factor=10.0):
+    """Algorithms::generateSphere (Algorithms.hpp:88-112) -> (n, 3) float32 points."""
+    T = np.ascontiguousarray(transformation12 if transformation12 is not None else [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32).reshape(12)
+    cap = int((2 * factor + 2) * (factor + 2)) + 16
+    out = np.zeros((cap, 3), np.float32)
+    n = lib().ref_generate_sphere(float(radius), _p(T, C.c_float), float(z_threshold), float(factor), _p(out, C.c_float), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+def reposition_camera(pose12, distance=300):
+    pose = np.ascontiguousarray(pose12, np.float32).reshape(12); out = np.zeros(12, np.float32)
+    lib().ref_reposition_camera(_p(pose, C.c_float), int(distance), _p(out, C.c_float))
+    return out
+
+
+def optimize_camera_position(vol, K, H, W, pose12):
+    """Algorithms::optimizeCameraPosition(volume, engine, res, camera) (Algorithms.hpp:394-421) -> the camera it returns."""
+    K = np.ascontiguousarray(K, np.float32); pose = np.ascontiguousarray(pose12, np.float32).reshape(12); out = np.zeros(12, np.float32)
+    lib().ref_optimize_camera_position(vol.h, _p(K, C.c_float), H, W, _p(pose, C.c_float), _p(out, C.c_float))
+    return out

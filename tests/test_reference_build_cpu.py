@@ -115,3 +115,64 @@ def test_restatement_equals_reference_source_anisotropic_volume(dmf, oracle, ref
     # its float-accumulating loops index voxels_ one past the end (the restatement counts those reads in Counters::oob and
     # treats them as empty), which is undefined behaviour -- the compiled reference segfaults on it.
     assert oracle.reverse(ov, K, H, W, poses[0], fast=False)["counters"]["oob"] > 0
+
+
+# ---- the consumers next to the hot path: the reference's Algorithms.hpp, compiled unmodified ------------------
+def test_greedy_set_cover_equals_reference_source(dmf, oracle, ref):
+    """Algorithms::greedySetCover (Algorithms.hpp:38-86) against the restatement: random sets (ties in size -> lowest index wins,
+    fewer than 5 new ids -> stop, empty sets, duplicates of earlier sets) and the reverse-visible sets of a real sweep."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for n_sets, universe, mean in ((1, 50, 10), (8, 40, 12), (40, 400, 60), (120, 3000, 150), (25, 30, 6)):
+        sets = [np.unique(rng.integers(0, universe, size=max(0, int(rng.normal(mean, mean / 3))))).astype(np.uint64) for _ in range(n_sets)]
+        if n_sets > 3:
+            sets[2] = sets[1].copy(); sets[-1] = np.zeros(0, np.uint64)
+        cases.append(sets)
+    cases.append([np.arange(10, dtype=np.uint64), np.arange(10, 20, dtype=np.uint64), np.arange(5, 15, dtype=np.uint64)])   # equal sizes
+    cases.append([np.arange(4, dtype=np.uint64)])                                                                          # < 5: nothing selected
+    sc = dmf.scenes.scene("S64")
+    ov = oracle.volume_from_scene(sc, flat=False)
+    K = _K(dmf)
+    cases.append([np.sort(oracle.reverse(ov, K, H, W, p, fast=True)["ids"]) for p in dmf.scenes.poses_sphere_lookat(float(sc.bounds[1]), 120)[::6]])
+    n_sel = 0
+    for sets in cases:
+        a, b = oracle.greedy_set_cover(sets), ref.greedy_set_cover(sets)
+        assert np.array_equal(a, b), (len(sets), a, b)
+        n_sel += len(b)
+    assert n_sel > 20
+
+
+def test_pose_generators_equal_reference_source(dmf, ref):
+    """generateSphere (Algorithms.hpp:88-112), positionCameras / positionCamera (:190-236, :282-298) and repositionCamera
+    (:170-188) against the Python mirror's scene helpers, bit for bit."""
+    for factor in (10.0, 24.0):
+        pts = ref.generate_sphere(0.45, z_threshold=-10.0, factor=factor)
+        d = dmf.scenes.sphere_directions(factor)
+        assert len(pts) == len(d)
+        assert np.array_equal(pts, (0.45 * d).astype(np.float32))            # radius * direction in double, stored to float
+    rng = np.random.default_rng(5)
+    p = rng.uniform(-0.4, 1.3, size=(300, 3)).astype(np.float32)
+    n = rng.normal(size=(300, 3)); n /= np.linalg.norm(n, axis=1, keepdims=True)
+    n[:20, 2] = 0.0                                                          # z == 0: flipped (<= 0), the "zero z" branches print only
+    for dist in (300, 457, 600):
+        assert np.array_equal(dmf.scenes.position_cameras(p, n, dist), ref.position_cameras(p, n.astype(np.float32), dist)), dist
+    # repositionCamera: p - Vector3f(third ROW of the linear part) * distance / 1000.0, in float (moveCamera :170-178)
+    for pose in dmf.scenes.poses_sphere_lookat(1.0, 60)[::7]:
+        got = ref.reposition_camera(pose, 450).reshape(3, 4)
+        T = np.asarray(pose, np.float32).reshape(3, 4)
+        nvec = (T[2, :3] * np.float32(450.0)) / np.float32(1000.0)
+        want = T.copy(); want[:, 3] = T[:, 3] - nvec
+        assert np.array_equal(got, want)
+
+
+def test_optimize_camera_position_equals_reference_source(dmf, oracle, ref):
+    """Algorithms::optimizeCameraPosition(volume, engine, res, camera) (Algorithms.hpp:394-421): the stand-off binary search
+    with two reverseRayTrace casts per step, on a dyadic scene (where the full-grid scan stays in bounds)."""
+    sc = dmf.scenes.scene("S64")
+    K = _K(dmf)
+    ov, rv = oracle.volume_from_scene(sc, flat=False), ref.volume_from_scene(sc)
+    L = float(sc.bounds[1])
+    for p in list(dmf.scenes.poses_position_camera(L, 40)[[3, 17]]) + [dmf.scenes.poses_sphere_lookat(L, 60)[21]]:
+        mid, want = oracle.optimize_standoff(ov, K, H, W, p)
+        got = ref.optimize_camera_position(rv, K, H, W, p)
+        assert np.array_equal(got, want), (mid, got, want)
