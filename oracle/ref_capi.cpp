@@ -31,6 +31,7 @@ using namespace Eigen;   // the reference's CommonUtilities.hpp names Vector3f u
 #include <iterator>
 #include <iostream>
 #include <Algorithms.hpp>
+#include <FileRoutines.hpp>   // read/writeCameraLocations: the pose-file wire format
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -227,6 +228,20 @@ void ref_optimize_camera_position(void* h, const float* K, int H, int W, const f
     RayTracingEngine engine(cam);
     Eigen::Affine3f r = Algorithms::optimizeCameraPosition(*(VoxelVolume*)h, engine, 1, pose_from12(pose12));
     for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) out12[4 * i + j] = r(i, j);
+}
+
+// ---- FileRoutines.hpp: the camera-pose text files the drivers exchange (:69-112) ------------------------------------------
+void ref_write_camera_locations(const char* filename, const float* poses12, long n) {
+    std::vector<Eigen::Affine3f> T;
+    for (long i = 0; i < n; i++) T.push_back(pose_from12(poses12 + 12 * i));
+    writeCameraLocations(filename, T);
+}
+// returns the number of poses in the file; writes at most cap of them
+long ref_read_camera_locations(const char* filename, float* poses12, long cap) {
+    Quiet q;
+    auto T = readCameraLocations(filename);
+    for (long i = 0; i < (long)T.size() && i < cap; i++) for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) poses12[12 * i + 4 * r + c] = T[i](r, c);
+    return (long)T.size();
 }
 
 int ref_max_threads() {

@@ -59,6 +59,9 @@ def lib():
         L.ref_generate_sphere.argtypes = [C.c_double, fp, C.c_double, C.c_double, fp, C.c_long]
         L.ref_reposition_camera.argtypes = [fp, C.c_uint, fp]
         L.ref_optimize_camera_position.argtypes = [vp, fp, C.c_int, C.c_int, fp, fp]
+        L.ref_write_camera_locations.argtypes = [C.c_char_p, fp, C.c_long]
+        L.ref_read_camera_locations.restype = C.c_long
+        L.ref_read_camera_locations.argtypes = [C.c_char_p, fp, C.c_long]
         _lib = L
     return _lib
 
@@ -177,3 +180,16 @@ def optimize_camera_position(vol, K, H, W, pose12):
     K = np.ascontiguousarray(K, np.float32); pose = np.ascontiguousarray(pose12, np.float32).reshape(12); out = np.zeros(12, np.float32)
     lib().ref_optimize_camera_position(vol.h, _p(K, C.c_float), H, W, _p(pose, C.c_float), _p(out, C.c_float))
     return out
+
+
+# ---- the reference's FileRoutines.hpp: camera-pose text files (:69-112) -------------------------------------------------
+def write_camera_locations(filename, poses):
+    a = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
+    lib().ref_write_camera_locations(str(filename).encode(), _p(a, C.c_float), len(a))
+
+
+def read_camera_locations(filename, cap=4096):
+    out = np.zeros((cap, 12), np.float32)
+    n = lib().ref_read_camera_locations(str(filename).encode(), _p(out, C.c_float), cap)
+    assert n <= cap
+    return out[:n].copy()

@@ -176,3 +176,20 @@ def test_optimize_camera_position_equals_reference_source(dmf, oracle, ref):
         mid, want = oracle.optimize_standoff(ov, K, H, W, p)
         got = ref.optimize_camera_position(rv, K, H, W, p)
         assert np.array_equal(got, want), (mid, got, want)
+
+
+def test_pose_file_wire_format_equals_reference_source(dmf, ref, tmp_path):
+    """writeCameraLocations / readCameraLocations (FileRoutines.hpp:69-112) against dmf_b200/posefile.py: the same bytes on
+    disk for the same poses, and each side reads the other's file to the same floats."""
+    from dmf_b200.posefile import read_camera_locations, write_camera_locations
+    rng = np.random.default_rng(3)
+    poses = np.concatenate([dmf.scenes.poses_sphere_lookat(1.0, 40)[::5], dmf.scenes.poses_position_camera(1.0, 6),
+                            (rng.normal(size=(6, 12)) * 10.0 ** rng.integers(-8, 7, size=(6, 12))).astype(np.float32)])
+    poses[0, :4] = [0.0, -0.0, 1e-7, 123456789.0]
+    a, b = tmp_path / "ours.txt", tmp_path / "ref.txt"
+    write_camera_locations(str(a), poses)
+    ref.write_camera_locations(b, poses)
+    assert a.read_bytes() == b.read_bytes()
+    ours_of_ref, ref_of_ours = read_camera_locations(str(b)), ref.read_camera_locations(a)
+    assert np.array_equal(ours_of_ref, ref_of_ours) and ours_of_ref.shape == (len(poses), 12)
+    assert np.allclose(ours_of_ref, poses, rtol=1e-5, atol=0)          # 6 significant digits survive the text format
