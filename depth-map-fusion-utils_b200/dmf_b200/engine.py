@@ -369,6 +369,31 @@ def optimizeCameraPosition(volume: VoxelVolume, engine: "RayTracingEngine", came
     return mid, out
 
 
+def reposition_from_minimum(cameras, nearest_mm) -> np.ndarray:
+    """The arithmetic of repositionCamerasSampled (tests/CameraPathGen.cpp:113-121), float for float: with bz = the camera's
+    z column and p = its translation, intersection = p + bz * float(double(float(nearest)) / 1000.0), new p = intersection -
+    bz * float(0.3); cameras whose cast found nothing (nearest == -1) are returned unchanged (:108-113)."""
+    f32 = np.float32
+    T = _poses12(cameras).reshape(-1, 3, 4).copy()
+    near = np.asarray(nearest_mm, np.int64).reshape(-1)
+    s = (near.astype(f32).astype(np.float64) / 1000.0).astype(f32)          # Vector3f * double narrows the scalar to float
+    bz, p = T[:, :, 2], T[:, :, 3]
+    inter = p + bz * s[:, None]
+    new_p = inter - bz * f32(0.3)
+    hit = near != -1
+    T[hit, :, 3] = new_p[hit]
+    return T.reshape(-1, 12)
+
+
+def repositionCamerasSampled(cameras, volume: VoxelVolume, engine: "RayTracingEngine") -> np.ndarray:
+    """repositionCamerasSampled(cameras, volume, cam) of the reference driver (tests/CameraPathGen.cpp:94-126) for a batch:
+    one rayTraceAndGetMinimum cast per camera (zdelta = 1, sparse: its defaults), then every camera that hit something is
+    moved to 0.3 m in front of the nearest hit along its optical axis.  Returns (n, 12) poses."""
+    poses = _poses12(cameras)
+    r = engine.forward_views(volume, poses, MODE_MINIMUM, 1, True, want=())
+    return reposition_from_minimum(poses, r["min_depth"])
+
+
 def greedySetCover(candidate_bitsets: np.ndarray, ctx: Optional[Context] = None) -> np.ndarray:
     """Algorithms::greedySetCover (Algorithms.hpp:38-86) over visibility bitsets [n_sets][words]."""
     ctx = ctx or Context.default()

@@ -1,7 +1,8 @@
 // DmfAlgorithms.hpp -- batched B200 replacements for the ray-marching helpers the reference keeps OUTSIDE
 // RayTracingEngine: the driver-local willCollide() (tests/CameraPathGen.cpp:128-156, CameraMotionTSP.cpp:236-261,
 // CameraMotionPlanner.cpp:246-271), the setCover() drivers (tests/SetCover.cpp:214-244, CameraPathGen.cpp:158-186) and
-// Algorithms::optimizeCameraPosition(volume, engine, res, Affine3f) (include/Algorithms.hpp:394-421).
+// Algorithms::optimizeCameraPosition(volume, engine, res, Affine3f) (include/Algorithms.hpp:394-421) and the driver-local
+// repositionCamerasSampled() (tests/CameraPathGen.cpp:94-126).
 //
 // Same argument lists and results as the functions they replace (minus the stdout chatter), so a driver swaps
 //     if (willCollide(volume, a, b) == true)          ->   if (dmf_dropin::willCollide(volume, a, b) == true)
@@ -78,6 +79,36 @@ template <class Volume>
 inline Eigen::Affine3f optimizeCameraPosition(Volume& volume, RayTracingEngine engine, int /*resolution_single_dimension*/, Eigen::Affine3f camera)
 {
     return optimizeCameraPositions(volume, engine, std::vector<Eigen::Affine3f>{camera})[0];
+}
+
+// vector<Affine3f> repositionCamerasSampled(vector<Affine3f> cameras, VoxelVolume& volume, Camera cam)
+// (tests/CameraPathGen.cpp:94-126): rayTraceAndGetMinimum for every camera as ONE batched cast (zdelta = 1, sparse: the
+// defaults the driver uses), then the driver's own arithmetic per camera -- 0.3 m back from the nearest hit along the optical
+// axis; a camera that hits nothing keeps its place.
+template <class Volume>
+inline std::vector<Eigen::Affine3f> repositionCamerasSampled(const std::vector<Eigen::Affine3f>& cameras, Volume& volume, Camera cam)
+{
+    const size_t n = cameras.size();
+    std::vector<Eigen::Affine3f> new_locations(cameras);
+    if (!n) return new_locations;
+    dmf_ctx* ctx = sync(cam, volume);
+    std::vector<float> poses(12 * n);
+    for (size_t i = 0; i < n; i++) pose12(cameras[i], &poses[12 * i]);
+    std::vector<int32_t> nearest(n, -1);
+    dmf_forward_params p = {DMF_MODE_MINIMUM, 1, 1, 1, DMF_GRID_BIT, 0};
+    dmf_forward_out out = {};
+    out.min_depth = nearest.data();
+    must(dmf_forward(ctx, &p, poses.data(), (int)n, &out), "dmf_forward");
+    for (size_t i = 0; i < n; i++) {
+        if (nearest[i] == -1) continue;                                       // CameraPathGen.cpp:108-113
+        const Eigen::Affine3f& camera = cameras[i];
+        Eigen::Vector3f bz(camera(0,2), camera(1,2), camera(2,2));
+        Eigen::Vector3f current_pt(camera(0,3), camera(1,3), camera(2,3));
+        Eigen::Vector3f intersection_pt = current_pt + bz*(float(nearest[i])/1000.0);      // :116, scalar narrowed to float by Eigen
+        Eigen::Vector3f new_point = intersection_pt - bz*(0.3);                             // :117
+        for (int k = 0; k < 3; k++) new_locations[i](k,3) = new_point(k);
+    }
+    return new_locations;
 }
 
 // vector<unsigned long long int> setCover(RayTracingEngine engine, VoxelVolume& volume, vector<Affine3f> camera_locations,

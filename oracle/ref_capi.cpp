@@ -31,7 +31,15 @@ using namespace Eigen;   // the reference's CommonUtilities.hpp names Vector3f u
 #include <iterator>
 #include <iostream>
 #include <Algorithms.hpp>
-#include <FileRoutines.hpp>   // read/writeCameraLocations: the pose-file wire format
+// (FileRoutines.hpp -- read/writeCameraLocations, the pose-file wire format of SURVEY 8f-4 -- arrives through the driver below)
+// The driver tests/CameraPathGen.cpp itself, for the three functions it defines next to the path: willCollide (:128-156),
+// repositionCamerasSampled (:94-126) and setCover (:158-181).  Its viewer / TSP / PCL-filter headers resolve to stand-ins in
+// oracle/ref_shim, and its main() is renamed away.
+#include <climits>
+#include <mutex>
+#define main ref_unused_camerapathgen_main
+#include <CameraPathGen.cpp>
+#undef main
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -242,6 +250,36 @@ long ref_read_camera_locations(const char* filename, float* poses12, long cap) {
     auto T = readCameraLocations(filename);
     for (long i = 0; i < (long)T.size() && i < cap; i++) for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) poses12[12 * i + 4 * r + c] = T[i](r, c);
     return (long)T.size();
+}
+
+// ---- tests/CameraPathGen.cpp: the driver's own helpers next to the path -------------------------------------------------------
+// willCollide(volume, a, b) (:128-156): 1 mm float march from a towards b, true at the first occupied voxel
+int ref_will_collide(void* h, const float* a, const float* b) {
+    Quiet q;
+    return willCollide(*(VoxelVolume*)h, Eigen::Vector3f(a[0], a[1], a[2]), Eigen::Vector3f(b[0], b[1], b[2])) ? 1 : 0;
+}
+// repositionCamerasSampled(cameras, volume, cam) (:94-126): rayTraceAndGetMinimum per camera, then 0.3 m back from the hit
+void ref_reposition_cameras_sampled(void* h, const float* K, int H, int W, const float* poses12, long n, float* out12) {
+    Quiet q;
+    std::vector<float> Kv(K, K + 9);
+    Camera cam(Kv, H, W);
+    std::vector<Eigen::Affine3f> cams;
+    for (long i = 0; i < n; i++) cams.push_back(pose_from12(poses12 + 12 * i));
+    scrub_stack();
+    auto out = repositionCamerasSampled(cams, *(VoxelVolume*)h, cam);
+    for (long i = 0; i < n; i++) for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) out12[12 * i + 4 * r + c] = out[i](r, c);
+}
+// setCover(engine, volume, camera_locations, resolution, sparse) (:158-181): reverseRayTraceFast per camera, sort, greedySetCover
+long ref_set_cover(void* h, const float* K, int H, int W, const float* poses12, long n, unsigned long long* selected_out) {
+    Quiet q;
+    std::vector<float> Kv(K, K + 9);
+    Camera cam(Kv, H, W);
+    RayTracingEngine engine(cam);
+    std::vector<Eigen::Affine3f> cams;
+    for (long i = 0; i < n; i++) cams.push_back(pose_from12(poses12 + 12 * i));
+    auto sel = setCover(engine, *(VoxelVolume*)h, cams, 1, false);
+    std::copy(sel.begin(), sel.end(), selected_out);
+    return (long)sel.size();
 }
 
 int ref_max_threads() {

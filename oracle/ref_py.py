@@ -59,6 +59,11 @@ def lib():
         L.ref_generate_sphere.argtypes = [C.c_double, fp, C.c_double, C.c_double, fp, C.c_long]
         L.ref_reposition_camera.argtypes = [fp, C.c_uint, fp]
         L.ref_optimize_camera_position.argtypes = [vp, fp, C.c_int, C.c_int, fp, fp]
+        L.ref_will_collide.restype = C.c_int
+        L.ref_will_collide.argtypes = [vp, fp, fp]
+        L.ref_reposition_cameras_sampled.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_long, fp]
+        L.ref_set_cover.restype = C.c_long
+        L.ref_set_cover.argtypes = [vp, fp, C.c_int, C.c_int, fp, C.c_long, u64p]
         L.ref_write_camera_locations.argtypes = [C.c_char_p, fp, C.c_long]
         L.ref_read_camera_locations.restype = C.c_long
         L.ref_read_camera_locations.argtypes = [C.c_char_p, fp, C.c_long]
@@ -193,3 +198,23 @@ def read_camera_locations(filename, cap=4096):
     n = lib().ref_read_camera_locations(str(filename).encode(), _p(out, C.c_float), cap)
     assert n <= cap
     return out[:n].copy()
+
+
+# ---- the reference's driver tests/CameraPathGen.cpp (compiled with its main renamed away) -------------------------------
+def will_collide(vol, a, b):
+    a = np.ascontiguousarray(a, np.float32).reshape(3); b = np.ascontiguousarray(b, np.float32).reshape(3)
+    return bool(lib().ref_will_collide(vol.h, _p(a, C.c_float), _p(b, C.c_float)))
+
+
+def reposition_cameras_sampled(vol, K, H, W, poses):
+    K = np.ascontiguousarray(K, np.float32); poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
+    out = np.zeros_like(poses)
+    lib().ref_reposition_cameras_sampled(vol.h, _p(K, C.c_float), H, W, _p(poses, C.c_float), len(poses), _p(out, C.c_float))
+    return out
+
+
+def set_cover(vol, K, H, W, poses):
+    K = np.ascontiguousarray(K, np.float32); poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 12)
+    sel = np.zeros(max(len(poses), 1), np.uint64)
+    n = lib().ref_set_cover(vol.h, _p(K, C.c_float), H, W, _p(poses, C.c_float), len(poses), _p(sel, C.c_ulonglong))
+    return sel[:n].astype(np.int64)

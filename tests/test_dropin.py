@@ -65,6 +65,15 @@ def test_dropin_headers_compile_and_link(driver):
     assert r.returncode != 0
 
 
+def test_dmf_algorithms_templates_instantiate():
+    """CPU tier: every template of DmfAlgorithms.hpp (willCollide, collisionMatrix, optimizeCameraPosition(s),
+    repositionCamerasSampled, setCover) instantiates with the reference's argument types -- compile only."""
+    cmd = [GXX, "-std=c++17", "-fsyntax-only", "-I", os.path.join(PKG, "dropin"), "-I", os.path.join(PKG, "dropin", "compat"),
+           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "dropin_compile_only.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 @pytest.mark.gpu
 def test_dropin_matches_oracle(driver, dmf, oracle, tmp_path):
     sc = dmf.scenes.scene("S64")

@@ -193,3 +193,55 @@ def test_pose_file_wire_format_equals_reference_source(dmf, ref, tmp_path):
     ours_of_ref, ref_of_ours = read_camera_locations(str(b)), ref.read_camera_locations(a)
     assert np.array_equal(ours_of_ref, ref_of_ours) and ours_of_ref.shape == (len(poses), 12)
     assert np.allclose(ours_of_ref, poses, rtol=1e-5, atol=0)          # 6 significant digits survive the text format
+
+
+# ---- the reference's driver tests/CameraPathGen.cpp, compiled with its main() renamed away -----------------------------------
+def test_will_collide_equals_reference_source(dmf, oracle, ref):
+    """willCollide(volume, a, b) (tests/CameraPathGen.cpp:128-156): segments through, beside, into, out of and entirely outside
+    the volume, zero-length and axis-parallel ones, on a dyadic and on the anisotropic off-origin volume."""
+    from tests.test_forward_gpu import _aniso_scene
+    rng = np.random.default_rng(23)
+    n_hit = 0
+    for sc in (dmf.scenes.scene("S64"), dmf.scenes.scene("S128-clutter"), _aniso_scene(dmf)):
+        ov, rv = oracle.volume_from_scene(sc, flat=False), ref.volume_from_scene(sc)
+        lo, hi = np.asarray(sc.bounds[0::2]), np.asarray(sc.bounds[1::2])
+        ext = hi - lo
+        a = rng.uniform(lo - 0.2 * ext, hi + 0.2 * ext, size=(160, 3)).astype(np.float32)
+        b = rng.uniform(lo - 0.2 * ext, hi + 0.2 * ext, size=(160, 3)).astype(np.float32)
+        b[:8] = a[:8]                                                   # zero length: v = (b-a).normalized() stays 0
+        b[8:16, 1:] = a[8:16, 1:]                                       # parallel to x
+        a[16:24] = (lo - 0.3 * ext).astype(np.float32); b[16:24] = (lo - 0.1 * ext).astype(np.float32)   # never inside
+        for p, q in zip(a, b):
+            want, _ = oracle.will_collide(ov, p, q, guard_coords=True)
+            got = ref.will_collide(rv, p, q)
+            assert got == want, (sc.name, p, q)
+            n_hit += int(got)
+    assert n_hit > 20
+
+
+def test_reposition_cameras_sampled_equals_reference_source(dmf, oracle, ref):
+    """repositionCamerasSampled (tests/CameraPathGen.cpp:94-126) against the mirror's arithmetic fed with the restatement's
+    rayTraceAndGetMinimum (zdelta 1, sparse: the defaults the driver uses), incl. a camera that sees nothing."""
+    sc = dmf.scenes.scene("S64")
+    K = _K(dmf)
+    ov, rv = oracle.volume_from_scene(sc, flat=False), ref.volume_from_scene(sc)
+    L = float(sc.bounds[1])
+    poses = np.concatenate([dmf.scenes.poses_sphere_lookat(L, 90)[::9], dmf.scenes.poses_position_camera(L, 12)[::3],
+                            dmf.scenes.look_at([0.5 * L, 0.5 * L, 0.9 * L], [0.5 * L, 0.5 * L, 2.0 * L])[None, :]])      # looks away
+    near = np.array([oracle.forward(ov, K, H, W, p, oracle.MODE_MINIMUM, 1, True, want_pixels=False)["min_depth"] for p in poses])
+    assert (near == -1).any() and (near > 0).sum() >= 8
+    got = ref.reposition_cameras_sampled(rv, K, H, W, poses)
+    assert np.array_equal(got, dmf.reposition_from_minimum(poses, near))
+
+
+def test_driver_set_cover_equals_reference_source(dmf, oracle, ref):
+    """setCover(engine, volume, cameras, res, false) (tests/CameraPathGen.cpp:158-181): reverseRayTraceFast per camera, sorted
+    ids, greedySetCover -- the pipeline examples/view_selection.py and DmfAlgorithms.hpp::setCover run on the GPU."""
+    sc = dmf.scenes.scene("S64")
+    K = _K(dmf)
+    ov, rv = oracle.volume_from_scene(sc, flat=False), ref.volume_from_scene(sc)
+    poses = dmf.scenes.poses_sphere_lookat(float(sc.bounds[1]), 160)[::8]
+    sets = [np.sort(oracle.reverse(ov, K, H, W, p, fast=True)["ids"]) for p in poses]
+    want = oracle.greedy_set_cover(sets)
+    got = ref.set_cover(rv, K, H, W, poses)
+    assert np.array_equal(got, want) and len(got) >= 3
