@@ -245,3 +245,19 @@ def test_driver_set_cover_equals_reference_source(dmf, oracle, ref):
     want = oracle.greedy_set_cover(sets)
     got = ref.set_cover(rv, K, H, W, poses)
     assert np.array_equal(got, want) and len(got) >= 3
+
+
+def test_reposition_cameras_sampled_glue(dmf):
+    """dmf_b200.repositionCamerasSampled = one batched MODE_MINIMUM cast (zdelta 1, sparse) + reposition_from_minimum."""
+    calls = []
+
+    class FakeEngine:
+        def forward_views(self, volume, poses, mode, zdelta, sparse, view_id0=1, want=(), carve=False):
+            calls.append((mode, zdelta, sparse, tuple(want), len(poses)))
+            return {"min_depth": np.array([250, -1, 731], np.int32), "found_any": np.array([1, 0, 1], np.int32)}
+
+    poses = dmf.scenes.poses_sphere_lookat(1.0, 30)[::10]
+    out = dmf.repositionCamerasSampled(poses, object(), FakeEngine())
+    assert calls == [(dmf.MODE_MINIMUM, 1, True, (), 3)]
+    assert np.array_equal(out, dmf.reposition_from_minimum(poses, [250, -1, 731]))
+    assert np.array_equal(out[1], np.asarray(poses[1], np.float32)) and not np.array_equal(out[0], np.asarray(poses[0], np.float32))

@@ -227,3 +227,19 @@ def test_reverse_anisotropic_offset_volume(dmf, oracle, ctx):
     b = np.random.default_rng(3).uniform(-0.4, 1.0, size=(64, 3)).astype(np.float32)
     got = dmf.willCollide(ctx, gv, a, b, True)
     assert np.array_equal(got, np.array([oracle.will_collide(ov, a[i], b[i], True)[0] for i in range(64)]))
+
+
+def test_reposition_cameras_sampled_batched(dmf, oracle, ctx):
+    """repositionCamerasSampled (tests/CameraPathGen.cpp:94-126) as one batched minimum cast: equals the per-camera
+    restatement (whose arithmetic tests/test_reference_build_cpu.py pins to the reference's compiled driver)."""
+    sc = dmf.scenes.scene("S64")
+    ov = oracle.volume_from_scene(sc, flat=True)
+    gv = dmf.VoxelVolume(ctx)
+    gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+    K = dmf.scenes.REFERENCE_K
+    L = float(sc.bounds[1])
+    poses = np.concatenate([dmf.scenes.poses_sphere_lookat(L, 90)[::9], dmf.scenes.look_at([0.5 * L, 0.5 * L, 0.9 * L], [0.5 * L, 0.5 * L, 2.0 * L])[None, :]])
+    near = [oracle.forward(ov, K, 480, 640, p, oracle.MODE_MINIMUM, 1, True, want_pixels=False)["min_depth"] for p in poses]
+    got = dmf.repositionCamerasSampled(poses, gv, dmf.RayTracingEngine(dmf.Camera(K), ctx))
+    assert np.array_equal(got, dmf.reposition_from_minimum(poses, near))
+    assert near[-1] == -1 and np.array_equal(got[-1], np.asarray(poses[-1], np.float32))
