@@ -13,7 +13,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "liboracle_dmf.so")
+# DMF_ORACLE_LIB: another build of the same library (the ASan/UBSan build of `make -C oracle asan`); default = in-tree
+_LIB = os.environ.get("DMF_ORACLE_LIB") or os.path.join(_HERE, "liboracle_dmf.so")
 
 MODE_POINTS, MODE_GOOD_POINTS, MODE_CLASSIFY, MODE_MARK, MODE_MINIMUM = range(5)
 
@@ -21,6 +22,8 @@ MODE_POINTS, MODE_GOOD_POINTS, MODE_CLASSIFY, MODE_MARK, MODE_MINIMUM = range(5)
 def build(force: bool = False) -> str:
     src = [os.path.join(_HERE, f) for f in ("dmf_oracle_capi.cpp", "dmf_oracle.hpp", "Makefile")]
     stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in src)
+    if os.environ.get("DMF_ORACLE_LIB"):
+        return _LIB                                  # a prebuilt variant: never rebuilt from here
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB
