@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "_ref", "libref_dmf.so")
+_LIB = os.environ.get("DMF_REF_LIB") or os.path.join(_HERE, "_ref", "libref_dmf.so")      # DMF_REF_LIB: e.g. an ASan build
 REF_TREE = os.environ.get("DMF_REFERENCE_TREE", "/root/reference")
 
 
