@@ -71,11 +71,12 @@ int dmf_reverse_dev(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_v
     DMF_CUDA(cudaSetDevice(c->device));
     if (d_out->ids || d_out->ids_offsets) return fail("dmf_reverse_dev does not produce id lists; use dmf_reverse or the visibility bitset");
     cudaStream_t st = pick_stream(c, stream);
+    DMF_TRY(order_after_previous(c, st));
     DMF_CUDA(cudaEventRecord(c->ev_k0, st));
     DMF_TRY(enqueue_reverse(c, fast, viz, d_poses, n_views, (unsigned*)d_out->visibility, (unsigned*)d_out->unoccluded, d_out->found_any, nullptr, nullptr, 0, st));
     DMF_CUDA(cudaEventRecord(c->ev_k1, st));
     c->timed = true;
-    return 0;
+    return mark_last(c, st);
 }
 
 int dmf_reverse(dmf_ctx* c, int fast, int viz, const float* poses, int n_views, const dmf_reverse_out* out) {
@@ -86,6 +87,7 @@ int dmf_reverse(dmf_ctx* c, int fast, int viz, const float* poses, int n_views, 
     const bool want_ids = out->ids_offsets != nullptr;
     if (want_ids) out->ids_offsets[0] = 0;
     cudaStream_t st = c->stream;
+    DMF_TRY(order_after_previous(c, st));
     const unsigned emit_cap = (unsigned)std::min<size_t>(2 * c->n_occ + 64, 0x7fffffffu);
     size_t per_view = 48 + 2 * vw * 8 + 16 + (want_ids ? (fast ? c->n_occ * 4 : (size_t)emit_cap * 16) : 0);
     int chunk = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n_views, (size_t)4096, ((size_t)1 << 30) / per_view}));
@@ -191,53 +193,30 @@ int dmf_zbuffer(dmf_ctx* c, const float pose[12], int32_t* depth, int64_t* n_spl
     return 0;
 }
 
-namespace {
-// exclusive scan of d_in[0..n) into d_out (may alias d_in); *total (host) receives the sum.  Synchronises the stream.
-int device_exclusive_scan(dmf_ctx* c, cudaStream_t st, const unsigned* d_in, unsigned* d_out, size_t n, unsigned* total) {
-    if (n == 0) { if (total) *total = 0; return 0; }
-    const size_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    DevBuf sums, sums_scanned;
-    DMF_TRY(sums.reserve(nb * 4)); DMF_TRY(sums_scanned.reserve(nb * 4));
-    k_scan_block<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, d_out, n, sums.as<unsigned>());
-    c->launches++;
-    int rc = 0;
-    unsigned tot = 0;
-    if (nb > 1) {
-        rc = device_exclusive_scan(c, st, sums.as<unsigned>(), sums_scanned.as<unsigned>(), nb, &tot);
-        if (!rc) { k_scan_add<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_out, n, sums_scanned.as<unsigned>()); c->launches++; }
-    } else {
-        if (cudaMemcpyAsync(&tot, sums.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail("scan: copy of the total failed");
-    }
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (!rc && e != cudaSuccess) rc = fail("device scan failed: %s", cudaGetErrorString(e));
-    if (!rc) { e = cudaGetLastError(); if (e != cudaSuccess) rc = fail("device scan failed: %s", cudaGetErrorString(e)); }
-    sums.release(); sums_scanned.release();
-    if (total) *total = tot;
-    return rc;
-}
-}  // namespace
-
 // setDimensions + setVolumeSize + constructVolume + integratePointCloud(cloud, normals) with the integration on the GPU
-// (dmf_integrate.cuh).  Same result as dmf_volume_from_points: occupied_cells_ in first-insertion order, normals per
-// voxel in point order.
+// (dmf_integrate.cuh) and the march structures built from its output where it lies (dmf_volume.cuh): the only host
+// traffic is the point cloud in and two counts out.  Same result as dmf_volume_from_points: occupied_cells_ in
+// first-insertion order, normals per voxel in point order.
 int dmf_volume_from_points_gpu(dmf_ctx* c, const double bounds[6], const int dims[3], const float* xyz, const float* normals, size_t n) {
     if (!c || !bounds || !dims || (!xyz && n > 0)) return fail("null argument");
     DMF_CUDA(cudaSetDevice(c->device));
     DMF_CUDA(cudaDeviceSynchronize());
     if (n >= 0xFFFFFFFFull) return fail("too many points for 32-bit point indices");
+    for (int a = 0; a < 3; a++) if (dims[a] < 1) return fail("bad dims");
     HostVolume hv;
     hv.construct(bounds, dims);
-    // geometry first (an empty upload fills VolDev's constants: bounds, reciprocals, float thresholds, padded dims)
-    DMF_TRY(upload_volume(c, bounds, hv.delta, hv.dim, nullptr, 0, nullptr, nullptr));
-    if (n == 0) return 0;
+    DMF_TRY(set_volume_geometry(c, bounds, hv.delta, hv.dim));
+    c->vol_set = false; c->mirror_valid = false;
     cudaStream_t st = c->stream;
-    const VolDev v = c->vol;
+    const VolDev v = c->vol;                                       // scalars only are used by the K0 kernels
     const size_t ncell = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
-    DevBuf d_xyz, d_nrm, d_key, d_first, d_flag, d_ord, d_ids, d_cnt, d_noff, d_cur, d_pidx, d_out;
-    auto cleanup = [&]() { for (DevBuf* b : {&d_xyz, &d_nrm, &d_key, &d_first, &d_flag, &d_ord, &d_ids, &d_cnt, &d_noff, &d_cur, &d_pidx, &d_out}) b->release(); };
+    DevBuf d_xyz, d_nrm, d_key, d_first, d_flag, d_ord, d_cnt, d_cur, d_pidx;
+    auto cleanup = [&]() { for (DevBuf* b : {&d_xyz, &d_nrm, &d_key, &d_first, &d_flag, &d_ord, &d_cnt, &d_cur, &d_pidx}) b->release(); };
     int rc = 0;
-    std::vector<uint64_t> h_ids; std::vector<uint32_t> h_noff; std::vector<float> h_nrm;
+    unsigned n_occ = 0, n_nrm = 0;
     do {
+        if ((rc = c->d_err.reserve(16))) break;
+        if (n == 0) break;
         if ((rc = d_xyz.reserve(n * 12)) || (rc = d_key.reserve(n * 4)) || (rc = d_first.reserve(ncell * 4)) || (rc = d_flag.reserve(n * 4)) || (rc = d_ord.reserve(n * 4))) break;
         if (cudaMemcpyAsync(d_xyz.p, xyz, n * 12, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail("H2D of the points failed"); break; }
         const unsigned g = blocks_for(n, 256, 148 * 16);
@@ -246,39 +225,38 @@ int dmf_volume_from_points_gpu(dmf_ctx* c, const double bounds[6], const int dim
         k_pt_first<<<g, 256, 0, st>>>(d_key.as<unsigned>(), n, d_first.as<unsigned>());
         k_pt_flag<<<g, 256, 0, st>>>(d_key.as<unsigned>(), d_first.as<unsigned>(), n, d_flag.as<unsigned>());
         c->launches += 3;
-        unsigned n_occ = 0;
-        if ((rc = device_exclusive_scan(c, st, d_flag.as<unsigned>(), d_ord.as<unsigned>(), n, &n_occ))) break;
+        if ((rc = scan_u32_async(c, st, d_flag.as<unsigned>(), d_ord.as<unsigned>(), n, c->d_err.as<unsigned>()))) break;
+        if (cudaMemcpyAsync(&n_occ, c->d_err.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = fail("device integratePointCloud failed (occupied count)"); break; }
         if (n_occ == 0) break;
-        if ((rc = d_ids.reserve((size_t)n_occ * 8))) break;
-        k_pt_assign<<<g, 256, 0, st>>>(v, d_key.as<unsigned>(), d_flag.as<unsigned>(), d_ord.as<unsigned>(), n, d_first.as<unsigned>(), d_ids.as<u64>());
+        if ((rc = c->d_occ_ids.reserve((size_t)n_occ * 8))) break;
+        k_pt_assign<<<g, 256, 0, st>>>(v, d_key.as<unsigned>(), d_flag.as<unsigned>(), d_ord.as<unsigned>(), n, d_first.as<unsigned>(), c->d_occ_ids.as<u64>());
         c->launches++;
-        h_ids.resize(n_occ); h_noff.assign((size_t)n_occ + 1, 0);
         if (normals) {
-            if ((rc = d_nrm.reserve(n * 12)) || (rc = d_cnt.reserve(((size_t)n_occ + 1) * 4)) || (rc = d_noff.reserve(((size_t)n_occ + 1) * 4)) || (rc = d_cur.reserve((size_t)n_occ * 4))) break;
+            if ((rc = d_nrm.reserve(n * 12)) || (rc = d_cnt.reserve(((size_t)n_occ + 1) * 4)) || (rc = c->d_noff.reserve(((size_t)n_occ + 1) * 4)) || (rc = d_cur.reserve((size_t)n_occ * 4))) break;
             if (cudaMemcpyAsync(d_nrm.p, normals, n * 12, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = fail("H2D of the normals failed"); break; }
             cudaMemsetAsync(d_cnt.p, 0, ((size_t)n_occ + 1) * 4, st); cudaMemsetAsync(d_cur.p, 0, (size_t)n_occ * 4, st);
             k_pt_count<<<g, 256, 0, st>>>(d_key.as<unsigned>(), d_first.as<unsigned>(), n, d_cnt.as<unsigned>());
             c->launches++;
-            unsigned n_nrm = 0;
-            if ((rc = device_exclusive_scan(c, st, d_cnt.as<unsigned>(), d_noff.as<unsigned>(), (size_t)n_occ + 1, &n_nrm))) break;
-            if ((rc = d_pidx.reserve(std::max<size_t>(n_nrm, 1) * 4)) || (rc = d_out.reserve(std::max<size_t>(n_nrm, 1) * 12))) break;
-            k_pt_scatter<<<g, 256, 0, st>>>(d_key.as<unsigned>(), d_first.as<unsigned>(), d_noff.as<unsigned>(), n, d_cur.as<unsigned>(), d_pidx.as<unsigned>());
-            k_seg_sort<<<(n_occ + 127) / 128, 128, 0, st>>>(d_noff.as<unsigned>(), n_occ, d_pidx.as<unsigned>());
-            k_gather_normals<<<blocks_for(n_nrm, 256, 148 * 16), 256, 0, st>>>(d_pidx.as<unsigned>(), d_nrm.as<float>(), n_nrm, d_out.as<float>());
+            if ((rc = scan_u32_async(c, st, d_cnt.as<unsigned>(), c->d_noff.as<unsigned>(), (size_t)n_occ + 1, c->d_err.as<unsigned>()))) break;
+            if (cudaMemcpyAsync(&n_nrm, c->d_err.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = fail("device integratePointCloud failed (normal count)"); break; }
+            if ((rc = d_pidx.reserve(std::max<size_t>(n_nrm, 1) * 4)) || (rc = c->d_normals.reserve(std::max<size_t>(n_nrm, 1) * 12))) break;
+            k_pt_scatter<<<g, 256, 0, st>>>(d_key.as<unsigned>(), d_first.as<unsigned>(), c->d_noff.as<unsigned>(), n, d_cur.as<unsigned>(), d_pidx.as<unsigned>());
+            k_seg_sort<<<(n_occ + 127) / 128, 128, 0, st>>>(c->d_noff.as<unsigned>(), n_occ, d_pidx.as<unsigned>());
+            k_gather_normals<<<blocks_for(n_nrm, 256, 148 * 16), 256, 0, st>>>(d_pidx.as<unsigned>(), d_nrm.as<float>(), n_nrm, c->d_normals.as<float>());
             c->launches += 3;
-            h_nrm.resize(3 * (size_t)n_nrm);
-            cudaMemcpyAsync(h_noff.data(), d_noff.p, ((size_t)n_occ + 1) * 4, cudaMemcpyDeviceToHost, st);
-            if (n_nrm) cudaMemcpyAsync(h_nrm.data(), d_out.p, (size_t)n_nrm * 12, cudaMemcpyDeviceToHost, st);
         }
-        cudaMemcpyAsync(h_ids.data(), d_ids.p, (size_t)n_occ * 8, cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) { rc = fail("device integratePointCloud failed: %s", cudaGetErrorString(e)); break; }
     } while (0);
     cleanup();
     if (rc) return rc;
-    // the march structures (bit grid, rank directory, clearance, ...) are derived from the occupied list as for any upload
-    return upload_volume(c, bounds, hv.delta, hv.dim, h_ids.data(), h_ids.size(), normals ? h_noff.data() : nullptr, normals ? h_nrm.data() : nullptr);
+    if (!normals || n_occ == 0) {                                   // no normal lists: an all-zero CSR
+        if ((rc = c->d_noff.reserve(((size_t)n_occ + 1) * 4))) return rc;
+        DMF_CUDA(cudaMemsetAsync(c->d_noff.p, 0, ((size_t)n_occ + 1) * 4, st));
+        n_nrm = 0;
+    }
+    return build_volume_device(c, n_occ, n_nrm);
 }
 
 int dmf_segments_collide(dmf_ctx* c, const float* a, const float* b, int n, int guard_coords, uint8_t* out) {

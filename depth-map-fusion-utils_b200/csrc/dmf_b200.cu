@@ -6,6 +6,7 @@
 #include "dmf_reverse.cuh"
 #include "dmf_distance.cuh"
 #include "dmf_integrate.cuh"
+#include "dmf_volume.cuh"
 #include "dmf_setcover.cuh"
 #include <algorithm>
 #include <climits>
@@ -18,6 +19,17 @@ using namespace dmf;
 namespace {
 
 inline cudaStream_t pick_stream(dmf_ctx* c, void* s) { return s ? (cudaStream_t)s : c->stream; }
+// All calls on a context share per-context scratch (view-start table, first-view array, inverse poses, projection tables, the
+// timing events).  A call enqueued on a different stream than the previous one therefore first waits for that one's work.
+inline int order_after_previous(dmf_ctx* c, cudaStream_t st) {
+    if (c->last_stream_valid && c->last_stream != st) DMF_CUDA(cudaStreamWaitEvent(st, c->ev_last, 0));
+    return 0;
+}
+inline int mark_last(dmf_ctx* c, cudaStream_t st) {
+    DMF_CUDA(cudaEventRecord(c->ev_last, st));
+    c->last_stream = st; c->last_stream_valid = true;
+    return 0;
+}
 inline unsigned blocks_for(size_t n, unsigned threads, unsigned cap = 148 * 16) {
     size_t b = (n + threads - 1) / threads;
     return (unsigned)std::max<size_t>(1, std::min<size_t>(b, cap));
@@ -31,18 +43,55 @@ int fill_u32(dmf_ctx* c, cudaStream_t st, void* p, size_t n, unsigned val) {
     return 0;
 }
 
-// ---- volume upload ------------------------------------------------------------------------------------------
-int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], const int dim[3],
-                  const uint64_t* ids, size_t n_occ, const uint32_t* noff, const float* normals) {
+// ---- device-wide exclusive scan of uint32, asynchronous -------------------------------------------------------
+// d_out may alias d_in.  Blocks of SCAN_BLOCK elements, recursive on the block sums; the per-level sums live in the
+// context's scan scratch.  If d_total is given it receives the grand total (device pointer).  Nothing synchronises.
+int scan_u32_async(dmf_ctx* c, cudaStream_t st, const unsigned* d_in, unsigned* d_out, size_t n, unsigned* d_total) {
+    if (n == 0) { if (d_total) DMF_CUDA(cudaMemsetAsync(d_total, 0, 4, st)); return 0; }
+    std::vector<size_t> level_n;                      // elements per level: n, ceil(n/B), ... down to one block
+    for (size_t m = n;; m = (m + SCAN_BLOCK - 1) / SCAN_BLOCK) { level_n.push_back(m); if (m <= (size_t)SCAN_BLOCK) break; }
+    size_t scratch = 1;
+    for (size_t l = 1; l < level_n.size(); l++) scratch += level_n[l];
+    DMF_TRY(c->d_scan.reserve((scratch + 1) * 4));
+    std::vector<unsigned*> lv(level_n.size() + 1);
+    unsigned* sp = c->d_scan.as<unsigned>();
+    for (size_t l = 1; l < level_n.size(); l++) { lv[l] = sp; sp += level_n[l]; }
+    unsigned* top_total = sp;                           // one word: the sum of the last level
+    for (size_t l = 0; l < level_n.size(); l++) {
+        const unsigned* in = l == 0 ? d_in : lv[l];
+        unsigned* out = l == 0 ? d_out : lv[l];
+        unsigned* sums = l + 1 < level_n.size() ? lv[l + 1] : top_total;
+        k_scan_block<<<(unsigned)((level_n[l] + SCAN_BLOCK - 1) / SCAN_BLOCK), SCAN_THREADS, 0, st>>>(in, out, level_n[l], sums);
+        c->launches++;
+    }
+    for (size_t l = level_n.size() - 1; l-- > 0;) {
+        unsigned* out = l == 0 ? d_out : lv[l];
+        k_scan_add<<<(unsigned)((level_n[l] + SCAN_BLOCK - 1) / SCAN_BLOCK), SCAN_THREADS, 0, st>>>(out, level_n[l], lv[l + 1]);
+        c->launches++;
+    }
+    if (d_total) DMF_CUDA(cudaMemcpyAsync(d_total, top_total, 4, cudaMemcpyDeviceToDevice, st));
+    DMF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- volume: host-side constants ----------------------------------------------------------------------------------
+// Validates (dim, bounds, delta) and fills the scalar half of VolDev: reciprocals, float thresholds, padded dims, the
+// float-accumulated axes of the whole-grid loops.  No occupancy yet.
+int set_volume_geometry(dmf_ctx* c, const double bounds[6], const double delta[3], const int dim[3]) {
     DMF_CUDA(cudaSetDevice(c->device));
     for (int a = 0; a < 3; a++) {
         if (dim[a] < 1 || dim[a] > 2048) return fail("volume dim %d out of range [1,2048] (voxel ids shift y by 20 bits as int, Volume.hpp:146)", dim[a]);
         if (!(delta[a] > 0) || !(bounds[2 * a + 1] > bounds[2 * a])) return fail("degenerate volume bounds/delta on axis %d", a);
+        // the marches index the padded grid [0,dim] without a range check, which is sound only if every in-bounds sample's
+        // quotient (p - vmin)/delta stays below dim + 1 (constructVolume's dim = int((max-min)/delta), Volume.hpp:121-123)
+        const double extent = (bounds[2 * a + 1] - bounds[2 * a]) / delta[a];
+        if (!(extent < (double)dim[a] + 1.0))
+            return fail("volume axis %d: (max-min)/delta = %.17g does not fit dim %d (need < dim+1): dim, bounds and delta are inconsistent", a, extent, dim[a]);
     }
+    if ((double)(dim[0] + 1) * (dim[1] + 1) * (dim[2] + 1) >= 4294967296.0) return fail("volume %dx%dx%d too large for the 32-bit linear voxel index", dim[0], dim[1], dim[2]);
     VolDev& v = c->vol;
     std::memcpy(c->bounds, bounds, sizeof c->bounds);
     c->voxel_size = delta[0] * delta[1] * delta[2];
-    if ((double)(dim[0] + 1) * (dim[1] + 1) * (dim[2] + 1) >= 4294967296.0) return fail("volume %dx%dx%d too large for the 32-bit linear voxel index", dim[0], dim[1], dim[2]);
     for (int a = 0; a < 3; a++) {
         const double vmin = bounds[2 * a], vmax = bounds[2 * a + 1];
         v.dim[a] = dim[a]; v.pdim[a] = dim[a] + 1; v.mdim[a] = (dim[a] + 1 + 7) / 8;
@@ -80,110 +129,6 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
         const float re = std::max(v.rev_eps[0], std::max(v.rev_eps[1], v.rev_eps[2]));
         v.rev_esafe = 2.0f * re + (float)std::ldexp((double)std::max(dim[0], std::max(dim[1], dim[2])) + 2.0, -21) + (float)std::ldexp(1.0, -12);
     }
-    const size_t nbits = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
-    const size_t nwords = ((nbits + 31) / 32 + 7) / 8 * 8;           // whole 8-word (256-bit) rank blocks
-    const size_t nmacro = (size_t)v.mdim[0] * v.mdim[1] * v.mdim[2];
-    std::vector<uint32_t> words(nwords, 0), prefix(nwords, 0), macro((nmacro + 31) / 32, 0);
-    auto locate = [&](uint64_t id, size_t& idx) -> bool {
-        const uint64_t mask = (1u << 20) - 1;
-        long long x = (long long)(id >> 40), y = (long long)((id >> 20) & mask), z = (long long)(id & mask);   // getVoxelCoords :158-165
-        if (x >= dim[0] || y >= dim[1] || z >= dim[2]) return false;
-        idx = ((size_t)x * v.pdim[1] + (size_t)y) * v.pdim[2] + (size_t)z;
-        size_t m = ((size_t)(x >> 3) * v.mdim[1] + (size_t)(y >> 3)) * v.mdim[2] + (size_t)(z >> 3);
-        macro[m >> 5] |= 1u << (m & 31);
-        return true;
-    };
-    for (size_t i = 0; i < n_occ; i++) {
-        size_t idx;
-        if (!locate(ids[i], idx)) return fail("occupied id %llu (#%zu) outside the %dx%dx%d grid", (unsigned long long)ids[i], i, dim[0], dim[1], dim[2]);
-        if ((words[idx >> 5] >> (idx & 31)) & 1u) return fail("duplicate occupied id %llu (#%zu)", (unsigned long long)ids[i], i);
-        words[idx >> 5] |= 1u << (idx & 31);
-    }
-    std::vector<uint32_t>& word_rank = prefix;
-    uint32_t run = 0;
-    for (size_t w = 0; w < nwords; w++) { prefix[w] = run; run += (uint32_t)__builtin_popcount(words[w]); }
-    std::vector<uint32_t> rank2occ(std::max<size_t>(n_occ, 1));
-    for (size_t i = 0; i < n_occ; i++) {
-        size_t idx; locate(ids[i], idx);
-        rank2occ[word_rank[idx >> 5] + __builtin_popcount(words[idx >> 5] & ((1u << (idx & 31)) - 1u))] = (uint32_t)i;
-    }
-    // Chebyshev distance (in macro cells) from every macro cell to the nearest "blocked" cell: one that holds an occupied
-    // voxel, is not entirely inside [0,dim) on every axis, or lies outside the grid.  Box dilation is separable, so each
-    // radius step is three 1-D passes.  clearance = 8*(D-1) - 0.25 voxels for D >= 2, else 0 (see k_forward_skip).
-    std::vector<float> clearance(nmacro, 0.0f);
-    {
-        const int mx = v.mdim[0], my = v.mdim[1], mz = v.mdim[2];
-        const int ex = mx + 2, ey = my + 2, ez = mz + 2;                      // one blocked border cell on every side
-        auto at = [&](int x, int y, int z) { return ((size_t)x * ey + y) * ez + z; };
-        std::vector<uint8_t> cur((size_t)ex * ey * ez, 1), tmp(cur.size());
-        std::vector<uint8_t> dist(nmacro, 0);
-        for (int x = 0; x < mx; x++) for (int y = 0; y < my; y++) for (int z = 0; z < mz; z++) {
-            size_t m = ((size_t)x * my + y) * mz + z;
-            bool blocked = ((macro[m >> 5] >> (m & 31)) & 1u) || 8 * (x + 1) > dim[0] || 8 * (y + 1) > dim[1] || 8 * (z + 1) > dim[2];
-            cur[at(x + 1, y + 1, z + 1)] = blocked ? 1 : 0;
-        }
-        const int kMaxD = 40;
-        for (int r = 1; r <= kMaxD; r++) {
-            // dilate by one cell along z, then y, then x
-            for (int pass = 0; pass < 3; pass++) {
-                const size_t stride = pass == 0 ? 1 : (pass == 1 ? (size_t)ez : (size_t)ey * ez);
-                for (size_t i = 0; i < cur.size(); i++) {
-                    uint8_t c = cur[i];
-                    if (!c) { if (i >= stride && cur[i - stride]) c = 1; else if (i + stride < cur.size() && cur[i + stride]) c = 1; }
-                    tmp[i] = c;
-                }
-                // the flat +-stride neighbours wrap across rows only into border cells, which are blocked anyway
-                cur.swap(tmp);
-            }
-            size_t fresh = 0;
-            for (int x = 0; x < mx; x++) for (int y = 0; y < my; y++) for (int z = 0; z < mz; z++) {
-                size_t m = ((size_t)x * my + y) * mz + z;
-                if (cur[at(x + 1, y + 1, z + 1)] && dist[m] == 0) {
-                    bool blocked0 = ((macro[m >> 5] >> (m & 31)) & 1u) || 8 * (x + 1) > dim[0] || 8 * (y + 1) > dim[1] || 8 * (z + 1) > dim[2];
-                    if (!blocked0) { dist[m] = (uint8_t)r; fresh++; }
-                }
-            }
-            if (!fresh) break;
-        }
-        for (size_t m = 0; m < nmacro; m++) {
-            size_t xm = m / ((size_t)my * mz), ym = (m / mz) % my, zm = m % mz;
-            bool blocked0 = ((macro[m >> 5] >> (m & 31)) & 1u) || 8 * ((int)xm + 1) > dim[0] || 8 * ((int)ym + 1) > dim[1] || 8 * ((int)zm + 1) > dim[2];
-            int D = blocked0 ? 0 : (dist[m] ? dist[m] : kMaxD + 1);           // never reached: farther than kMaxD
-            clearance[m] = D >= 2 ? 8.0f * (float)(D - 1) - 0.25f : 0.0f;
-        }
-    }
-    c->n_occ = n_occ;
-    c->h_occ.assign(ids, ids + n_occ);
-    c->h_noff.assign(n_occ + 1, 0);
-    if (noff) c->h_noff.assign(noff, noff + n_occ + 1);
-    c->n_normals = c->h_noff[n_occ];
-    c->h_normals.assign(3 * c->n_normals, 0.f);
-    if (normals && c->n_normals) c->h_normals.assign(normals, normals + 3 * c->n_normals);
-
-    DMF_TRY(c->d_bricks.reserve(nwords * 4)); DMF_TRY(c->d_prefix.reserve(prefix.size() * 4)); DMF_TRY(c->d_macro.reserve(macro.size() * 4)); DMF_TRY(c->d_clearance.reserve(clearance.size() * 4));
-    DMF_TRY(c->d_rank2occ.reserve(rank2occ.size() * 4)); DMF_TRY(c->d_occ_ids.reserve(std::max<size_t>(n_occ, 1) * 8));
-    DMF_TRY(c->d_noff.reserve((n_occ + 1) * 4)); DMF_TRY(c->d_normals.reserve(std::max<size_t>(c->h_normals.size(), 1) * 4));
-    DMF_TRY(c->d_view_mark.reserve(std::max<size_t>(n_occ, 1) * 4)); DMF_TRY(c->d_first_view.reserve(std::max<size_t>(n_occ, 1) * 4));
-    DMF_TRY(c->d_good_bits.reserve(((n_occ + 63) / 64 + 1) * 8));
-    cudaStream_t st = c->stream;
-    DMF_CUDA(cudaMemcpyAsync(c->d_bricks.p, words.data(), nwords * 4, cudaMemcpyHostToDevice, st));
-    DMF_CUDA(cudaMemcpyAsync(c->d_prefix.p, prefix.data(), prefix.size() * 4, cudaMemcpyHostToDevice, st));
-    DMF_CUDA(cudaMemcpyAsync(c->d_macro.p, macro.data(), macro.size() * 4, cudaMemcpyHostToDevice, st));
-    DMF_CUDA(cudaMemcpyAsync(c->d_clearance.p, clearance.data(), clearance.size() * 4, cudaMemcpyHostToDevice, st));
-    DMF_CUDA(cudaMemcpyAsync(c->d_rank2occ.p, rank2occ.data(), rank2occ.size() * 4, cudaMemcpyHostToDevice, st));
-    if (n_occ) DMF_CUDA(cudaMemcpyAsync(c->d_occ_ids.p, c->h_occ.data(), n_occ * 8, cudaMemcpyHostToDevice, st));
-    DMF_CUDA(cudaMemcpyAsync(c->d_noff.p, c->h_noff.data(), (n_occ + 1) * 4, cudaMemcpyHostToDevice, st));
-    if (c->h_normals.size()) DMF_CUDA(cudaMemcpyAsync(c->d_normals.p, c->h_normals.data(), c->h_normals.size() * 4, cudaMemcpyHostToDevice, st));
-    DMF_CUDA(cudaMemsetAsync(c->d_view_mark.p, 0, std::max<size_t>(n_occ, 1) * 4, st));
-    DMF_CUDA(cudaMemsetAsync(c->d_good_bits.p, 0, ((n_occ + 63) / 64 + 1) * 8, st));
-    DMF_TRY(fill_u32(c, st, c->d_first_view.p, std::max<size_t>(n_occ, 1), 0x7fffffffu));
-    DMF_CUDA(cudaStreamSynchronize(st));   // host staging vectors die here
-    v.bits = c->d_bricks.as<unsigned>(); v.prefix = c->d_prefix.as<unsigned>(); v.rank2occ = c->d_rank2occ.as<unsigned>(); v.macro = c->d_macro.as<unsigned>();
-    v.noff = c->d_noff.as<unsigned>(); v.normals = c->d_normals.as<float>(); v.occ_ids = c->d_occ_ids.as<u64>();
-    v.bytes = nullptr; v.n_occ = (int)n_occ;
-    c->bytes_built = false;
-    c->n_grid_words = nwords; c->observed_ready = false;     // a new volume starts unobserved
-    c->vol_set = true;
     // float-accumulated axes of the whole-grid loops (RayTracingEngine.hpp:54-56, :509-511)
     for (int a = 0; a < 3; a++) {
         std::vector<float> ax;
@@ -193,14 +138,124 @@ int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], con
         DMF_TRY(c->d_axis[a].reserve(std::max<size_t>(ax.size(), 1) * 4));
         if (!ax.empty()) DMF_CUDA(cudaMemcpy(c->d_axis[a].p, ax.data(), ax.size() * 4, cudaMemcpyHostToDevice));
     }
-    // centroid hashes of the occupied voxels (RayTracingEngine.hpp:151-163), view independent
+    return 0;
+}
+
+// ---- volume: the march structures, built on the device -------------------------------------------------------------
+// In: set_volume_geometry done; c->d_occ_ids (n_occ ids), c->d_noff (n_occ + 1) and c->d_normals (3 * n_normals floats)
+// already hold the volume ON THE DEVICE (uploaded by the host, produced by K0, or received from a peer GPU).
+// Out: bit grid, macro-cell bits + clearance, rank directory, rank -> ordinal table, centroid hashes, cleared marks.
+// One synchronisation at the end (the error words).  Timed with CUDA events: dmf_volume_prepare_ms.
+int build_volume_device(dmf_ctx* c, size_t n_occ, size_t n_normals) {
+    VolDev& v = c->vol;
+    cudaStream_t st = c->stream;
+    const size_t nbits = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
+    const size_t nwords = ((nbits + 31) / 32 + 7) / 8 * 8;           // whole 8-word (256-bit) rank blocks
+    const size_t nmacro = (size_t)v.mdim[0] * v.mdim[1] * v.mdim[2];
+    const size_t macro_words = (nmacro + 31) / 32;
+    if (n_occ >= 0xFFFFFFFFull) return fail("too many occupied voxels");
+    DMF_TRY(c->d_bricks.reserve(nwords * 4)); DMF_TRY(c->d_prefix.reserve(nwords * 4)); DMF_TRY(c->d_macro.reserve(macro_words * 4)); DMF_TRY(c->d_clearance.reserve(nmacro * 4));
+    DMF_TRY(c->d_rank2occ.reserve(std::max<size_t>(n_occ, 1) * 4)); DMF_TRY(c->d_occ_ids.reserve(std::max<size_t>(n_occ, 1) * 8));
+    DMF_TRY(c->d_noff.reserve((n_occ + 1) * 4)); DMF_TRY(c->d_normals.reserve(std::max<size_t>(3 * n_normals, 1) * 4));
+    DMF_TRY(c->d_view_mark.reserve(std::max<size_t>(n_occ, 1) * 4)); DMF_TRY(c->d_first_view.reserve(std::max<size_t>(n_occ, 1) * 4));
+    DMF_TRY(c->d_good_bits.reserve(((n_occ + 63) / 64 + 1) * 8));
     DMF_TRY(c->d_centroid_hash.reserve(std::max<size_t>(n_occ, 1) * 8));
+    DMF_TRY(c->d_macro_dist[0].reserve(nmacro)); DMF_TRY(c->d_macro_dist[1].reserve(nmacro));
+    DMF_TRY(c->d_err.reserve(16));
+    v.bits = c->d_bricks.as<unsigned>(); v.prefix = c->d_prefix.as<unsigned>(); v.rank2occ = c->d_rank2occ.as<unsigned>(); v.macro = c->d_macro.as<unsigned>();
+    v.noff = c->d_noff.as<unsigned>(); v.normals = c->d_normals.as<float>(); v.occ_ids = c->d_occ_ids.as<u64>();
+    v.bytes = nullptr; v.n_occ = (int)n_occ;
+    c->n_occ = n_occ; c->n_normals = n_normals;
+    c->bytes_built = false;
+    c->n_grid_words = nwords; c->observed_ready = false;     // a new volume starts unobserved
+
+    DMF_CUDA(cudaEventRecord(c->ev_p0, st));
+    DMF_CUDA(cudaMemsetAsync(c->d_bricks.p, 0, nwords * 4, st));
+    DMF_CUDA(cudaMemsetAsync(c->d_macro.p, 0, macro_words * 4, st));
+    DMF_CUDA(cudaMemsetAsync(c->d_err.p, 0xFF, 16, st));
+    if (n_occ) {
+        k_vol_mark<<<blocks_for(n_occ, 256), 256, 0, st>>>(v.occ_ids, (unsigned)n_occ, v, c->d_bricks.as<unsigned>(), c->d_macro.as<unsigned>(), c->d_err.as<unsigned>());
+        k_vol_check_csr<<<blocks_for(n_occ, 256), 256, 0, st>>>(v.noff, (unsigned)n_occ, c->d_err.as<unsigned>());
+        c->launches += 2;
+    }
+    k_vol_popc<<<blocks_for(nwords, 256), 256, 0, st>>>(v.bits, c->d_prefix.as<unsigned>(), nwords);
+    c->launches++;
+    DMF_TRY(scan_u32_async(c, st, c->d_prefix.as<unsigned>(), c->d_prefix.as<unsigned>(), nwords, nullptr));
+    if (n_occ) {
+        k_vol_rank2occ<<<blocks_for(n_occ, 256), 256, 0, st>>>(v.occ_ids, (unsigned)n_occ, v, v.bits, v.prefix, c->d_rank2occ.as<unsigned>());
+        c->launches++;
+    }
+    // macro-cell clearance (k_forward_skip): Chebyshev distance, in cells, to the nearest blocked cell; cells outside the
+    // grid are blocked (VIRTUAL_BORDER).  Three O(n) line passes over at most 257^3 bytes.
+    {
+        unsigned char *ma = c->d_macro_dist[0].as<unsigned char>(), *mb = c->d_macro_dist[1].as<unsigned char>();
+        const int m0 = v.mdim[0], m1 = v.mdim[1], m2 = v.mdim[2];
+        k_macro_seed<<<blocks_for(nmacro, 256), 256, 0, st>>>(v, v.macro, ma);
+        k_dt_lines<2, true, false, EncodeNone><<<blocks_for((size_t)m0 * m1, 128), 128, 0, st>>>(ma, mb, m0, m1, m2, EncodeNone());
+        k_dt_lines<1, true, false, EncodeNone><<<blocks_for((size_t)m0 * m2, 128), 128, 0, st>>>(mb, ma, m0, m1, m2, EncodeNone());
+        k_dt_lines<0, true, false, EncodeNone><<<blocks_for((size_t)m1 * m2, 128), 128, 0, st>>>(ma, mb, m0, m1, m2, EncodeNone());
+        k_macro_clearance<<<blocks_for(nmacro, 256), 256, 0, st>>>(mb, c->d_clearance.as<float>(), (unsigned)nmacro);
+        c->launches += 5;
+    }
+    DMF_CUDA(cudaMemsetAsync(c->d_view_mark.p, 0, std::max<size_t>(n_occ, 1) * 4, st));
+    DMF_CUDA(cudaMemsetAsync(c->d_good_bits.p, 0, ((n_occ + 63) / 64 + 1) * 8, st));
+    DMF_TRY(fill_u32(c, st, c->d_first_view.p, std::max<size_t>(n_occ, 1), 0x7fffffffu));
+    // centroid hashes of the occupied voxels (RayTracingEngine.hpp:151-163), view independent
     if (n_occ) {
         k_centroid_hash<<<blocks_for(n_occ, 256), 256, 0, st>>>(c->vol, c->d_centroid_hash.as<u64>());
         c->launches++;
-        DMF_CUDA(cudaGetLastError());
-        DMF_CUDA(cudaStreamSynchronize(st));
     }
+    DMF_CUDA(cudaEventRecord(c->ev_p1, st));
+    DMF_CUDA(cudaGetLastError());
+    unsigned err[4];
+    DMF_CUDA(cudaMemcpyAsync(err, c->d_err.p, 16, cudaMemcpyDeviceToHost, st));
+    DMF_CUDA(cudaStreamSynchronize(st));
+    c->prepare_timed = true;
+    if (err[0] != 0xFFFFFFFFu) { c->vol_set = false; return fail("occupied id #%u lies outside the %dx%dx%d grid", err[0], v.dim[0], v.dim[1], v.dim[2]); }
+    if (err[1] != 0xFFFFFFFFu) { c->vol_set = false; return fail("duplicate occupied id (#%u)", err[1]); }
+    if (err[2] != 0xFFFFFFFFu) { c->vol_set = false; return fail("normal_offsets not monotone at voxel %u", err[2]); }
+    c->vol_set = true;
+    return 0;
+}
+
+// ---- volume upload from host arrays -----------------------------------------------------------------------------------
+int upload_volume(dmf_ctx* c, const double bounds[6], const double delta[3], const int dim[3],
+                  const uint64_t* ids, size_t n_occ, const uint32_t* noff, const float* normals) {
+    if (n_occ && !ids) return fail("null occupied id list");
+    if (noff) {
+        // CSR of the per-voxel normal lists: any_normal_faces walks it on the device without further checks
+        if (noff[0] != 0) return fail("normal_offsets[0] must be 0 (got %u)", noff[0]);
+        for (size_t i = 0; i < n_occ; i++) if (noff[i + 1] < noff[i]) return fail("normal_offsets not monotone at voxel %zu (%u > %u)", i, noff[i], noff[i + 1]);
+        if (noff[n_occ] && !normals) return fail("normal_offsets describe %u normals but the normals array is null", noff[n_occ]);
+    }
+    DMF_TRY(set_volume_geometry(c, bounds, delta, dim));
+    c->vol_set = false;
+    // host mirrors (dmf_volume_get_*): the caller's arrays as they are
+    c->h_occ.assign(ids, ids + n_occ);
+    c->h_noff.assign(n_occ + 1, 0);
+    if (noff) c->h_noff.assign(noff, noff + n_occ + 1);
+    const size_t n_normals = c->h_noff[n_occ];
+    c->h_normals.assign(3 * n_normals, 0.f);
+    if (normals && n_normals) c->h_normals.assign(normals, normals + 3 * n_normals);
+    c->mirror_valid = true;
+    DMF_TRY(c->d_occ_ids.reserve(std::max<size_t>(n_occ, 1) * 8)); DMF_TRY(c->d_noff.reserve((n_occ + 1) * 4)); DMF_TRY(c->d_normals.reserve(std::max<size_t>(3 * n_normals, 1) * 4));
+    cudaStream_t st = c->stream;
+    if (n_occ) DMF_CUDA(cudaMemcpyAsync(c->d_occ_ids.p, c->h_occ.data(), n_occ * 8, cudaMemcpyHostToDevice, st));
+    DMF_CUDA(cudaMemcpyAsync(c->d_noff.p, c->h_noff.data(), (n_occ + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (n_normals) DMF_CUDA(cudaMemcpyAsync(c->d_normals.p, c->h_normals.data(), 3 * n_normals * 4, cudaMemcpyHostToDevice, st));
+    return build_volume_device(c, n_occ, n_normals);
+}
+
+// host mirrors of a volume that was built or received on the device: fetched on first use
+int ensure_host_mirror(dmf_ctx* c) {
+    if (c->mirror_valid) return 0;
+    DMF_CUDA(cudaSetDevice(c->device));
+    c->h_occ.resize(c->n_occ); c->h_noff.assign(c->n_occ + 1, 0); c->h_normals.resize(3 * c->n_normals);
+    DMF_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->n_occ) DMF_CUDA(cudaMemcpy(c->h_occ.data(), c->d_occ_ids.p, c->n_occ * 8, cudaMemcpyDeviceToHost));
+    DMF_CUDA(cudaMemcpy(c->h_noff.data(), c->d_noff.p, (c->n_occ + 1) * 4, cudaMemcpyDeviceToHost));
+    if (c->n_normals) DMF_CUDA(cudaMemcpy(c->h_normals.data(), c->d_normals.p, 3 * c->n_normals * 4, cudaMemcpyDeviceToHost));
+    c->mirror_valid = true;
     return 0;
 }
 
@@ -229,19 +284,20 @@ int ensure_bytes(dmf_ctx* c, cudaStream_t st) {
     VolDev& v = c->vol;
     const size_t n = (size_t)v.pdim[0] * v.pdim[1] * v.pdim[2];
     DMF_TRY(c->d_bytes.reserve(n));
-    DevBuf tmp;
-    DMF_TRY(tmp.reserve(n));
+    DMF_TRY(c->d_dt_tmp.reserve(n));
+    unsigned char *bytes = c->d_bytes.as<unsigned char>(), *tmp = c->d_dt_tmp.as<unsigned char>();
     const unsigned nlines = (unsigned)v.pdim[0] * (unsigned)v.pdim[1];
-    k_dt_z<<<(nlines + 127) / 128, 128, 0, st>>>(v, c->d_bytes.as<unsigned char>());
-    k_dt_axis<1, false><<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(v, c->d_bytes.as<unsigned char>(), tmp.as<unsigned char>());
-    k_dt_axis<0, true><<<blocks_for(n, 256, 148 * 32), 256, 0, st>>>(v, tmp.as<unsigned char>(), c->d_bytes.as<unsigned char>());
+    DMF_CUDA(cudaEventRecord(c->ev_b0, st));
+    k_dt_z<<<blocks_for(nlines, 8, 148 * 32), 256, 0, st>>>(v, bytes);
+    k_dt_lines<1, false, false, EncodeNone><<<blocks_for((size_t)v.pdim[0] * v.pdim[2], 128, 148 * 32), 128, 0, st>>>(bytes, tmp, v.pdim[0], v.pdim[1], v.pdim[2], EncodeNone());
+    k_dt_lines<0, false, true, EncodeVoxel><<<blocks_for((size_t)v.pdim[1] * v.pdim[2], 128, 148 * 32), 128, 0, st>>>(tmp, bytes, v.pdim[0], v.pdim[1], v.pdim[2], EncodeVoxel{v.bits});
+    DMF_CUDA(cudaEventRecord(c->ev_b1, st));
     c->launches += 3;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    tmp.release();
     if (e != cudaSuccess) return fail("distance transform failed: %s", cudaGetErrorString(e));
-    v.bytes = c->d_bytes.as<unsigned char>();
-    c->bytes_built = true;
+    v.bytes = bytes;
+    c->bytes_built = true; c->bytes_timed = true;
     return 0;
 }
 
@@ -452,6 +508,8 @@ int dmf_create(dmf_ctx** out, int device) {
     DMF_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); DMF_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     DMF_CUDA(cudaEventCreate(&c->ev_k0)); DMF_CUDA(cudaEventCreate(&c->ev_k1));
     DMF_CUDA(cudaEventCreate(&c->ev_h0)); DMF_CUDA(cudaEventCreate(&c->ev_h1));
+    DMF_CUDA(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
+    DMF_CUDA(cudaEventCreate(&c->ev_p0)); DMF_CUDA(cudaEventCreate(&c->ev_p1)); DMF_CUDA(cudaEventCreate(&c->ev_b0)); DMF_CUDA(cudaEventCreate(&c->ev_b1));
     for (int i = 0; i < 2; i++) {
         DMF_CUDA(cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
         DMF_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
@@ -471,10 +529,12 @@ void dmf_destroy(dmf_ctx* c) {
     DevBuf* bufs[] = {&c->d_bricks, &c->d_macro, &c->d_clearance, &c->d_dcx, &c->d_dcy, &c->d_prefix, &c->d_rank2occ, &c->d_bytes, &c->d_noff, &c->d_normals, &c->d_occ_ids, &c->d_centroid_hash,
                       &c->d_view_mark, &c->d_good_bits, &c->d_first_view, &c->d_observed, &c->d_axis[0], &c->d_axis[1], &c->d_axis[2], &c->d_xtab, &c->d_ytab, &c->d_ztab, &c->d_kstart,
                       &c->d_poses[0], &c->d_poses[1], &c->d_inv_poses, &c->d_first_key, &c->d_ray_key, &c->d_ray_occ, &c->d_tmp_a, &c->d_tmp_b,
-                      &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters};
+                      &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters,
+                      &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err};
     for (auto* b : bufs) b->release();
     for (int i = 0; i < 2; i++) for (int j = 0; j < 8; j++) c->d_out[i][j].release();
     for (int i = 0; i < 2; i++) { if (c->ev_compute[i]) cudaEventDestroy(c->ev_compute[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
+    for (cudaEvent_t e : {c->ev_p0, c->ev_p1, c->ev_b0, c->ev_b1, c->ev_last}) if (e) cudaEventDestroy(e);
     if (c->ev_h0) cudaEventDestroy(c->ev_h0);
     if (c->ev_h1) cudaEventDestroy(c->ev_h1);
     if (c->ev_k0) cudaEventDestroy(c->ev_k0);
@@ -528,11 +588,13 @@ int dmf_volume_info(dmf_ctx* c, int dims[3], double deltas[3], double* voxel_siz
 }
 int dmf_volume_get_occupied(dmf_ctx* c, uint64_t* ids) {
     if (!c || !c->vol_set) return fail("no volume uploaded");
+    DMF_TRY(ensure_host_mirror(c));
     std::copy(c->h_occ.begin(), c->h_occ.end(), ids);
     return 0;
 }
 int dmf_volume_get_normals(dmf_ctx* c, uint32_t* offsets, float* normals) {
     if (!c || !c->vol_set) return fail("no volume uploaded");
+    DMF_TRY(ensure_host_mirror(c));
     std::copy(c->h_noff.begin(), c->h_noff.end(), offsets);
     std::copy(c->h_normals.begin(), c->h_normals.end(), normals);
     return 0;
@@ -547,8 +609,9 @@ int dmf_clear_marks(dmf_ctx* c) {
     return 0;
 }
 
-int dmf_download_marks(dmf_ctx* c, int32_t* view, uint8_t* good) {
+int dmf_download_marks(dmf_ctx* c, int32_t* view, uint8_t* good, size_t n) {
     if (!c || !c->vol_set) return fail("no volume uploaded");
+    if (n != c->n_occ) return fail("dmf_download_marks: caller has %zu voxels, the uploaded volume %zu", n, c->n_occ);
     DMF_CUDA(cudaSetDevice(c->device));
     DMF_CUDA(cudaStreamSynchronize(c->stream));
     if (view && c->n_occ) DMF_CUDA(cudaMemcpy(view, c->d_view_mark.p, c->n_occ * 4, cudaMemcpyDeviceToHost));
@@ -560,12 +623,13 @@ int dmf_download_marks(dmf_ctx* c, int32_t* view, uint8_t* good) {
     return 0;
 }
 
-int dmf_upload_marks(dmf_ctx* c, const int32_t* view, const uint8_t* good) {
+int dmf_upload_marks(dmf_ctx* c, const int32_t* view, const uint8_t* good, size_t n) {
     if (!c || !c->vol_set) return fail("no volume uploaded");
+    if (n != c->n_occ) return fail("dmf_upload_marks: caller has %zu voxels, the uploaded volume %zu", n, c->n_occ);
+    if (!c->n_occ) return 0;                       // an empty volume has no marks (std::vector<>(0).data() may be null)
     if (!view || !good) return fail("null argument");
     DMF_CUDA(cudaSetDevice(c->device));
     DMF_CUDA(cudaStreamSynchronize(c->stream));
-    if (!c->n_occ) return 0;
     std::vector<uint32_t> bits((c->n_occ + 63) / 64 * 2 + 2, 0);
     for (size_t i = 0; i < c->n_occ; i++) if (good[i]) bits[i >> 5] |= 1u << (i & 31);
     DMF_CUDA(cudaMemcpy(c->d_view_mark.p, view, c->n_occ * 4, cudaMemcpyHostToDevice));
@@ -632,11 +696,12 @@ int dmf_forward_dev(dmf_ctx* c, const dmf_forward_params* p, const float* d_pose
     if (d_out->ids || d_out->ids_offsets) return fail("dmf_forward_dev does not produce id lists; use dmf_forward or the visibility bitset");
     FwdPlan pl; DMF_TRY(plan_forward(c, p, pl));
     cudaStream_t st = pick_stream(c, stream);
+    DMF_TRY(order_after_previous(c, st));
     DMF_CUDA(cudaEventRecord(c->ev_k0, st));
     DMF_TRY(enqueue_forward(c, p, pl, d_poses, n_views, p->view_id0, *d_out, nullptr, nullptr, nullptr, st));
     DMF_CUDA(cudaEventRecord(c->ev_k1, st));
     c->timed = true;
-    return 0;
+    return mark_last(c, st);
 }
 
 int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int n_views, const dmf_forward_out* out) {
@@ -660,6 +725,7 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
     else if (!want_ids && n_views >= 8) chunk = std::min(chunk, (n_views + 3) / 4);
     if (const char* e = std::getenv("DMF_FWD_CHUNKS")) { const int nc = std::atoi(e); if (nc >= 1 && !want_ids) chunk = std::max(1, (n_views + nc - 1) / nc); }   // tuning aid
     cudaStream_t st = c->stream, cs = c->copy_stream;
+    DMF_TRY(order_after_previous(c, st));
     if (!want_ids) {
         // Whole batch resident on the device (up to 4 GiB of outputs per pass; HBM has room), marched as a few launches over
         // consecutive view ranges.  Nothing but those launches sits on the compute stream between them, so the GPU never idles;
@@ -821,6 +887,20 @@ int dmf_last_hot_kernel_ms(dmf_ctx* c, float* ms) {
     DMF_CUDA(cudaSetDevice(c->device));
     DMF_CUDA(cudaEventSynchronize(c->ev_h1));
     DMF_CUDA(cudaEventElapsedTime(ms, c->ev_h0, c->ev_h1));
+    return 0;
+}
+int dmf_volume_prepare_ms(dmf_ctx* c, float* build_ms, float* bytes_ms) {
+    if (!c || !c->vol_set) return fail("no volume uploaded");
+    DMF_CUDA(cudaSetDevice(c->device));
+    if (build_ms) { *build_ms = -1.f; if (c->prepare_timed) { DMF_CUDA(cudaEventSynchronize(c->ev_p1)); DMF_CUDA(cudaEventElapsedTime(build_ms, c->ev_p0, c->ev_p1)); } }
+    if (bytes_ms) { *bytes_ms = -1.f; if (c->bytes_built && c->bytes_timed) { DMF_CUDA(cudaEventSynchronize(c->ev_b1)); DMF_CUDA(cudaEventElapsedTime(bytes_ms, c->ev_b0, c->ev_b1)); } }
+    return 0;
+}
+int dmf_prepare_grid(dmf_ctx* c, int grid_format) {
+    if (!c || !c->vol_set) return fail("no volume uploaded");
+    DMF_CUDA(cudaSetDevice(c->device));
+    if (grid_format == DMF_GRID_BYTE) return ensure_bytes(c, c->stream);
+    if (grid_format != DMF_GRID_BIT) return fail("bad grid_format %d", grid_format);
     return 0;
 }
 int dmf_synchronize(dmf_ctx* c) {

@@ -126,14 +126,18 @@ struct dmf_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;     // bracket the kernels of the last call
     cudaEvent_t ev_compute[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;     // bracket the dominant march kernel of the last call
-    bool timed = false, hot_timed = false;
+    cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;   // volume preparation: structures / distance bytes
+    bool timed = false, hot_timed = false, prepare_timed = false, bytes_timed = false;
+    cudaEvent_t ev_last = nullptr; cudaStream_t last_stream = nullptr; bool last_stream_valid = false;   // the previous *_dev call (stream ordering of shared scratch)
     // camera
     bool cam_set = false; float K[9]; int H = 0, W = 0;
     // volume
     bool vol_set = false;
     VolDev vol{};
     double bounds[6]; double voxel_size = 0; size_t n_occ = 0, n_normals = 0;
-    std::vector<uint64_t> h_occ; std::vector<uint32_t> h_noff; std::vector<float> h_normals;
+    std::vector<uint64_t> h_occ; std::vector<uint32_t> h_noff; std::vector<float> h_normals;   // host mirrors (dmf_volume_get_*)
+    bool mirror_valid = false;                        // false: the volume was built / received on the device, mirrors fetched on demand
+    dmf::DevBuf d_scan, d_dt_tmp, d_macro_dist[2], d_err;   // scan scratch, distance-transform ping-pong, macro-cell distances, error words
     dmf::DevBuf d_bricks /* bit grid words */, d_macro, d_prefix, d_rank2occ, d_bytes, d_noff, d_normals, d_occ_ids, d_centroid_hash;
     bool bytes_built = false;
     int reverse_format = DMF_GRID_BYTE;   // grid the reverse march probes (dmf_set_reverse_format)

@@ -55,8 +55,10 @@ SYMBOLS = {
     "dmf_volume_get_occupied": (C.c_int, [vp, u64p]),
     "dmf_volume_get_normals": (C.c_int, [vp, u32p, fp]),
     "dmf_clear_marks": (C.c_int, [vp]),
-    "dmf_download_marks": (C.c_int, [vp, i32p, u8p]),
-    "dmf_upload_marks": (C.c_int, [vp, i32p, u8p]),
+    "dmf_download_marks": (C.c_int, [vp, i32p, u8p, C.c_size_t]),
+    "dmf_upload_marks": (C.c_int, [vp, i32p, u8p, C.c_size_t]),
+    "dmf_volume_prepare_ms": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "dmf_prepare_grid": (C.c_int, [vp, C.c_int]),
     "dmf_visibility_words": (C.c_size_t, [vp]),
     "dmf_observed_words": (C.c_size_t, [vp]),
     "dmf_clear_observed": (C.c_int, [vp]),

@@ -213,7 +213,7 @@ class VoxelVolume:
         """(view, good) of every occupied voxel, in occupied_cells_ order (Voxel::view / Voxel::good)."""
         n = len(self.occupied_cells_)
         view, good = np.zeros(n, np.int32), np.zeros(n, np.uint8)
-        check(self.ctx.lib.dmf_download_marks(self.ctx.h, _ptr(view, C.c_int32), _ptr(good, C.c_uint8)))
+        check(self.ctx.lib.dmf_download_marks(self.ctx.h, _ptr(view, C.c_int32), _ptr(good, C.c_uint8), n))
         return view, good
 
     def clear_marks(self):

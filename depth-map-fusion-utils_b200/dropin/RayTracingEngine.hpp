@@ -89,14 +89,14 @@ inline void push_marks(dmf_ctx* ctx, Volume& volume)
     const size_t n = volume.occupied_cells_.size();
     std::vector<int32_t> view(n); std::vector<uint8_t> good(n);
     for (size_t i = 0; i < n; i++) { auto* v = volume.voxelOf(i); view[i] = v->view; good[i] = v->good ? 1 : 0; }
-    must(dmf_upload_marks(ctx, view.data(), good.data()), "dmf_upload_marks");
+    must(dmf_upload_marks(ctx, view.data(), good.data(), n), "dmf_upload_marks");
 }
 template <class Volume>
 inline void pull_marks(dmf_ctx* ctx, Volume& volume)
 {
     const size_t n = volume.occupied_cells_.size();
     std::vector<int32_t> view(n); std::vector<uint8_t> good(n);
-    must(dmf_download_marks(ctx, view.data(), good.data()), "dmf_download_marks");
+    must(dmf_download_marks(ctx, view.data(), good.data(), n), "dmf_download_marks");
     for (size_t i = 0; i < n; i++) { auto* v = volume.voxelOf(i); v->view = view[i]; v->good = good[i] != 0; }
 }
 

@@ -7,6 +7,7 @@
 // uploads a compact device mirror (occupied ids + per-voxel normal lists) through dmf_upload_volume whenever
 // revision() changed, and writes view/good back after calls that mutate them.
 #pragma once
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <tuple>
@@ -30,9 +31,18 @@ struct Voxel
     Voxel(pcl::PointXYZRGB pt, pcl::Normal normal) : view(0), good(false) { pts.push_back(pt); normals.push_back(normal); }
 };
 
+// Revisions come from one process-wide counter, so no two states of any two volumes ever share one: a new VoxelVolume that
+// happens to live at the address of a destroyed one (stack local in a loop, heap reuse) can never be mistaken for it by the
+// engine's (&volume, revision) cache.
+inline unsigned long long dmf_next_volume_revision()
+{
+    static std::atomic<unsigned long long> counter{0};
+    return ++counter;
+}
+
 class VoxelVolume
 {
-    unsigned long long revision_ = 0;      // bumped on every change of occupancy / normals / geometry
+    unsigned long long revision_ = dmf_next_volume_revision();   // renewed on every change of occupancy / normals / geometry
     public:
     vector<unsigned long long int> occupied_cells_;
     double xmin_, xmax_, ymin_, ymax_, zmin_, zmax_;
@@ -57,14 +67,14 @@ class VoxelVolume
         xcenter_ = xmin_ + (xmax_ - xmin_) / 2.0;
         ycenter_ = ymin_ + (ymax_ - ymin_) / 2.0;
         zcenter_ = zmin_ + (zmax_ - zmin_) / 2.0;
-        revision_++;
+        revision_ = dmf_next_volume_revision();
     }
-    void setResolution(double xdelta, double ydelta, double zdelta) { xdelta_ = xdelta; ydelta_ = ydelta; zdelta_ = zdelta; revision_++; }
+    void setResolution(double xdelta, double ydelta, double zdelta) { xdelta_ = xdelta; ydelta_ = ydelta; zdelta_ = zdelta; revision_ = dmf_next_volume_revision(); }
     void setVolumeSize(int xdim, int ydim, int zdim)
     {
         xdim_ = xdim; ydim_ = ydim; zdim_ = zdim;
         xdelta_ = (xmax_ - xmin_) / xdim; ydelta_ = (ymax_ - ymin_) / ydim; zdelta_ = (zmax_ - zmin_) / zdim;
-        revision_++;
+        revision_ = dmf_next_volume_revision();
     }
     bool constructVolume()
     {
@@ -76,7 +86,7 @@ class VoxelVolume
         voxel_size_ = xdelta_ * ydelta_ * zdelta_;
         voxels_.assign(xdim_, vector<vector<Voxel*>>(ydim_, vector<Voxel*>(zdim_, nullptr)));
         occupied_cells_.clear();
-        revision_++;
+        revision_ = dmf_next_volume_revision();
         return true;
     }
     template <typename PointT> bool addPointCloud(typename pcl::PointCloud<PointT>::Ptr) { return true; }
@@ -123,7 +133,7 @@ class VoxelVolume
 
     // ---- additions (not in the reference): what the GPU engine needs to mirror this volume ----
     unsigned long long revision() const { return revision_; }
-    void touch() { revision_++; }     // call after editing voxels_ / normals by hand
+    void touch() { revision_ = dmf_next_volume_revision(); }     // call after editing voxels_ / normals by hand
     // CSR of the per-voxel normal lists in occupied_cells_ order
     void exportNormals(vector<uint32_t>& offsets, vector<float>& xyz)
     {
@@ -162,7 +172,7 @@ class VoxelVolume
                 if (normals) slot->normals.push_back(normals->points[i]);
             }
         }
-        revision_++;
+        revision_ = dmf_next_volume_revision();
         return true;    // the reference falls off the end of a bool function here (UB)
     }
 };

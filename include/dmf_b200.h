@@ -13,6 +13,10 @@
  *   - voxel ids are VoxelVolume::getHashId values: (x<<40)^(y<<20)^z  (include/Volume.hpp:143-148).
  *   - "occupied order" is the order of VoxelVolume::occupied_cells_ (first insertion, Volume.hpp:216).
  *   - one host thread per context; a context owns one CUDA device, its streams and all device buffers.
+ *   - the *_dev entry points enqueue on the caller's stream and return; calls on one context share scratch buffers, so the
+ *     library orders each call after the previous one on that context (an event wait when the stream changes).  Host-buffer
+ *     calls (dmf_forward, dmf_reverse, ...) run on the context's own streams and synchronise; do not overlap them with *_dev
+ *     work of the same context that is still in flight on another stream.
  *   - there is NO CPU fallback: every compute entry point fails if no sm_100 device is usable.
  */
 #ifndef DMF_B200_H
@@ -87,8 +91,10 @@ int dmf_volume_get_normals(dmf_ctx* ctx, uint32_t* offsets, float* normals);
 
 /* Voxel::view / Voxel::good (Volume.hpp:33-34) live on the device between calls. */
 int dmf_clear_marks(dmf_ctx* ctx);
-int dmf_download_marks(dmf_ctx* ctx, int32_t* view /* n_occ */, uint8_t* good /* n_occ */);
-int dmf_upload_marks(dmf_ctx* ctx, const int32_t* view /* n_occ */, const uint8_t* good /* n_occ */);
+/* n = entries in the caller's arrays; must equal the uploaded volume's n_occ (fails otherwise: a mismatch means the caller's
+ * VoxelVolume is not the one mirrored on the device).  n == 0 is a no-op. */
+int dmf_download_marks(dmf_ctx* ctx, int32_t* view /* n */, uint8_t* good /* n */, size_t n);
+int dmf_upload_marks(dmf_ctx* ctx, const int32_t* view /* n */, const uint8_t* good /* n */, size_t n);
 
 /* ---- forward per-pixel march ------------------------------------------------------------------ */
 typedef struct {
@@ -231,6 +237,13 @@ int dmf_reset_counters(dmf_ctx* ctx);
 int dmf_last_kernel_ms(dmf_ctx* ctx, float* ms);
 /* same, for the dominant march kernel(s) alone (the k_forward* / k_reverse launches of the last call or pass) */
 int dmf_last_hot_kernel_ms(dmf_ctx* ctx, float* ms);
+/* One-off cost of preparing the uploaded volume for the march, measured with CUDA events: build_ms = bit grid + rank directory
+ * + macro-cell clearance + centroid hashes from the occupied id list (all on the device, dmf_volume.cuh); bytes_ms = the
+ * Chebyshev distance bytes of DMF_GRID_BYTE (dmf_distance.cuh; -1 until that format has been used or dmf_prepare_grid called).
+ * Replaces constructVolume + the per-probe pointer grid of the reference (Volume.hpp:119-128). */
+int dmf_volume_prepare_ms(dmf_ctx* ctx, float* build_ms, float* bytes_ms);
+/* build the structures of `grid_format` now instead of on first use (so that a timed first call does not include them) */
+int dmf_prepare_grid(dmf_ctx* ctx, int grid_format);
 int dmf_synchronize(dmf_ctx* ctx);
 
 #ifdef __cplusplus
