@@ -15,6 +15,7 @@ int fill_rev_args(dmf_ctx* c, RevArgs& a) {
     a.centroid_hash = c->d_centroid_hash.as<u64>();
     for (int i = 0; i < 3; i++) { a.ax[i] = c->d_axis[i].as<float>(); a.nax[i] = c->n_axis[i]; }
     a.vis = nullptr; a.unocc = nullptr; a.vis_words32 = (int)(((c->n_occ + 63) / 64) * 2);
+    a.vis_stride32 = (unsigned)a.vis_words32; std::memset(&a.pub, 0, sizeof a.pub);
     a.found_any = nullptr; a.viz = 0;
     a.view_mark = c->d_view_mark.as<int>(); a.good_bits = c->d_good_bits.as<unsigned>();
     a.emit_list = nullptr; a.emit_count = nullptr; a.emit_cap = 0; a.zbuf = nullptr;
@@ -25,7 +26,8 @@ int fill_rev_args(dmf_ctx* c, RevArgs& a) {
 
 // enqueue the reverse march of n_views poses (device) into device outputs
 int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_views, unsigned* d_vis, unsigned* d_unocc, int* d_found,
-                    u64* d_emit_list, unsigned* d_emit_count, unsigned emit_cap, cudaStream_t st) {
+                    u64* d_emit_list, unsigned* d_emit_count, unsigned emit_cap, cudaStream_t st,
+                    unsigned vis_stride32 = 0, const PubTable* pub = nullptr) {
     if (n_views <= 0) return 0;
     if (c->reverse_format == DMF_GRID_BYTE && c->vol_set) DMF_TRY(ensure_bytes(c, st));
     if (n_views > 65535) return fail("at most 65535 views per launch (got %d)", n_views);
@@ -35,12 +37,14 @@ int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_v
     c->launches++;
     DMF_CUDA(cudaGetLastError());
     const size_t vw = (c->n_occ + 63) / 64;
-    if (d_vis && vw) DMF_CUDA(cudaMemsetAsync(d_vis, 0, (size_t)n_views * vw * 8, st));
+    if (d_vis && vw && !vis_stride32) DMF_CUDA(cudaMemsetAsync(d_vis, 0, (size_t)n_views * vw * 8, st));   // (a sharded sweep zeroes its interleaved rows itself)
     if (d_unocc && vw) DMF_CUDA(cudaMemsetAsync(d_unocc, 0, (size_t)n_views * vw * 8, st));
     if (d_found) DMF_CUDA(cudaMemsetAsync(d_found, 0, (size_t)n_views * 4, st));
     if (d_emit_count) DMF_CUDA(cudaMemsetAsync(d_emit_count, 0, (size_t)n_views * 4, st));
     a.poses = d_poses; a.inv_poses = c->d_inv_poses.as<float>();
     a.vis = d_vis; a.unocc = d_unocc; a.found_any = d_found; a.viz = viz;
+    if (vis_stride32) a.vis_stride32 = vis_stride32;
+    if (pub) a.pub = *pub;
     a.emit_list = d_emit_list; a.emit_count = d_emit_count; a.emit_cap = emit_cap;
     DMF_CUDA(cudaEventRecord(c->ev_h0, st));
     if (fast) {

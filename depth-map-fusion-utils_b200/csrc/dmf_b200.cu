@@ -380,7 +380,8 @@ int plan_forward(dmf_ctx* c, const dmf_forward_params* p, FwdPlan& pl) {
 // (measured: ~0.1 ms per launch boundary otherwise).  `st` is joined with the auxiliary stream before returning.
 int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, const float* d_poses, int n_views, int view_id0,
                     const dmf_forward_out& out, unsigned* first_key, unsigned* ray_key, int* ray_occ, cudaStream_t st,
-                    int sub_views = 0, const std::function<int(int, int, cudaStream_t)>* after_sub = nullptr) {
+                    int sub_views = 0, const std::function<int(int, int, cudaStream_t)>* after_sub = nullptr,
+                    unsigned vis_stride32 = 0, const PubTable* pub = nullptr) {
     if (n_views <= 0) return 0;
     if (n_views > 65535) return fail("at most 65535 views per launch (got %d)", n_views);
     DMF_TRY(ensure_tables(c, pl.z0, p->zdelta, pl.cstride, pl.rstride, st));
@@ -394,7 +395,8 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     if (out.depth_u16 && sparse_lattice) DMF_CUDA(cudaMemsetAsync(out.depth_u16, 0xFF, n_views * HW * 2, st));
     if (out.hit_voxel && sparse_lattice) DMF_CUDA(cudaMemsetAsync(out.hit_voxel, 0xFF, n_views * HW * 8, st));
     if (out.points && sparse_lattice) DMF_CUDA(cudaMemsetAsync(out.points, 0, n_views * HW * 12, st));
-    if (out.visibility && vis_words64) DMF_CUDA(cudaMemsetAsync(out.visibility, 0, (size_t)n_views * vis_words64 * 8, st));
+    // (a sharded sweep passes its own row pitch: the rows live interleaved in the gathered buffer and the caller zeroed them)
+    if (out.visibility && vis_words64 && !vis_stride32) DMF_CUDA(cudaMemsetAsync(out.visibility, 0, (size_t)n_views * vis_words64 * 8, st));
     if (out.found_any) DMF_CUDA(cudaMemsetAsync(out.found_any, 0, (size_t)n_views * 4, st));
     if (p->mode == DMF_MODE_MINIMUM) {
         if (!out.min_depth) return fail("MINIMUM mode needs out.min_depth");
@@ -411,6 +413,8 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     a.S = c->S; a.Wc = c->Wc; a.Hc = c->Hc; a.W = c->W; a.H = c->H; a.cstride = pl.cstride; a.rstride = pl.rstride; a.z0 = pl.z0; a.zdelta = p->zdelta;
     a.depth = out.depth_mm; a.depth16 = out.depth_u16; a.points = out.points; a.hit_voxel = (u64*)out.hit_voxel;
     a.vis = (unsigned*)out.visibility; a.vis_words32 = (int)(vis_words64 * 2);
+    a.vis_stride32 = vis_stride32 ? vis_stride32 : (unsigned)(vis_words64 * 2);
+    if (pub) a.pub = *pub; else std::memset(&a.pub, 0, sizeof a.pub);
     a.found_any = out.found_any; a.min_depth = out.min_depth;
     a.first_key = first_key; a.ray_key = ray_key; a.ray_occ = ray_occ;
     a.first_view = c->d_first_view.as<int>(); a.good_bits = c->d_good_bits.as<unsigned>(); a.view_mark = c->d_view_mark.as<int>();

@@ -28,6 +28,63 @@ __device__ __forceinline__ void raise_flag(int* p) {
     if (*p == 0) *p = 1;
 }
 
+// ---- fused exchange of a sharded sweep (dmf_comm.cuh) -------------------------------------------------------------------
+// Candidate views are sharded over the GPUs of a box; every GPU needs every view's visibility row (the set-cover consumer).
+// Rows are disjoint by view, so no collective is needed: the march kernel writes its views' rows in place in its OWN copy of
+// the gathered [n_views][row_words] buffer, and the last block to finish a view (a ticket per view) pushes the finished row
+// into every peer's copy through peer-mapped pointers -- plain 16-byte stores over NVLink, no cross-GPU atomics.  The block
+// that completes the last view of the pass raises this GPU's sequence flag in every peer (system-scope release); consumers
+// wait on their own copy of the flags (cuStreamWaitValue32), so the transfer overlaps the march view by view and nothing
+// but the flag wait remains after the kernel.
+#define DMF_MAX_PEERS 8
+struct PubTable {
+    unsigned* ticket;                    // [views of this pass] blocks that finished each view (zeroed per pass)
+    unsigned* views_done;                // views of this pass whose row has been pushed (zeroed per pass)
+    u64* peer_rows[DMF_MAX_PEERS];       // the gathered buffer (this pass's parity) in each OTHER member, as mapped here
+    unsigned* peer_flag[DMF_MAX_PEERS];  // this rank's flag word in each other member's flag array
+    const int* found_any;                // [views of this pass] per-view flag, copied into the row's extra word (null: 0)
+    int n_peers;
+    int n_views_pass;                    // views this GPU marches in the pass (all sub-launches together)
+    int row0, row_step;                  // global row of local view j = row0 + j * row_step (views are dealt round-robin)
+    unsigned row_words;                  // u64 words per gathered row: vis words + 1 (found flag), padded to an even count
+    unsigned vis_words;                  // u64 words of visibility per row
+    unsigned seq;                        // value to raise the flags to
+    int enabled;
+};
+
+// Called by EVERY thread of the block at the very end of a march kernel (after the block's last visibility atomic).
+// own_row: this view's row in this GPU's own gathered buffer (the kernel's visibility atomics went there).
+__device__ __forceinline__ void publish_view_row(const PubTable& pub, u64* own_row, int view_local, unsigned blocks_per_view) {
+    __shared__ int s_last;
+    __syncthreads();                                       // every warp of the block has issued its visibility atomics
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // cumulative: orders the block's atomics (observed through the barrier) before the ticket
+        s_last = atomicAdd(pub.ticket + view_local, 1u) == blocks_per_view - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();                                       // the other blocks' atomics of this view are visible (they precede their tickets)
+    const unsigned found = pub.found_any ? (unsigned)__ldcg(pub.found_any + view_local) : 0u;
+    const size_t g_off = (size_t)(pub.row0 + view_local * pub.row_step) * pub.row_words;
+    const unsigned n16 = pub.row_words >> 1;               // 16-byte pieces per row (row_words is even)
+    if (threadIdx.x == 0) own_row[pub.vis_words] = (u64)found;
+    for (unsigned i = threadIdx.x; i < n16; i += blockDim.x) {
+        uint4 val = __ldcg(reinterpret_cast<const uint4*>(own_row) + i);     // L2: the L1 may hold a stale copy from the read-before-atomic test
+        if (2u * i <= pub.vis_words && pub.vis_words < 2u * i + 2u) {          // the piece that holds the found word
+            if (pub.vis_words & 1u) { val.z = found; val.w = 0u; } else { val.x = found; val.y = 0u; }
+        }
+        for (int p = 0; p < pub.n_peers; p++) reinterpret_cast<uint4*>(pub.peer_rows[p] + g_off)[i] = val;
+    }
+    __threadfence_system();                                // this thread's peer stores are performed before anything that follows
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(pub.views_done, 1u) == (unsigned)pub.n_views_pass - 1u) {
+            __threadfence_system();                        // cumulative over the other finishing blocks' pushes (observed through views_done)
+            for (int p = 0; p < pub.n_peers; p++) *reinterpret_cast<volatile unsigned*>(pub.peer_flag[p]) = pub.seq;
+        }
+    }
+}
+
 // Packed FP32 pairs (sm_100 FFMA2 / FADD2): two independent IEEE round-to-nearest operations per issued instruction,
 // each half bit-identical to the scalar fmaf / __fadd_rn / __fsub_rn.  For loops that are bound by instruction issue,
 // not by the FMA pipe.  A pair lives in one 64-bit register (lo = .x, hi = .y); pack/unpack are register-pair renames.

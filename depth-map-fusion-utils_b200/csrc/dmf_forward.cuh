@@ -32,8 +32,10 @@ struct FwdArgs {
     unsigned short* depth16;           // [n_views][H][W]  same, 0xFFFF = none
     float* points;                     // [n_views][H][W][3]
     u64* hit_voxel;                    // [n_views][H][W]
-    unsigned* vis;                     // [n_views][vis_words32] bitset over occupied order
-    int vis_words32;
+    unsigned* vis;                     // bitset over occupied order, row of view v at vis + v * vis_stride32
+    int vis_words32;                   // 32-bit words of visibility per view
+    unsigned vis_stride32;             // row pitch (== vis_words32 for a dense [n_views][words] array; the gathered buffer of a sharded sweep interleaves ranks)
+    PubTable pub;                      // sharded sweep: push finished rows to the peer GPUs (pub.enabled)
     int* found_any;                    // [n_views]
     int* min_depth;                    // [n_views]  (INT_MAX-initialised; MINIMUM mode)
     // discovery-order bookkeeping (ids requested)
@@ -129,7 +131,7 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
             // (possibly stale, the bits only ever get set) cached read already shows the bit
             const unsigned peers = __match_any_sync(__activemask(), emit ? occ : -1);
             if (emit && (unsigned)(threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
-                unsigned* w = a.vis + ((unsigned)view * (unsigned)a.vis_words32 + ((unsigned)occ >> 5));
+                unsigned* w = a.vis + ((size_t)(unsigned)view * a.vis_stride32 + ((unsigned)occ >> 5));
                 const unsigned m = 1u << (occ & 31);
                 if (!(*w & m)) atomicOr(w, m);
             }
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
     }
 
     forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23, n_samples, n_inb, n_exact, n_f64, 0u);
+    if (a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)(unsigned)view * a.vis_stride32), view, gridDim.x * gridDim.y);
 }
 
 // ---- K1 with empty-space skipping -----------------------------------------------------------------------------
@@ -440,6 +443,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, 8) k_forward_skip(const FwdArgs 
     }
     const unsigned n_samples = active ? (unsigned)min(k, S) : 0u;
     forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23, n_samples, n_inb, n_exact, n_f64, n_skip);
+    if (a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)(unsigned)view * a.vis_stride32), view, gridDim.x * gridDim.y);
 }
 
 // Per view: how many leading probes every ray may skip.  All rays leave from the camera centre t; probe k of any ray is
@@ -634,6 +638,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
     }
     const unsigned n_samples = active ? (unsigned)min(k, S) : 0u;
     forward_epilogue<MODE>(a, s_cnt, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, m03, m13, m23, n_samples, n_inb, n_exact, n_f64, n_skip);
+    if (a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)(unsigned)view * a.vis_stride32), view, gridDim.x * gridDim.y);
 }
 
 // ---- K1 on distance bytes, line-first: k_forward_line ------------------------------------------------------------
@@ -1099,6 +1104,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
     if (MODE == 1 || MODE == 2) { t0 = s_pose[3]; t1 = s_pose[7]; t2 = s_pose[11]; }
     forward_epilogue<MODE>(a, nullptr, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, t0, t1, t2, n_samples, n_inb, n_exact, n_f64, n_skip);
+    if (MODE != 4 && a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)(unsigned)view * a.vis_stride32), view, gridDim.x * gridDim.y);
 #ifdef DMF_LINE_STATS
     if (lane == 0) {
         unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));

@@ -93,9 +93,11 @@ struct RevArgs {
     const u64* __restrict__ centroid_hash; // [n_occ]  (fast)
     const float* __restrict__ ax[3];       // float-accumulated axes (whole-grid variants)
     int nax[3];
-    unsigned* vis;                         // emitted
-    unsigned* unocc;                       // not occluded
+    unsigned* vis;                         // emitted; row of view v at vis + v * vis_stride32
+    unsigned* unocc;                       // not occluded; dense [n_views][vis_words32]
     int vis_words32;
+    unsigned vis_stride32;                 // == vis_words32 unless the rows live in the gathered buffer of a sharded sweep
+    PubTable pub;                          // sharded sweep (FAST only): push finished rows to the peer GPUs
     int* found_any;
     int viz;
     int* view_mark;
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(128, REV_MIN_BLOCKS) k_reverse(const RevArgs a
                 f_emit = emit;
                 if (emit && !FAST) {
                     if (a.viz) atomicOr(a.good_bits + (occ >> 5), 1u << (occ & 31)); // :112, :215
-                    if (a.vis) atomicOr(a.vis + (size_t)view * a.vis_words32 + (occ >> 5), 1u << (occ & 31));
+                    if (a.vis) atomicOr(a.vis + (size_t)view * a.vis_stride32 + (occ >> 5), 1u << (occ & 31));
                     if (a.emit_count) {
                         unsigned slot = atomicAdd(a.emit_count + view, 1u);
                         if (a.emit_list && slot < a.emit_cap) {
@@ -343,16 +345,16 @@ __global__ void __launch_bounds__(128, REV_MIN_BLOCKS) k_reverse(const RevArgs a
         // publishes its results with one atomic per bitset instead of one per voxel
         const unsigned mu = __ballot_sync(0xffffffffu, f_unocc), me = __ballot_sync(0xffffffffu, f_emit);
         if ((threadIdx.x & 31) == 0 && mu) {
-            const size_t w = (size_t)view * a.vis_words32 + (size_t)(t >> 5);
             if (a.found_any) raise_flag(a.found_any + view);
-            if (a.unocc) atomicOr(a.unocc + w, mu);
+            if (a.unocc) atomicOr(a.unocc + (size_t)view * a.vis_words32 + (size_t)(t >> 5), mu);
             if (me) {
                 if (a.viz) atomicOr(a.good_bits + (t >> 5), me);                     // :112, :215
-                if (a.vis) atomicOr(a.vis + w, me);
+                if (a.vis) atomicOr(a.vis + (size_t)view * a.vis_stride32 + (size_t)(t >> 5), me);
             }
         }
     }
     flush_counters(a.counters, n_samples, n_inb, n_hits, n_exact, n_oob, n_ties, n_runaway, n_f64, n_skip);
+    if (FAST && a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)view * a.vis_stride32), view, gridDim.x);
 }
 
 // ---- K7: willCollide (tests/CameraPathGen.cpp:128-156 and the unguarded copies in CameraMotionTSP.cpp:236-261,
