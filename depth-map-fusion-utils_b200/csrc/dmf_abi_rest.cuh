@@ -368,7 +368,11 @@ int dmf_or_reduce_dev(dmf_ctx* c, uint64_t* d_dst, const uint64_t* d_src, int n_
     return 0;
 }
 
+static int greedy_set_cover_strided(dmf_ctx* c, const uint64_t* d_bits, int n_sets, size_t words, size_t stride, int32_t* selected, int* n_selected);
 int dmf_greedy_set_cover_dev(dmf_ctx* c, const uint64_t* d_bits, int n_sets, size_t words, int32_t* selected, int* n_selected) {
+    return greedy_set_cover_strided(c, d_bits, n_sets, words, words, selected, n_selected);
+}
+static int greedy_set_cover_strided(dmf_ctx* c, const uint64_t* d_bits, int n_sets, size_t words, size_t stride, int32_t* selected, int* n_selected) {
     if (!c || !selected || !n_selected) return fail("null argument");
     DMF_CUDA(cudaSetDevice(c->device));
     *n_selected = 0;
@@ -380,9 +384,9 @@ int dmf_greedy_set_cover_dev(dmf_ctx* c, const uint64_t* d_bits, int n_sets, siz
     DMF_CUDA(cudaMemsetAsync(taken.p, 0, (size_t)n_sets * 4, st));
     DMF_CUDA(cudaEventRecord(c->ev_k0, st));
     while (true) {
-        k_cover_gain<<<n_sets, 256, 0, st>>>((const u64*)d_bits, covered.as<u64>(), taken.as<int>(), words, gain.as<unsigned>());
+        k_cover_gain<<<n_sets, 256, 0, st>>>((const u64*)d_bits, covered.as<u64>(), taken.as<int>(), words, stride, gain.as<unsigned>());
         k_cover_pick<<<1, 1024, 0, st>>>(gain.as<unsigned>(), n_sets, result.as<int>());
-        k_cover_apply<<<blocks_for(words, 256, 148 * 4), 256, 0, st>>>((const u64*)d_bits, covered.as<u64>(), taken.as<int>(), words, result.as<int>());
+        k_cover_apply<<<blocks_for(words, 256, 148 * 4), 256, 0, st>>>((const u64*)d_bits, covered.as<u64>(), taken.as<int>(), words, stride, result.as<int>());
         c->launches += 3;
         DMF_CUDA(cudaGetLastError());
         int res[2];

@@ -452,7 +452,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     DMF_CUDA(cudaEventRecord(c->ev_h1, st));
     c->hot_timed = true;
     DMF_CUDA(cudaGetLastError());
-    if (p->mode == DMF_MODE_CLASSIFY && c->n_occ) {
+    if (p->mode == DMF_MODE_CLASSIFY && c->n_occ && !c->defer_first_view) {
         k_apply_first_view<<<blocks_for(c->n_occ, 256, 1u << 30), 256, 0, st>>>(c->d_view_mark.as<int>(), c->d_first_view.as<int>(), (int)c->n_occ, view_id0);
         c->launches++;
         DMF_CUDA(cudaGetLastError());
@@ -917,3 +917,4 @@ int dmf_synchronize(dmf_ctx* c) {
 }  // extern "C"
 
 #include "dmf_abi_rest.cuh"
+#include "dmf_comm.cuh"

@@ -136,6 +136,7 @@ struct dmf_ctx {
     VolDev vol{};
     double bounds[6]; double voxel_size = 0; size_t n_occ = 0, n_normals = 0;
     std::vector<uint64_t> h_occ; std::vector<uint32_t> h_noff; std::vector<float> h_normals;   // host mirrors (dmf_volume_get_*)
+    bool defer_first_view = false;                    // sharded CLASSIFY: leave first_view for dmf_comm_fuse_marks instead of applying it locally
     bool mirror_valid = false;                        // false: the volume was built / received on the device, mirrors fetched on demand
     dmf::DevBuf d_scan, d_dt_tmp, d_macro_dist[2], d_err;   // scan scratch, distance-transform ping-pong, macro-cell distances, error words
     dmf::DevBuf d_bricks /* bit grid words */, d_macro, d_prefix, d_rank2occ, d_bytes, d_noff, d_normals, d_occ_ids, d_centroid_hash;

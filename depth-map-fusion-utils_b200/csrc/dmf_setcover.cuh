@@ -14,13 +14,14 @@ __global__ void k_or_reduce(u64* __restrict__ dst, const u64* __restrict__ src, 
 
 // gain[s] = |set_s \ covered| = popcount(bits[s] & ~covered)   (the set_difference of Algorithms.hpp:57), one block per set;
 // sets already selected get gain 0 (they are erased from set_ids, :83)
+// (stride = u64 words between consecutive sets: == words for a dense array, larger for the gathered buffer of a sharded sweep)
 __global__ void __launch_bounds__(256) k_cover_gain(const u64* __restrict__ bits, const u64* __restrict__ covered, const int* __restrict__ taken,
-                                                    size_t words, unsigned* __restrict__ gain) {
+                                                    size_t words, size_t stride, unsigned* __restrict__ gain) {
     __shared__ unsigned s_warp[8];
     const int s = blockIdx.x;
     unsigned cnt = 0;
     if (!taken[s]) {
-        const u64* b = bits + (size_t)s * words;
+        const u64* b = bits + (size_t)s * stride;
         for (size_t w = threadIdx.x; w < words; w += blockDim.x) cnt += __popcll(__ldg(b + w) & ~covered[w]);
     }
     for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
@@ -51,10 +52,10 @@ __global__ void __launch_bounds__(1024) k_cover_pick(const unsigned* __restrict_
     }
 }
 
-__global__ void k_cover_apply(const u64* __restrict__ bits, u64* __restrict__ covered, int* __restrict__ taken, size_t words, const int* __restrict__ result) {
+__global__ void k_cover_apply(const u64* __restrict__ bits, u64* __restrict__ covered, int* __restrict__ taken, size_t words, size_t stride, const int* __restrict__ result) {
     const int sel = result[0];
     if (sel < 0 || result[1] < 5) return;
-    const u64* b = bits + (size_t)sel * words;
+    const u64* b = bits + (size_t)sel * stride;
     for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) covered[w] |= b[w];
     if (blockIdx.x == 0 && threadIdx.x == 0) taken[sel] = 1;
 }

@@ -36,6 +36,10 @@ class ReverseOut(C.Structure):
     ]
 
 
+class SweepOut(C.Structure):
+    _fields_ = [("visibility", C.c_void_p), ("found_any", C.c_void_p), ("rows_to_host", C.c_int)]
+
+
 # every symbol include/dmf_b200.h declares: name -> (restype, argtypes)
 vp, fp, dp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)
 u64p, u32p, i32p, i64p, u8p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_uint8)
@@ -75,6 +79,23 @@ SYMBOLS = {
     "dmf_greedy_set_cover": (C.c_int, [vp, u64p, C.c_int, C.c_size_t, i32p, ip]),
     "dmf_greedy_set_cover_dev": (C.c_int, [vp, vp, C.c_int, C.c_size_t, i32p, ip]),
     "dmf_or_reduce_dev": (C.c_int, [vp, vp, vp, C.c_int, C.c_size_t, vp]),
+    "dmf_comm_init_all": (C.c_int, [C.POINTER(vp), C.c_int]),
+    "dmf_comm_unique_id": (C.c_int, [vp]),
+    "dmf_comm_init_rank": (C.c_int, [C.POINTER(vp), vp, vp, C.c_int, C.c_int]),
+    "dmf_comm_destroy": (None, [vp]),
+    "dmf_comm_info": (C.c_int, [vp, ip, ip, ip, ip]),
+    "dmf_comm_ctx": (vp, [vp, C.c_int]),
+    "dmf_comm_set_camera": (C.c_int, [vp, fp, C.c_int, C.c_int]),
+    "dmf_comm_replicate_volume": (C.c_int, [vp, C.c_int]),
+    "dmf_comm_synchronize": (C.c_int, [vp]),
+    "dmf_sweep_forward": (C.c_int, [vp, C.POINTER(ForwardParams), fp, C.c_int, C.POINTER(SweepOut)]),
+    "dmf_sweep_reverse": (C.c_int, [vp, C.c_int, fp, C.c_int, C.POINTER(SweepOut)]),
+    "dmf_sweep_forward_dev": (C.c_int, [vp, C.POINTER(ForwardParams), C.POINTER(vp), C.c_int, C.POINTER(vp)]),
+    "dmf_sweep_reverse_dev": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp)]),
+    "dmf_sweep_gathered_dev": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), ip]),
+    "dmf_sweep_set_cover": (C.c_int, [vp, i32p, ip]),
+    "dmf_comm_fuse_observed": (C.c_int, [vp]),
+    "dmf_comm_fuse_marks": (C.c_int, [vp, C.c_int]),
     "dmf_host_angle_test": (C.c_int, [fp]),
     "dmf_set_reverse_format": (C.c_int, [vp, C.c_int]),
     "dmf_selftest_div1000": (C.c_int, [vp, u64p]),

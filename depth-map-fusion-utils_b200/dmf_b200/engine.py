@@ -55,6 +55,9 @@ class Context:
         return cls._default
 
     def close(self):
+        if getattr(self, "h", None) and getattr(self, "_borrowed", False):
+            self.h = None                                       # owned by a Comm group (dmf_comm_init_all)
+            return
         if getattr(self, "h", None):
             self.lib.dmf_destroy(self.h)
             self.h = None

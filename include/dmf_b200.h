@@ -204,6 +204,67 @@ int dmf_greedy_set_cover_dev(dmf_ctx* ctx, const uint64_t* d_bitsets, int n_sets
 /* d_dst[w] |= OR over r of d_src[r*words + w];  device pointers, enqueued on stream */
 int dmf_or_reduce_dev(dmf_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int n_src, size_t words, void* stream);
 
+/* ---- multi-GPU: the candidate-view sweep sharded over the GPUs of one box ---------------------------------------------
+ * Replaces the per-view loops of the reference's drivers (tests/SetCover.cpp:218-240, tests/CameraMotionPlanner.cpp:334-356,
+ * tests/CameraPathGen.cpp:158-180: one reverseRayTraceFast / rayTraceAndGetPoints call per candidate view, one CPU thread).
+ * Views are dealt round-robin (GPU r marches views r, r+N, ...), the volume is replicated on every GPU, and every GPU ends up
+ * with every view's visibility row: the march kernels push finished rows into the peers' buffers over NVLink themselves
+ * (peer-mapped stores; no collective call), or -- where the GPUs cannot address each other, or with DMF_COMM_EXCHANGE=nccl --
+ * the rows travel through ncclAllGather.  NCCL is loaded with dlopen when a group is formed. */
+typedef struct dmf_comm dmf_comm;
+#define DMF_UNIQUE_ID_BYTES 128
+enum { DMF_EXCHANGE_NONE = 0, DMF_EXCHANGE_FUSED_P2P = 1, DMF_EXCHANGE_NCCL = 2 };
+enum { DMF_SWEEP_ROWS_OWN = 0, DMF_SWEEP_ROWS_ALL = 1 };
+
+/* ONE process drives n_gpus devices (0 .. n_gpus-1; n_gpus <= 0: all visible, at most 8): creates a context per device,
+ * enables peer access, forms the NCCL communicators (ncclCommInitAll).  The shape the reference's single-threaded drivers need. */
+int dmf_comm_init_all(dmf_comm** out, int n_gpus);
+/* One process per GPU (torchrun / MPI): rank 0 makes an id (dmf_comm_unique_id: ncclGetUniqueId), shares it out of band, every
+ * rank calls dmf_comm_init_rank with its own context (ncclCommInitRank; peer buffers are mapped with CUDA IPC). */
+int dmf_comm_unique_id(void* id /* DMF_UNIQUE_ID_BYTES */);
+int dmf_comm_init_rank(dmf_comm** out, dmf_ctx* ctx, const void* unique_id, int rank, int world);
+void dmf_comm_destroy(dmf_comm* comm);
+int dmf_comm_info(dmf_comm* comm, int* world, int* n_local, int* first_rank, int* exchange /* DMF_EXCHANGE_* */);
+dmf_ctx* dmf_comm_ctx(dmf_comm* comm, int local_index);           /* the context of local member i (0 .. n_local-1) */
+int dmf_comm_set_camera(dmf_comm* comm, const float K[9], int height, int width);
+/* The volume uploaded on rank `root` goes to every other GPU, GPU to GPU: only the occupied id list and the normals travel
+ * (cudaMemcpyPeer / ncclBroadcast), each GPU rebuilds its march structures on the device.  Collective. */
+int dmf_comm_replicate_volume(dmf_comm* comm, int root);
+int dmf_comm_synchronize(dmf_comm* comm);
+
+/* Host outputs of a sweep, in VIEW order; any pointer may be NULL. */
+typedef struct {
+    uint64_t* visibility;   /* [n_views][dmf_visibility_words]                                                        */
+    int32_t*  found_any;    /* [n_views]                                                                              */
+    int       rows_to_host; /* one process per GPU: DMF_SWEEP_ROWS_OWN copies back only the rows this rank marched (the others
+                               are left untouched), DMF_SWEEP_ROWS_ALL the whole gathered array.  A single-process group always
+                               fills the whole array: every GPU sends its own rows over its own PCIe link.                  */
+} dmf_sweep_out;
+
+/* n_views consecutive calls of one forward routine (POINTS, GOOD_POINTS or CLASSIFY; RayTracingEngine.hpp:311,377,447), resp. of
+ * reverseRayTraceFast (:136-226), sharded over the group.  poses = the WHOLE list [n_views][12] (every rank passes the same
+ * list).  Collective; synchronises when `out` is given.  Afterwards every member holds all rows (dmf_sweep_gathered_dev) and
+ * dmf_sweep_set_cover runs Algorithms::greedySetCover (Algorithms.hpp:38-86) over them.  After a CLASSIFY sweep call
+ * dmf_comm_fuse_marks; with DMF_FWD_CARVE call dmf_comm_fuse_observed. */
+int dmf_sweep_forward(dmf_comm* comm, const dmf_forward_params* p, const float* poses, int n_views, const dmf_sweep_out* out);
+int dmf_sweep_reverse(dmf_comm* comm, int fast, const float* poses, int n_views, const dmf_sweep_out* out);
+/* The same with each local member's poses already on its device (d_poses[i][j] = global view first_rank + i + j * world) and
+ * nothing copied back: enqueues on streams[i] (NULL array / entry = the member's own stream) and returns; the last thing
+ * enqueued on each stream is the wait for the peers' rows. */
+int dmf_sweep_forward_dev(dmf_comm* comm, const dmf_forward_params* p, const float* const* d_poses, int n_views, void* const* streams);
+int dmf_sweep_reverse_dev(dmf_comm* comm, int fast, const float* const* d_poses, int n_views, void* const* streams);
+/* the gathered rows of the last sweep on local member i: [n_views] rows of row_words uint64 (vis_words of visibility, then one
+ * word holding found_any, then padding) */
+int dmf_sweep_gathered_dev(dmf_comm* comm, int local_index, uint64_t** d_rows, size_t* row_words, size_t* vis_words, int* n_views);
+int dmf_sweep_set_cover(dmf_comm* comm, int32_t* selected /* capacity n_views */, int* n_selected);
+
+/* Carve mode over the group: bitwise OR of the members' observed grids, as a reduce-scatter + all-gather over peer memory
+ * (every GPU reduces 1/N of the words from all peers and pushes the result back); afterwards every grid is the union. */
+int dmf_comm_fuse_observed(dmf_comm* comm);
+/* After a sharded CLASSIFY sweep: Voxel::view = view_id0 + the smallest global view index that hit the voxel (first-wins in call
+ * order, RayTracingEngine.hpp:354-355) where it was still 0 -- a min-reduce over the GPUs --, Voxel::good = OR (:356-370). */
+int dmf_comm_fuse_marks(dmf_comm* comm, int view_id0);
+
 /* ---- host utility (no GPU needed) ------------------------------------------------------------- */
 /* The reference's good-point test  degree(acos(n.v)) in [0,90]  (CommonUtilities.hpp:17, RayTracingEngine.hpp:211-212)
  * depends on the HOST libm's float acos.  The library bisects it once; the kernels then test dot_min <= d <= 1.
