@@ -5,10 +5,15 @@
 // tests/CameraMotionPlanner.cpp:334-356, tests/CameraPathGen.cpp:158-180).  Views are independent, so they are dealt
 // round-robin over the GPUs (rank r marches views r, r+N, ...: neighbouring views cost about the same, so every GPU gets
 // the same mix), with the volume replicated on every GPU.  What has to cross GPUs:
-//   * every view's visibility row, to every GPU (the set-cover consumer): FUSED into the march kernels -- the last block of
-//     a view pushes the finished row into every peer's gathered buffer over NVLink (publish_view_row, dmf_device.cuh), the
-//     block that ends the pass raises a sequence flag in every peer, consumers wait on their own flag words
-//     (cuStreamWaitValue32).  No collective call remains.  Where peer mapping is not possible the rows go through
+//   * every view's visibility row, to every GPU (the set-cover consumer).  Rows are disjoint by view, so no collective is
+//     needed: the march writes its rows in place in its own copy of the gathered [n_views][row_words] buffer, and the finished
+//     rows are stored straight into every peer's copy through peer-mapped pointers (16-byte stores over NVLink); a sequence
+//     flag raised in every peer (system-scope release) tells consumers, which wait on their own flag words
+//     (cuStreamWaitValue32), that this GPU's rows have landed.  Two issuers of those stores exist: a small push kernel right
+//     behind the march (k_publish_rows, the default) and the march kernels' own epilogue (publish_view_row in dmf_device.cuh:
+//     a ticket per view finds the last block, DMF_COMM_EXCHANGE=epilogue).  Measured on B200 the epilogue variant costs the
+//     march ~20 % (barrier + fence + atomic round trip at the tail of every ~8 us block) to overlap a transfer that takes a
+//     few microseconds, so the push kernel is the default.  Where peer mapping is not possible the rows go through
 //     ncclAllGather + an interleave kernel instead (DMF_COMM_EXCHANGE=nccl forces that path: the A/B baseline);
 //   * the observed (occupied/free) grids and the Voxel::view / Voxel::good marks of a sharded fusion run: bitwise OR, resp.
 //     min over the first view id, as a reduce-scatter + all-gather over peer memory: every GPU reduces 1/N of the words from
@@ -84,6 +89,34 @@ __global__ void k_wait_flags(const unsigned* flags, const int* ranks, int n, uns
     __threadfence_system();
 }
 
+// Default exchange: ONE small kernel behind the march pushes this GPU's finished rows into every peer's gathered buffer
+// (16-byte peer stores over NVLink), writes each row's found word, and the block that finishes last raises this GPU's flag
+// in every peer.  Measured against the in-kernel epilogue (publish_view_row) it wins: the ticket protocol adds a barrier, a
+// fence and an atomic round trip to the tail of every 8-microsecond march block (+20 % on k_forward_line), while the rows of
+// a whole step are 2 MB -- a few microseconds of NVLink time that need no overlap.
+__global__ void __launch_bounds__(256) k_publish_rows(const PubTable pub, u64* __restrict__ own_rows, size_t pitch_words) {
+    const int j = blockIdx.x;                                  // local view
+    u64* const row = own_rows + (size_t)j * pitch_words;
+    const unsigned found = pub.found_any ? (unsigned)pub.found_any[j] : 0u;
+    const size_t g_off = (size_t)(pub.row0 + j * pub.row_step) * pub.row_words;
+    const unsigned n16 = pub.row_words >> 1;
+    for (unsigned i = threadIdx.x; i < n16; i += blockDim.x) {
+        uint4 val = reinterpret_cast<const uint4*>(row)[i];
+        if (2u * i <= pub.vis_words && pub.vis_words < 2u * i + 2u) {           // the piece that holds the found word
+            if (pub.vis_words & 1u) { val.z = found; val.w = 0u; } else { val.x = found; val.y = 0u; }
+            reinterpret_cast<uint4*>(row)[i] = val;
+        }
+        for (int p = 0; p < pub.n_peers; p++) reinterpret_cast<uint4*>(pub.peer_rows[p] + g_off)[i] = val;
+    }
+    if (pub.n_peers == 0) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(pub.views_done, 1u) == (unsigned)pub.n_views_pass - 1u) {
+        __threadfence_system();
+        for (int p = 0; p < pub.n_peers; p++) *reinterpret_cast<volatile unsigned*>(pub.peer_flag[p]) = pub.seq;
+    }
+}
+
 struct PeerReduceArgs { unsigned* stage[DMF_MAX_PEERS]; int world; size_t lo, hi; };     // [lo, hi) in 16-byte units: this rank's slice
 // OP 0: bitwise OR, OP 1: min over int32.  Reads the slice from every member's staging copy (peer loads), pushes the result
 // into every member's staging copy (peer stores).  Slices are disjoint by rank, so nobody reads what another rank writes.
@@ -139,7 +172,7 @@ struct dmf_comm {
     int world = 1, n_local = 1, rank0 = 0;
     bool single_process = true, owns_ctx = false;
     bool p2p = false;                            // every member can address every other member's arena
-    int exchange = 0;                            // 0: fused peer stores, 1: NCCL all-gather
+    int exchange = 0;                            // 0: peer stores by a push kernel behind the march, 1: NCCL all-gather, 2: peer stores from the march kernels' epilogue
     std::vector<CommMember> m;
     size_t gather_cap = 0, stage_cap = 0;        // bytes per gather buffer / of the staging region (same on every rank)
     unsigned seq = 0, rseq = 0;                  // sequence numbers of the gather and reduce flag protocols
@@ -273,20 +306,22 @@ inline size_t reduce_stage_bytes(const dmf_comm* g) {
 struct SweepSpec {
     bool reverse = false; int fast = 1, viz = 0;
     const dmf_forward_params* fwd = nullptr;
+    const dmf_forward_out* const* d_out = nullptr;    // optional per-member device outputs (depth / points / hit voxels of the member's own views)
 };
 
 // Enqueue one member's share of a sweep on `st`: zero its rows and tickets, march with the publish table, then (NCCL path)
 // the all-gather + interleave.  d_poses: this member's views (j-th = global view rank + j * world), already on its device.
-int sweep_member_enqueue(dmf_comm* g, CommMember& mm, const SweepSpec& spec, const float* d_poses, int n_views, cudaStream_t st) {
+int sweep_member_enqueue(dmf_comm* g, CommMember& mm, const SweepSpec& spec, const float* d_poses, int n_views, cudaStream_t st, const dmf_forward_out* extra) {
     dmf_ctx* c = mm.ctx;
     DMF_CUDA(cudaSetDevice(c->device));
     const int n_my = my_view_count(n_views, mm.rank, g->world);
     mm.n_my = n_my;
     const size_t rw = g->last_row_words, vw = g->last_vis_words;
     u64* rows = (u64*)(mm.arena + off_gather(g, g->last_parity));
-    const bool fused = g->exchange == 0 || g->world == 1;
-    // the kernel's visibility atomics go straight into this member's rows of its own gathered buffer (fused), or into a dense
-    // local array that NCCL gathers afterwards
+    const bool fused = g->exchange != 1 || g->world == 1;    // peer stores (push kernel or epilogue)
+    const bool epilogue = g->exchange == 2 && g->world > 1;
+    // the kernel's visibility atomics go straight into this member's rows of its own gathered buffer (peer-store paths), or into
+    // a dense local array that NCCL gathers afterwards
     u64* my_rows; size_t pitch_words;
     if (fused) { my_rows = rows + (size_t)mm.rank * rw; pitch_words = (size_t)g->world * rw; }
     else { my_rows = mm.d_dense.as<u64>(); pitch_words = rw; }
@@ -314,13 +349,19 @@ int sweep_member_enqueue(dmf_comm* g, CommMember& mm, const SweepSpec& spec, con
         if (!spec.reverse) {
             FwdPlan pl; DMF_TRY(plan_forward(c, spec.fwd, pl));
             dmf_forward_out o{};
+            if (extra) { o.depth_mm = extra->depth_mm; o.depth_u16 = extra->depth_u16; o.points = extra->points; o.hit_voxel = extra->hit_voxel; }
             o.visibility = (uint64_t*)my_rows; o.found_any = mm.d_found.as<int32_t>();
             c->defer_first_view = spec.fwd->mode == DMF_MODE_CLASSIFY && g->world > 1;    // resolved across GPUs by dmf_comm_fuse_marks
-            const int rc = enqueue_forward(c, spec.fwd, pl, d_poses, n_my, spec.fwd->view_id0, o, nullptr, nullptr, nullptr, st, 0, nullptr, (unsigned)(pitch_words * 2), fused ? &pub : nullptr);
+            const int rc = enqueue_forward(c, spec.fwd, pl, d_poses, n_my, spec.fwd->view_id0, o, nullptr, nullptr, nullptr, st, 0, nullptr, (unsigned)(pitch_words * 2), epilogue ? &pub : nullptr);
             c->defer_first_view = false;
             DMF_TRY(rc);
         } else {
-            DMF_TRY(enqueue_reverse(c, spec.fast, spec.viz, d_poses, n_my, (unsigned*)my_rows, nullptr, mm.d_found.as<int>(), nullptr, nullptr, 0, st, (unsigned)(pitch_words * 2), fused ? &pub : nullptr));
+            DMF_TRY(enqueue_reverse(c, spec.fast, spec.viz, d_poses, n_my, (unsigned*)my_rows, nullptr, mm.d_found.as<int>(), nullptr, nullptr, 0, st, (unsigned)(pitch_words * 2), epilogue ? &pub : nullptr));
+        }
+        if (fused && !epilogue) {            // the push kernel: found words into the rows, rows to the peers, flags
+            k_publish_rows<<<n_my, 256, 0, st>>>(pub, my_rows, pitch_words);
+            c->launches++;
+            DMF_CUDA(cudaGetLastError());
         }
         DMF_TRY(mark_last(c, st));
     } else if (fused && g->world > 1) {
@@ -370,7 +411,7 @@ int sweep_begin(dmf_comm* g, int n_views) {
     for (auto& mm : g->m) {
         DMF_CUDA(cudaSetDevice(mm.ctx->device));
         DMF_TRY(mm.d_ticket.reserve(((size_t)n_max + 2) * 4)); DMF_TRY(mm.d_found.reserve(((size_t)n_max + 1) * 4)); DMF_TRY(mm.d_poses.reserve(((size_t)n_max + 1) * 48));
-        if (g->exchange != 0 && g->world > 1) {
+        if (g->exchange == 1 && g->world > 1) {
             DMF_TRY(mm.d_dense.reserve(std::max<size_t>((size_t)n_max * rw * 8, 256))); DMF_TRY(mm.d_nccl_gather.reserve(std::max<size_t>((size_t)g->world * n_max * rw * 8, 256)));
             DMF_CUDA(cudaMemsetAsync(mm.d_dense.p, 0, std::max<size_t>((size_t)n_max * rw * 8, 256), mm.ctx->stream));       // rows beyond n_my stay zero
         }
@@ -400,13 +441,13 @@ int sweep_run(dmf_comm* g, const SweepSpec& spec, const float* host_poses, const
         const float* dp = d_poses ? d_poses[i] : mm.d_poses.as<float>();
         if (!d_poses && n_my)            // this member's views out of the whole list: rows rank, rank + world, ...
             DMF_CUDA(cudaMemcpy2DAsync(mm.d_poses.p, 48, host_poses + 12 * (size_t)mm.rank, 48 * (size_t)g->world, 48, (size_t)n_my, cudaMemcpyHostToDevice, st));
-        DMF_TRY(sweep_member_enqueue(g, mm, spec, dp, n_views, st));
+        DMF_TRY(sweep_member_enqueue(g, mm, spec, dp, n_views, st, spec.d_out ? spec.d_out[i] : nullptr));
     }
-    if (g->exchange != 0 && g->world > 1) DMF_TRY(sweep_exchange_nccl(g, n_views, streams));
+    if (g->exchange == 1 && g->world > 1) DMF_TRY(sweep_exchange_nccl(g, n_views, streams));
     for (size_t i = 0; i < g->m.size(); i++) {
         CommMember& mm = g->m[i];
         cudaStream_t st = streams && streams[i] ? (cudaStream_t)streams[i] : mm.ctx->stream;
-        if (g->exchange == 0) DMF_TRY(comm_wait(g, mm, kFlagGather, g->seq, st));
+        if (g->exchange != 1) DMF_TRY(comm_wait(g, mm, kFlagGather, g->seq, st));
         if (!out) continue;
         DMF_CUDA(cudaSetDevice(mm.ctx->device));
         const u64* rows = (const u64*)(mm.arena + off_gather(g, g->last_parity));
@@ -433,7 +474,7 @@ int comm_reduce(dmf_comm* g, const std::vector<unsigned*>& bufs, size_t n32, int
     if (g->world == 1 || n32 == 0) return 0;
     const size_t n16 = (n32 + 3) / 4;                         // 16-byte units; the staging tail beyond n32 is padded with the identity
     DMF_TRY(comm_reserve(g, std::max<size_t>(g->gather_cap, 256), std::max(n16 * 16, reduce_stage_bytes(g))));
-    const bool fused = g->exchange == 0;
+    const bool fused = g->exchange != 1;
     NcclApi* nc = nccl_api();
     if (!fused && op == 0) for (auto& mm : g->m) { DMF_CUDA(cudaSetDevice(mm.ctx->device)); DMF_TRY(mm.d_nccl_gather.reserve((size_t)g->world * n16 * 16)); }
     g->rseq++;
@@ -507,7 +548,7 @@ int comm_finish_init(dmf_comm* g) {
     else cudaGetLastError();
     const char* ex = std::getenv("DMF_COMM_EXCHANGE");
     if (ex && std::string(ex) == "nccl") g->p2p = false;             // forced: the A/B baseline (must be set on every rank alike)
-    g->exchange = g->p2p ? 0 : 1;
+    g->exchange = g->p2p ? ((ex && std::string(ex) == "epilogue") ? 2 : 0) : 1;
     if (g->world > DMF_MAX_PEERS) return fail("at most %d GPUs per group (got %d)", DMF_MAX_PEERS, g->world);
     if (g->exchange == 1 && g->world > 1 && (!nccl_api() || !g->m[0].nccl)) return fail("GPUs cannot address each other and NCCL is not available (%s)", nccl_api() ? "no communicator" : "dlopen failed");
     for (auto& mm : g->m) mm.peer.assign(g->world, nullptr);
@@ -560,7 +601,11 @@ int dmf_comm_init_all(dmf_comm** out, int n_gpus) {
             else if (e != cudaSuccess) { cudaGetLastError(); g->p2p = false; }
         }
     }
-    if (n_gpus > 1) {
+    // one process, peers addressable: nothing needs NCCL (and ncclCommInitAll costs seconds); it is formed only as the fallback
+    // exchange, or when DMF_COMM_EXCHANGE=nccl asks for the A/B baseline
+    const char* ex_env = std::getenv("DMF_COMM_EXCHANGE");
+    const bool want_nccl = !g->p2p || (ex_env && std::string(ex_env) == "nccl");
+    if (n_gpus > 1 && want_nccl) {
         if (NcclApi* nc = nccl_api()) {
             std::vector<NcclComm> comms(n_gpus, nullptr); std::vector<int> devs(n_gpus);
             for (int i = 0; i < n_gpus; i++) devs[i] = i;
@@ -618,7 +663,7 @@ int dmf_comm_info(dmf_comm* g, int* world, int* n_local, int* first_rank, int* e
     if (world) *world = g->world;
     if (n_local) *n_local = g->n_local;
     if (first_rank) *first_rank = g->rank0;
-    if (exchange) *exchange = g->world == 1 ? DMF_EXCHANGE_NONE : (g->exchange == 0 ? DMF_EXCHANGE_FUSED_P2P : DMF_EXCHANGE_NCCL);
+    if (exchange) *exchange = g->world == 1 ? DMF_EXCHANGE_NONE : (g->exchange == 0 ? DMF_EXCHANGE_P2P_PUSH : (g->exchange == 1 ? DMF_EXCHANGE_NCCL : DMF_EXCHANGE_P2P_EPILOGUE));
     return 0;
 }
 
@@ -694,10 +739,10 @@ int dmf_sweep_forward(dmf_comm* g, const dmf_forward_params* p, const float* pos
     SweepSpec s; s.reverse = false; s.fwd = p;
     return sweep_run(g, s, poses, nullptr, n_views, nullptr, out);
 }
-int dmf_sweep_forward_dev(dmf_comm* g, const dmf_forward_params* p, const float* const* d_poses, int n_views, void* const* streams) {
+int dmf_sweep_forward_dev(dmf_comm* g, const dmf_forward_params* p, const float* const* d_poses, int n_views, const dmf_forward_out* const* d_out, void* const* streams) {
     if (!g || !p || !d_poses) return fail("null argument");
     if (p->mode == DMF_MODE_MINIMUM || p->mode == DMF_MODE_MARK) return fail("dmf_sweep_forward supports POINTS, GOOD_POINTS and CLASSIFY");
-    SweepSpec s; s.reverse = false; s.fwd = p;
+    SweepSpec s; s.reverse = false; s.fwd = p; s.d_out = d_out;
     return sweep_run(g, s, nullptr, d_poses, n_views, streams, nullptr);
 }
 int dmf_sweep_reverse(dmf_comm* g, int fast, const float* poses, int n_views, const dmf_sweep_out* out) {

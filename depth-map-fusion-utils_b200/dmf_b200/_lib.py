@@ -90,7 +90,7 @@ SYMBOLS = {
     "dmf_comm_synchronize": (C.c_int, [vp]),
     "dmf_sweep_forward": (C.c_int, [vp, C.POINTER(ForwardParams), fp, C.c_int, C.POINTER(SweepOut)]),
     "dmf_sweep_reverse": (C.c_int, [vp, C.c_int, fp, C.c_int, C.POINTER(SweepOut)]),
-    "dmf_sweep_forward_dev": (C.c_int, [vp, C.POINTER(ForwardParams), C.POINTER(vp), C.c_int, C.POINTER(vp)]),
+    "dmf_sweep_forward_dev": (C.c_int, [vp, C.POINTER(ForwardParams), C.POINTER(vp), C.c_int, C.POINTER(C.POINTER(ForwardOut)), C.POINTER(vp)]),
     "dmf_sweep_reverse_dev": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp)]),
     "dmf_sweep_gathered_dev": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), ip]),
     "dmf_sweep_set_cover": (C.c_int, [vp, i32p, ip]),

@@ -17,7 +17,8 @@ from . import _lib
 from ._lib import ForwardParams, SweepOut, check
 from .engine import Context, GRID_BYTE, MODE_POINTS, _poses12
 
-EXCHANGE_NAMES = {0: "none (1 GPU)", 1: "fused peer stores from the march kernels (NVLink)", 2: "ncclAllGather"}
+EXCHANGE_NAMES = {0: "none (1 GPU)", 1: "peer-mapped stores over NVLink by a push kernel behind the march", 2: "ncclAllGather",
+                  3: "peer-mapped stores over NVLink from the march kernels' epilogue (ticket per view)"}
 ROWS_OWN, ROWS_ALL = 0, 1
 
 

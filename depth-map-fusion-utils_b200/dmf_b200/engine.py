@@ -152,6 +152,25 @@ class VoxelVolume:
         self._bounds = None
         self._req_dims = None
 
+    @classmethod
+    def attach(cls, ctx: "Context") -> "VoxelVolume":
+        """A host-side handle on the volume that is ALREADY on ctx's device (replicated from a peer GPU by
+        Comm.replicate_volume, or uploaded through the C ABI directly): nothing is uploaded again."""
+        v = cls(ctx)
+        dims = np.zeros(3, np.int32)
+        deltas = np.zeros(3, np.float64)
+        vs, no, nn = C.c_double(), C.c_size_t(), C.c_size_t()
+        check(ctx.lib.dmf_volume_info(ctx.h, _ptr(dims, C.c_int), _ptr(deltas, C.c_double), C.byref(vs), C.byref(no), C.byref(nn)))
+        v.xdim_, v.ydim_, v.zdim_ = (int(d) for d in dims)
+        v.xdelta_, v.ydelta_, v.zdelta_ = (float(d) for d in deltas)
+        v.voxel_size_, v.n_normals_ = vs.value, nn.value
+        v.occupied_cells_ = np.zeros(no.value, np.uint64)
+        if no.value:
+            check(ctx.lib.dmf_volume_get_occupied(ctx.h, _ptr(v.occupied_cells_, C.c_uint64)))
+        v._dirty = False
+        ctx._volume_token = v
+        return v
+
     # -- Volume.hpp:89-128
     def setDimensions(self, xmin, xmax, ymin, ymax, zmin, zmax):
         self._bounds = np.array([xmin, xmax, ymin, ymax, zmin, zmax], np.float64)

@@ -113,9 +113,10 @@ inline std::vector<Eigen::Affine3f> repositionCamerasSampled(const std::vector<E
 
 // vector<unsigned long long int> setCover(RayTracingEngine engine, VoxelVolume& volume, vector<Affine3f> camera_locations,
 //                                         int resolution_single_dimension, bool sparse = true)
-// (tests/SetCover.cpp:214-244): reverseRayTraceFast for every location + Algorithms::greedySetCover, as one batched
-// reverse march into visibility bitsets and the device greedy loop.  Returns the selected location indices in
-// selection order, like the reference.
+// (tests/SetCover.cpp:214-244): reverseRayTraceFast for every location + Algorithms::greedySetCover.  The per-view loop
+// (:218-240) is dealt over every GPU of the process's group (dmf_sweep_reverse: views r, r+N, ... on GPU r, the volume
+// replicated GPU to GPU, finished visibility rows pushed to the peers by the march kernels), then the greedy loop runs on
+// the device over the gathered rows.  Returns the selected location indices in selection order, like the reference.
 template <class Volume>
 inline std::vector<unsigned long long int> setCover(RayTracingEngine engine, Volume& volume, const std::vector<Eigen::Affine3f>& camera_locations,
                                                     int /*resolution_single_dimension*/ = 1, bool /*sparse*/ = true)
@@ -126,6 +127,12 @@ inline std::vector<unsigned long long int> setCover(RayTracingEngine engine, Vol
     const size_t words = (size_t)dmf_visibility_words(ctx);
     std::vector<float> poses(12 * n);
     for (size_t i = 0; i < n; i++) pose12(camera_locations[i], &poses[12 * i]);
+    if (dmf_comm* comm = sync_group(engine.cam_, volume)) {
+        must(dmf_sweep_reverse(comm, 1, poses.data(), (int)n, nullptr), "dmf_sweep_reverse");
+        std::vector<int32_t> selected(n); int n_selected = 0;
+        must(dmf_sweep_set_cover(comm, selected.data(), &n_selected), "dmf_sweep_set_cover");
+        return std::vector<unsigned long long int>(selected.begin(), selected.begin() + n_selected);
+    }
     std::vector<uint64_t> vis(n * (words ? words : 1));
     dmf_reverse_out out = {};
     out.visibility = vis.data();

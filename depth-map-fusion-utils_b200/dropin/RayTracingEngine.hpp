@@ -37,16 +37,31 @@ inline void must(int rc, const char* what)
     if (rc != 0) { std::fprintf(stderr, "libdmf_b200: %s failed: %s\n", what, dmf_last_error()); std::abort(); }
 }
 
+// One per process.  By default it forms a group over every visible GPU (dmf_comm_init_all: this one host thread drives them
+// all): single-view calls run on GPU 0, the per-view loops of the drivers (setCover) are dealt over all of them.
+// DMF_GPUS=n limits the group to the first n devices; DMF_DEVICE=d pins everything to one device (no group).
 struct Global {
     dmf_ctx* ctx = nullptr;
+    dmf_comm* comm = nullptr;
     const void* volume = nullptr;
     unsigned long long revision = ~0ull;
+    unsigned long long replicated_revision = ~0ull;     // revision the other GPUs of the group hold
+    const void* replicated_volume = nullptr;
     Global()
     {
         const char* dev = std::getenv("DMF_DEVICE");
-        must(dmf_create(&ctx, dev ? std::atoi(dev) : 0), "dmf_create");
+        const char* gpus = std::getenv("DMF_GPUS");
+        if (dev) { must(dmf_create(&ctx, std::atoi(dev)), "dmf_create"); return; }
+        must(dmf_comm_init_all(&comm, gpus ? std::atoi(gpus) : 0), "dmf_comm_init_all");
+        ctx = dmf_comm_ctx(comm, 0);
     }
-    ~Global() { dmf_destroy(ctx); }
+    ~Global() { if (comm) dmf_comm_destroy(comm); else dmf_destroy(ctx); }
+    int gpus() const
+    {
+        int world = 1;
+        if (comm) dmf_comm_info(comm, &world, nullptr, nullptr, nullptr);
+        return world;
+    }
 };
 inline Global& global() { static Global g; return g; }
 
@@ -71,6 +86,21 @@ inline dmf_ctx* sync_volume(Volume& volume)
         g.volume = &volume; g.revision = volume.revision();
     }
     return g.ctx;
+}
+
+// the group's other GPUs hold the current volume and camera (GPU 0 -> peers, GPU to GPU); no-op for a single device
+template <class Volume>
+inline dmf_comm* sync_group(Camera& cam, Volume& volume)
+{
+    Global& g = global();
+    sync_volume(volume);
+    if (!g.comm) return nullptr;
+    must(dmf_comm_set_camera(g.comm, cam.intrinsics().data(), cam.getHeight(), cam.getWidth()), "dmf_comm_set_camera");
+    if (g.replicated_volume != (const void*)&volume || g.replicated_revision != volume.revision()) {
+        must(dmf_comm_replicate_volume(g.comm, 0), "dmf_comm_replicate_volume");
+        g.replicated_volume = &volume; g.replicated_revision = volume.revision();
+    }
+    return g.comm;
 }
 
 // volume as above + camera intrinsics every call (cheap)

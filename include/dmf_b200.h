@@ -208,12 +208,16 @@ int dmf_or_reduce_dev(dmf_ctx* ctx, uint64_t* d_dst, const uint64_t* d_src, int 
  * Replaces the per-view loops of the reference's drivers (tests/SetCover.cpp:218-240, tests/CameraMotionPlanner.cpp:334-356,
  * tests/CameraPathGen.cpp:158-180: one reverseRayTraceFast / rayTraceAndGetPoints call per candidate view, one CPU thread).
  * Views are dealt round-robin (GPU r marches views r, r+N, ...), the volume is replicated on every GPU, and every GPU ends up
- * with every view's visibility row: the march kernels push finished rows into the peers' buffers over NVLink themselves
- * (peer-mapped stores; no collective call), or -- where the GPUs cannot address each other, or with DMF_COMM_EXCHANGE=nccl --
- * the rows travel through ncclAllGather.  NCCL is loaded with dlopen when a group is formed. */
+ * with every view's visibility row: each GPU's kernels store its finished rows straight into the peers' gathered buffers
+ * through peer-mapped pointers over NVLink (no collective call; rows are disjoint by view), or -- where the GPUs cannot address
+ * each other, or with DMF_COMM_EXCHANGE=nccl -- the rows travel through ncclAllGather.  NCCL is loaded with dlopen when a group is formed. */
 typedef struct dmf_comm dmf_comm;
 #define DMF_UNIQUE_ID_BYTES 128
-enum { DMF_EXCHANGE_NONE = 0, DMF_EXCHANGE_FUSED_P2P = 1, DMF_EXCHANGE_NCCL = 2 };
+/* how the visibility rows reach the peers: peer-mapped 16-byte stores over NVLink issued by one small push kernel right behind
+ * the march (default), the same stores issued from the march kernels' own epilogue (DMF_COMM_EXCHANGE=epilogue: a ticket per
+ * view finds the last block; measured slower, kept as the A/B), or ncclAllGather (DMF_COMM_EXCHANGE=nccl, and the fallback
+ * where the GPUs cannot address each other) */
+enum { DMF_EXCHANGE_NONE = 0, DMF_EXCHANGE_P2P_PUSH = 1, DMF_EXCHANGE_NCCL = 2, DMF_EXCHANGE_P2P_EPILOGUE = 3 };
 enum { DMF_SWEEP_ROWS_OWN = 0, DMF_SWEEP_ROWS_ALL = 1 };
 
 /* ONE process drives n_gpus devices (0 .. n_gpus-1; n_gpus <= 0: all visible, at most 8): creates a context per device,
@@ -251,7 +255,11 @@ int dmf_sweep_reverse(dmf_comm* comm, int fast, const float* poses, int n_views,
 /* The same with each local member's poses already on its device (d_poses[i][j] = global view first_rank + i + j * world) and
  * nothing copied back: enqueues on streams[i] (NULL array / entry = the member's own stream) and returns; the last thing
  * enqueued on each stream is the wait for the peers' rows. */
-int dmf_sweep_forward_dev(dmf_comm* comm, const dmf_forward_params* p, const float* const* d_poses, int n_views, void* const* streams);
+/* d_out (NULL, or one entry per local member, each may be NULL): device buffers for the per-pixel outputs of the member's own
+ * views -- depth_mm / depth_u16 / points / hit_voxel, [views of the member][H][W] -- ; the other fields are ignored (visibility
+ * and found_any live in the gathered rows). */
+int dmf_sweep_forward_dev(dmf_comm* comm, const dmf_forward_params* p, const float* const* d_poses, int n_views,
+                          const dmf_forward_out* const* d_out, void* const* streams);
 int dmf_sweep_reverse_dev(dmf_comm* comm, int fast, const float* const* d_poses, int n_views, void* const* streams);
 /* the gathered rows of the last sweep on local member i: [n_views] rows of row_words uint64 (vis_words of visibility, then one
  * word holding found_any, then padding) */

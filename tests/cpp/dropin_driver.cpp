@@ -135,6 +135,31 @@ int main(int argc, char** argv)
         auto cover = dmf_dropin::setCover(engine, volume, camera_locations, 1, false);
         wr_ids(out, !cover.empty(), cover);
     }
+    // Volumes that come and go at ONE address (a stack local in a loop): the engine's device mirror must follow the volume,
+    // never the address.  Round 0 / 2 hold the scene, round 1 is EMPTY (every routine must then do nothing, like the
+    // reference -- including the ones that push/pull Voxel::view and Voxel::good).
+    for (int round = 0; round < 3; round++) {
+        VoxelVolume local;
+        local.setDimensions(bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5]);
+        local.setVolumeSize(dims[0], dims[1], dims[2]);
+        local.constructVolume();
+        if (round != 1) local.integratePointCloud(cloud, normals);
+        int64_t addr = (int64_t)(intptr_t)&local;
+        wr(out, &addr, 1);
+        bool found; vector<unsigned long long int> ids;
+        tie(found, ids) = engine.rayTraceAndGetPoints(local, camera_locations[0], zdelta, false);  wr_ids(out, found, ids);
+        tie(found, ids) = engine.reverseRayTraceFast(local, camera_locations[0], true);           wr_ids(out, found, ids);
+        engine.rayTrace(local, camera_locations[0], zdelta, true);
+        engine.rayTraceAndClassify(local, camera_locations[0], zdelta, 3, true);
+        engine.rayTraceVolume(local, camera_locations[0]);
+        wr_marks(out, local);
+        auto cover = dmf_dropin::setCover(engine, local, camera_locations, 1, false);
+        wr_ids(out, !cover.empty(), cover);
+    }
+    {
+        int32_t gpus = dmf_dropin::global().gpus();
+        wr(out, &gpus, 1);
+    }
     fclose(out);
     std::cout << "dropin_driver: " << n_occ << " occupied voxels, " << n_poses << " poses" << std::endl;
     return 0;

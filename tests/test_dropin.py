@@ -127,5 +127,28 @@ def test_dropin_matches_oracle(driver, dmf, oracle, tmp_path):
         assert m == mids[i] and np.array_equal(q, moved[i]), i
     f, sel = rd.ids()
     sets = [np.sort(oracle.reverse(ov, K, H, W, p, fast=True)["ids"]) for p in poses]
-    assert np.array_equal(sel.astype(np.int64), oracle.greedy_set_cover(sets))
+    cover_want = oracle.greedy_set_cover(sets)
+    assert np.array_equal(sel.astype(np.int64), cover_want)
+    # three volumes in turn at one address: scene, EMPTY, scene -- the mirror follows the volume, not the address
+    addrs = []
+    for rnd in range(3):
+        addrs.append(int(rd.take(np.int64)[0]))
+        f_fwd, ids_fwd = rd.ids(); f_rev, ids_rev = rd.ids(); view, good = rd.marks(); f_cov, cov = rd.ids()
+        if rnd == 1:
+            assert not f_fwd and not f_rev and len(ids_fwd) == 0 and len(ids_rev) == 0 and len(view) == 0 and len(cov) == 0
+        else:
+            o = oracle.forward(ov, K, H, W, poses[0], oracle.MODE_POINTS, zd, False, want_pixels=False)
+            assert f_fwd == o["found_any"] and np.array_equal(ids_fwd, o["ids"])
+            assert np.array_equal(ids_rev, oracle.reverse(ov, K, H, W, poses[0], fast=True)["ids"])
+            ov.clear_marks()
+            oracle.reverse(ov, K, H, W, poses[0], fast=True, viz=True)
+            oracle.forward(ov, K, H, W, poses[0], oracle.MODE_MARK, zd, True, want_pixels=False)
+            oracle.forward(ov, K, H, W, poses[0], oracle.MODE_CLASSIFY, zd, True, view=3, want_pixels=False)
+            oracle.zbuffer(ov, K, H, W, poses[0])
+            assert np.array_equal(view, ov.marks()[0]) and np.array_equal(good, ov.marks()[1])
+            assert np.array_equal(cov.astype(np.int64), cover_want)
+    assert len(set(addrs)) == 1, "the three stack-local volumes were expected at one address (the case under test)"
+    gpus = int(rd.take(np.int32)[0])
+    import torch
+    assert gpus == torch.cuda.device_count(), "the drop-in's group should span every visible GPU"
     assert rd.o == len(rd.b)

@@ -31,17 +31,17 @@ def _run(cmd, env=None, timeout=600):
 
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("exchange", ["fused", "nccl"])
+@pytest.mark.parametrize("exchange", ["push", "epilogue", "nccl"])
 def test_sweep_single_process_all_gpus(exchange):
     """dmf_comm_init_all: ONE process drives every GPU through the C ABI (the reference drivers' shape): gathered rows, set cover,
     fused observed grids and fused marks equal the single-GPU results; fused peer stores and the NCCL path"""
     r = _run([sys.executable, os.path.join(ROOT, "tools", "comm_check.py"), "all", str(min(_gpus(), 8))], {"DMF_COMM_EXCHANGE": exchange})
     assert r.returncode == 0 and "OK single process" in r.stdout, (r.stdout + r.stderr)[-3000:]
-    assert ("fused" in r.stdout) == (exchange == "fused"), r.stdout
+    assert {"push": "push kernel", "epilogue": "epilogue", "nccl": "ncclAllGather"}[exchange] in r.stdout, r.stdout
 
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("exchange", ["fused", "nccl"])
+@pytest.mark.parametrize("exchange", ["push", "epilogue", "nccl"])
 def test_sweep_one_process_per_gpu(exchange):
     """dmf_comm_init_rank under torchrun: arenas mapped with CUDA IPC, rows pushed by the march kernels (or ncclAllGather)"""
     n = min(_gpus(), 8)
