@@ -55,5 +55,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_checked(force: bool = False) -> str:
+    """libdmf_b200_checked.so: the same sources with -DDMF_CHECKED (every computed grid index bounds-checked and counted,
+    dmf_device.cuh); tests/test_fuzz_gpu.py runs the fuzz against it.  compute-sanitizer is not available on the GPU pool."""
+    global OUT
+    out = os.path.join(HERE, "libdmf_b200_checked.so")
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in DEPS):
+        return out
+    saved, saved_env = OUT, os.environ.get("DMF_NVCC_EXTRA")
+    OUT = out
+    os.environ["DMF_NVCC_EXTRA"] = ((saved_env or "") + " -DDMF_CHECKED").strip()
+    try:
+        return build(force=True)
+    finally:
+        OUT = saved
+        if saved_env is None:
+            os.environ.pop("DMF_NVCC_EXTRA", None)
+        else:
+            os.environ["DMF_NVCC_EXTRA"] = saved_env
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

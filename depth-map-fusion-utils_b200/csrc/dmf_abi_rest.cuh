@@ -110,30 +110,40 @@ int dmf_reverse(dmf_ctx* c, int fast, int viz, const float* poses, int n_views, 
             d_emit = c->d_misc[0].as<u64>(); d_emit_count = c->d_misc[1].as<unsigned>();
         }
         DMF_TRY(enqueue_reverse(c, fast, viz, c->d_poses[0].as<float>(), nv, d_vis, d_unocc, d_found, d_emit, d_emit_count, emit_cap, st));
+        bool found_delivered = false;
         if (want_ids && fast) {
-            // emission order of reverseRayTraceFast == occupied order: expand each view's bitset in ascending order
-            std::vector<int> n_ids(nv, 0);
-            std::vector<long long> offs(nv + 1, 0);
+            // emission order of reverseRayTraceFast == occupied order: expand each view's bitset in ascending order.  Counts ->
+            // offsets -> gather stay on the device; one copy of (offsets, found flags, first ids) into pinned staging, one sync.
+            const long long cap_dev = (long long)nv * (long long)std::max<size_t>(c->n_occ, 1);
+            const size_t off_bytes = (size_t)(nv + 1) * 8, found_bytes = ((size_t)nv * 4 + 7) / 8 * 8;
+            const size_t first_ids = (size_t)std::min<long long>(cap_dev, 128 * 1024);
+            DMF_TRY(c->stage.reserve(off_bytes + found_bytes + first_ids * 8));
+            DMF_TRY(c->d_offsets.reserve((size_t)(nv + 1) * 8)); DMF_TRY(c->d_n_ids.reserve((size_t)nv * 4));
+            char* hs = (char*)c->stage.p;
             if (c->n_occ) {
-                DMF_TRY(c->d_out_occ.reserve((size_t)nv * c->n_occ * 4)); DMF_TRY(c->d_n_ids.reserve((size_t)nv * 4)); DMF_TRY(c->d_offsets.reserve((size_t)(nv + 1) * 8));
+                DMF_TRY(c->d_out_occ.reserve((size_t)nv * c->n_occ * 4)); DMF_TRY(c->d_ids.reserve((size_t)cap_dev * 8));
                 k_bits_to_list<<<nv, 256, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_out_occ.as<int>(), c->d_n_ids.as<int>(), (int)c->n_occ);
-                c->launches++;
+                k_ids_offsets<<<1, 1024, 0, st>>>(c->d_n_ids.as<int>(), nv, c->d_offsets.as<long long>());
+                k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->d_centroid_hash.as<u64>(), c->d_ids.as<u64>(), (int)c->n_occ, cap_dev);
+                c->launches += 3;
                 DMF_CUDA(cudaGetLastError());
-                DMF_CUDA(cudaMemcpyAsync(n_ids.data(), c->d_n_ids.p, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
-                DMF_CUDA(cudaStreamSynchronize(st));
+                DMF_CUDA(cudaMemcpyAsync(hs, c->d_offsets.p, off_bytes, cudaMemcpyDeviceToHost, st));
+                DMF_CUDA(cudaMemcpyAsync(hs + off_bytes + found_bytes, c->d_ids.p, first_ids * 8, cudaMemcpyDeviceToHost, st));
             }
-            for (int i = 0; i < nv; i++) offs[i + 1] = offs[i] + n_ids[i];
-            if ((size_t)(ids_total + offs[nv]) > out->ids_capacity || (!out->ids && offs[nv] > 0)) return fail("ids_capacity %zu too small (need >= %lld)", out->ids_capacity, (long long)(ids_total + offs[nv]));
-            if (offs[nv] > 0) {
-                DMF_TRY(c->d_ids.reserve((size_t)offs[nv] * 8));
-                DMF_CUDA(cudaMemcpyAsync(c->d_offsets.p, offs.data(), (size_t)(nv + 1) * 8, cudaMemcpyHostToDevice, st));
-                k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->d_centroid_hash.as<u64>(), c->d_ids.as<u64>(), (int)c->n_occ);
-                c->launches++;
-                DMF_CUDA(cudaGetLastError());
-                DMF_CUDA(cudaMemcpyAsync(out->ids + ids_total, c->d_ids.p, (size_t)offs[nv] * 8, cudaMemcpyDeviceToHost, st));
+            DMF_CUDA(cudaMemcpyAsync(hs + off_bytes, d_found, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+            DMF_CUDA(cudaStreamSynchronize(st));
+            if (!c->n_occ) std::memset(hs, 0, off_bytes);
+            const long long* offs = (const long long*)hs;
+            const long long total = offs[nv];
+            if ((size_t)(ids_total + total) > out->ids_capacity || (!out->ids && total > 0)) return fail("ids_capacity %zu too small (need >= %lld)", out->ids_capacity, (long long)(ids_total + total));
+            if (total > 0) {
+                const size_t head = (size_t)std::min<long long>(total, (long long)first_ids);
+                std::memcpy(out->ids + ids_total, hs + off_bytes + found_bytes, head * 8);
+                if ((size_t)total > head) DMF_CUDA(cudaMemcpy(out->ids + ids_total + head, c->d_ids.as<u64>() + head, ((size_t)total - head) * 8, cudaMemcpyDeviceToHost));
             }
             for (int i = 0; i < nv; i++) out->ids_offsets[v0 + i + 1] = ids_total + offs[i + 1];
-            ids_total += offs[nv];
+            if (out->found_any) { std::memcpy(out->found_any + v0, hs + off_bytes, (size_t)nv * 4); found_delivered = true; }
+            ids_total += total;
         }
         if (want_ids && !fast) {
             // whole-grid scan: the kernel appended (scan index, centroid hash) pairs in arbitrary order; the reference's
@@ -156,12 +166,12 @@ int dmf_reverse(dmf_ctx* c, int fast, int viz, const float* poses, int n_views, 
         }
         if (out->visibility && vw) DMF_CUDA(cudaMemcpyAsync(out->visibility + v0 * vw, d_vis, nv * vw * 8, cudaMemcpyDeviceToHost, st));
         if (out->unoccluded && vw) DMF_CUDA(cudaMemcpyAsync(out->unoccluded + v0 * vw, d_unocc, nv * vw * 8, cudaMemcpyDeviceToHost, st));
-        if (out->found_any) DMF_CUDA(cudaMemcpyAsync(out->found_any + v0, d_found, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
-        DMF_CUDA(cudaStreamSynchronize(st));
+        if (out->found_any && !found_delivered) DMF_CUDA(cudaMemcpyAsync(out->found_any + v0, d_found, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+        // (the fast id path has already synchronised; another sync is needed only if something was enqueued after it)
+        if ((out->visibility && vw) || (out->unoccluded && vw) || (out->found_any && !found_delivered) || !(want_ids && fast)) DMF_CUDA(cudaStreamSynchronize(st));
     }
     DMF_CUDA(cudaEventRecord(c->ev_k1, st));
     c->timed = true;
-    DMF_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 

@@ -164,9 +164,9 @@ int build_volume_device(dmf_ctx* c, size_t n_occ, size_t n_normals) {
     DMF_TRY(c->d_err.reserve(16));
     v.bits = c->d_bricks.as<unsigned>(); v.prefix = c->d_prefix.as<unsigned>(); v.rank2occ = c->d_rank2occ.as<unsigned>(); v.macro = c->d_macro.as<unsigned>();
     v.noff = c->d_noff.as<unsigned>(); v.normals = c->d_normals.as<float>(); v.occ_ids = c->d_occ_ids.as<u64>();
-    v.bytes = nullptr; v.n_occ = (int)n_occ;
+    v.bytes = nullptr; v.n_occ = (int)n_occ; v.n_cells = (unsigned)nbits;
     c->n_occ = n_occ; c->n_normals = n_normals;
-    c->bytes_built = false;
+    c->bytes_built = false; c->auto_uses = 0;
     c->n_grid_words = nwords; c->observed_ready = false;     // a new volume starts unobserved
 
     DMF_CUDA(cudaEventRecord(c->ev_p0, st));
@@ -357,13 +357,18 @@ void launch_forward_fmt(const FwdArgs& a, int fmt, bool skip, bool two_probe, di
     }
 }
 
-struct FwdPlan { int z0, cstride, rstride; };
+struct FwdPlan { int z0, cstride, rstride, grid_format; };
 int plan_forward(dmf_ctx* c, const dmf_forward_params* p, FwdPlan& pl) {
     if (!c->cam_set) return fail("dmf_set_camera has not been called");
     if (!c->vol_set) return fail("no volume uploaded");
     if (p->mode < 0 || p->mode > 4) return fail("bad mode %d", p->mode);
     if (p->zdelta < 1) return fail("zdelta must be >= 1 (the reference loops forever on zdelta <= 0)");
-    if (p->grid_format != DMF_GRID_BIT && p->grid_format != DMF_GRID_BYTE) return fail("bad grid_format %d", p->grid_format);
+    if (p->grid_format != DMF_GRID_BIT && p->grid_format != DMF_GRID_BYTE && p->grid_format != DMF_GRID_AUTO) return fail("bad grid_format %d", p->grid_format);
+    // DMF_GRID_AUTO: the bit grid is ready as soon as the volume is uploaded; the distance bytes cost a one-off transform (2.6 ms at
+    // 512^3, 16 ms at 1024^3) and make every later march ~4x faster.  Use them once they exist (the reverse march builds them) or
+    // from the second forward call on one volume.
+    pl.grid_format = p->grid_format;
+    if (p->grid_format == DMF_GRID_AUTO) pl.grid_format = (c->bytes_built || ++c->auto_uses >= 2) ? DMF_GRID_BYTE : DMF_GRID_BIT;
     if ((p->flags & DMF_FWD_CARVE) && p->mode == DMF_MODE_MINIMUM)
         return fail("DMF_FWD_CARVE is not defined for MINIMUM mode (rayTraceAndGetMinimum returns mid-plane: the samples it visits depend on the pixel order)");
     pl.z0 = p->mode == DMF_MODE_MINIMUM ? 5 : 10;                                        // :239 vs :280,:327,:396,:461
@@ -385,7 +390,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     if (n_views <= 0) return 0;
     if (n_views > 65535) return fail("at most 65535 views per launch (got %d)", n_views);
     DMF_TRY(ensure_tables(c, pl.z0, p->zdelta, pl.cstride, pl.rstride, st));
-    if (p->grid_format == DMF_GRID_BYTE) DMF_TRY(ensure_bytes(c, st));
+    if (pl.grid_format == DMF_GRID_BYTE) DMF_TRY(ensure_bytes(c, st));
     const bool carve = (p->flags & DMF_FWD_CARVE) != 0;
     if (carve) DMF_TRY(ensure_observed(c, st));
     const size_t HW = (size_t)c->H * c->W;
@@ -425,7 +430,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     DMF_TRY(c->d_kstart.reserve((size_t)n_views * 8));
     a.kstart = c->d_kstart.as<int>(); a.veps = c->d_kstart.as<float>() + n_views;
     const bool skip = !(p->flags & DMF_FWD_NO_SKIP);
-    const bool byte_skip = skip && p->grid_format == DMF_GRID_BYTE;
+    const bool byte_skip = skip && pl.grid_format == DMF_GRID_BYTE;
     const bool two_probe = (p->flags & DMF_FWD_TWO_PROBE) != 0;
     if (sub_views <= 0 || sub_views > n_views) sub_views = n_views;
     DMF_CUDA(cudaEventRecord(c->ev_h0, st));
@@ -439,11 +444,11 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
         a.view0 = v0;
         dim3 grid((c->Wc + FWD_TILE_W - 1) / FWD_TILE_W, (c->Hc + FWD_TILE_H - 1) / FWD_TILE_H, nv);
         switch (p->mode) {
-            case 0: launch_forward_fmt<0>(a, p->grid_format, skip, two_probe, grid, ls); break;
-            case 1: launch_forward_fmt<1>(a, p->grid_format, skip, two_probe, grid, ls); break;
-            case 2: launch_forward_fmt<2>(a, p->grid_format, skip, two_probe, grid, ls); break;
-            case 3: launch_forward_fmt<3>(a, p->grid_format, skip, two_probe, grid, ls); break;
-            default: launch_forward_fmt<4>(a, p->grid_format, skip, two_probe, grid, ls); break;
+            case 0: launch_forward_fmt<0>(a, pl.grid_format, skip, two_probe, grid, ls); break;
+            case 1: launch_forward_fmt<1>(a, pl.grid_format, skip, two_probe, grid, ls); break;
+            case 2: launch_forward_fmt<2>(a, pl.grid_format, skip, two_probe, grid, ls); break;
+            case 3: launch_forward_fmt<3>(a, pl.grid_format, skip, two_probe, grid, ls); break;
+            default: launch_forward_fmt<4>(a, pl.grid_format, skip, two_probe, grid, ls); break;
         }
         c->launches++;
         if (after_sub) DMF_TRY((*after_sub)(v0, nv, ls));
@@ -470,7 +475,13 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
 // ======================================================= C ABI ==============================================
 extern "C" {
 
-int dmf_version(void) { return 100; }
+int dmf_version(void) {                                  // 2xx: round 2 ABI; odd: the checked build (-DDMF_CHECKED)
+#ifdef DMF_CHECKED
+    return 201;
+#else
+    return 200;
+#endif
+}
 
 int dmf_host_angle_test(float out[3]) {
     if (!out) return fail("null argument");
@@ -536,6 +547,7 @@ void dmf_destroy(dmf_ctx* c) {
                       &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters,
                       &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err};
     for (auto* b : bufs) b->release();
+    c->stage.release();
     for (int i = 0; i < 2; i++) for (int j = 0; j < 8; j++) c->d_out[i][j].release();
     for (int i = 0; i < 2; i++) { if (c->ev_compute[i]) cudaEventDestroy(c->ev_compute[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     for (cudaEvent_t e : {c->ev_p0, c->ev_p1, c->ev_b0, c->ev_b1, c->ev_last}) if (e) cudaEventDestroy(e);
@@ -784,6 +796,7 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
     DMF_CUDA(cudaEventRecord(c->ev_k0, st));
     int64_t ids_total = 0;
     int n_chunks = 0;
+    bool any_copy = false;
     for (int v0 = 0; v0 < n_views; v0 += chunk, n_chunks++) {
         const int nv = std::min(chunk, n_views - v0);
         const int b = n_chunks & 1;
@@ -806,33 +819,45 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
         }
         DMF_TRY(enqueue_forward(c, p, pl, c->d_poses[b].as<float>(), nv, p->view_id0 + v0, d, fk, rk, ro, st));
         if (want_ids) {
+            // The id lists leave the device without a host round trip in the middle: counts -> offsets -> gather all on the device,
+            // then ONE copy of (offsets, found flags, the first ids) into pinned staging and one synchronisation.  Only a view list
+            // longer than the staging area costs a second copy.  (Round 1: D2H of the counts, sync, H2D of the offsets, gather, D2H,
+            // sync -- 0.36 ms per single-view call, most of it waiting.)
             DMF_TRY(c->d_tmp_a.reserve(nv * R * 4)); DMF_TRY(c->d_tmp_b.reserve(nv * R * 4)); DMF_TRY(c->d_out_occ.reserve(nv * R * 4));
             DMF_TRY(c->d_n_ids.reserve((size_t)nv * 4)); DMF_TRY(c->d_offsets.reserve((size_t)(nv + 1) * 8));
             const int nb = (int)((R + WIN_BLOCK - 1) / WIN_BLOCK);
             DMF_TRY(c->d_misc[0].reserve((size_t)nv * nb * 4)); DMF_TRY(c->d_misc[1].reserve((size_t)nv * nb * 4));
+            const long long cap_dev = (long long)nv * (long long)std::min<size_t>(R, std::max<size_t>(c->n_occ, 1));     // a view cannot return more ids than rays or voxels
+            DMF_TRY(c->d_ids.reserve((size_t)std::max<long long>(cap_dev, 1) * 8));
             k_win_count<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[0].as<unsigned>(), (int)R, (int)c->n_occ, nb);
             k_win_offsets<<<nv, 1024, 0, st>>>(c->d_misc[0].as<unsigned>(), c->d_misc[1].as<unsigned>(), c->d_n_ids.as<int>(), nb);
             k_win_compact<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[1].as<unsigned>(), c->d_tmp_a.as<unsigned>(), (int)R, (int)c->n_occ, nb);
             k_order_ids<<<nv, ORD_THREADS, 32 * ORD_THREADS * 4, st>>>(ro, c->d_tmp_a.as<unsigned>(), c->d_tmp_b.as<unsigned>(), c->d_out_occ.as<int>(), c->d_n_ids.as<int>(), (int)R);
-            c->launches += 4;
+            k_ids_offsets<<<1, 1024, 0, st>>>(c->d_n_ids.as<int>(), nv, c->d_offsets.as<long long>());
+            k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->vol.occ_ids, c->d_ids.as<u64>(), (int)R, cap_dev);
+            c->launches += 6;
             DMF_CUDA(cudaGetLastError());
-            std::vector<int> n_ids(nv);
-            DMF_CUDA(cudaMemcpyAsync(n_ids.data(), c->d_n_ids.p, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+            // staging layout: [offsets (nv+1) x 8][found_any nv x 4, padded to 8][min_depth: unused here][first ids]
+            const size_t off_bytes = (size_t)(nv + 1) * 8, found_bytes = ((size_t)nv * 4 + 7) / 8 * 8;
+            const size_t first_ids = (size_t)std::min<long long>(cap_dev, 128 * 1024);
+            DMF_TRY(c->stage.reserve(off_bytes + found_bytes + first_ids * 8));
+            char* hs = (char*)c->stage.p;
+            DMF_CUDA(cudaMemcpyAsync(hs, c->d_offsets.p, off_bytes, cudaMemcpyDeviceToHost, st));
+            DMF_CUDA(cudaMemcpyAsync(hs + off_bytes, d.found_any, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+            if (first_ids) DMF_CUDA(cudaMemcpyAsync(hs + off_bytes + found_bytes, c->d_ids.p, first_ids * 8, cudaMemcpyDeviceToHost, st));
             DMF_CUDA(cudaStreamSynchronize(st));
-            std::vector<long long> offs(nv + 1, 0);
-            for (int i = 0; i < nv; i++) offs[i + 1] = offs[i] + n_ids[i];
-            if ((size_t)(ids_total + offs[nv]) > out->ids_capacity || (!out->ids && offs[nv] > 0)) return fail("ids_capacity %zu too small (need >= %lld)", out->ids_capacity, (long long)(ids_total + offs[nv]));
-            if (offs[nv] > 0) {
-                DMF_TRY(c->d_ids.reserve((size_t)offs[nv] * 8));
-                DMF_CUDA(cudaMemcpyAsync(c->d_offsets.p, offs.data(), (size_t)(nv + 1) * 8, cudaMemcpyHostToDevice, st));
-                k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->vol.occ_ids, c->d_ids.as<u64>(), (int)R);
-                c->launches++;
-                DMF_CUDA(cudaGetLastError());
-                DMF_CUDA(cudaMemcpyAsync(out->ids + ids_total, c->d_ids.p, (size_t)offs[nv] * 8, cudaMemcpyDeviceToHost, st));
-                DMF_CUDA(cudaStreamSynchronize(st));
+            const long long* offs = (const long long*)hs;
+            const long long total = offs[nv];
+            if (total > cap_dev) return fail("internal: %lld ids exceed the device bound %lld", total, cap_dev);
+            if ((size_t)(ids_total + total) > out->ids_capacity || (!out->ids && total > 0)) return fail("ids_capacity %zu too small (need >= %lld)", out->ids_capacity, (long long)(ids_total + total));
+            if (total > 0) {
+                const size_t head = (size_t)std::min<long long>(total, (long long)first_ids);
+                std::memcpy(out->ids + ids_total, hs + off_bytes + found_bytes, head * 8);
+                if ((size_t)total > head) DMF_CUDA(cudaMemcpy(out->ids + ids_total + head, c->d_ids.as<u64>() + head, ((size_t)total - head) * 8, cudaMemcpyDeviceToHost));
             }
             for (int i = 0; i < nv; i++) out->ids_offsets[v0 + i + 1] = ids_total + offs[i + 1];
-            ids_total += offs[nv];
+            if (out->found_any) std::memcpy(out->found_any + v0, hs + off_bytes, (size_t)nv * 4);
+            ids_total += total;
         }
         DMF_CUDA(cudaEventRecord(c->ev_compute[b], st));
         DMF_CUDA(cudaStreamWaitEvent(cs, c->ev_compute[b], 0));
@@ -841,14 +866,15 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
         if (out->points) DMF_CUDA(cudaMemcpyAsync(out->points + v0 * HW * 3, d.points, nv * HW * 12, cudaMemcpyDeviceToHost, cs));
         if (out->hit_voxel) DMF_CUDA(cudaMemcpyAsync(out->hit_voxel + v0 * HW, d.hit_voxel, nv * HW * 8, cudaMemcpyDeviceToHost, cs));
         if (out->visibility && vw) DMF_CUDA(cudaMemcpyAsync(out->visibility + v0 * vw, d.visibility, nv * vw * 8, cudaMemcpyDeviceToHost, cs));
-        if (out->found_any) DMF_CUDA(cudaMemcpyAsync(out->found_any + v0, d.found_any, (size_t)nv * 4, cudaMemcpyDeviceToHost, cs));
+        if (out->found_any && !want_ids) DMF_CUDA(cudaMemcpyAsync(out->found_any + v0, d.found_any, (size_t)nv * 4, cudaMemcpyDeviceToHost, cs));
         if (out->min_depth && d.min_depth) DMF_CUDA(cudaMemcpyAsync(out->min_depth + v0, d.min_depth, (size_t)nv * 4, cudaMemcpyDeviceToHost, cs));
+        any_copy = any_copy || out->depth_mm || out->depth_u16 || out->points || out->hit_voxel || (out->visibility && vw) || (out->found_any && !want_ids) || (out->min_depth && d.min_depth);
         DMF_CUDA(cudaEventRecord(c->ev_copied[b], cs));
     }
     DMF_CUDA(cudaEventRecord(c->ev_k1, st));
     c->timed = true;
-    DMF_CUDA(cudaStreamSynchronize(st));
-    DMF_CUDA(cudaStreamSynchronize(cs));
+    if (!want_ids || n_chunks > 1) DMF_CUDA(cudaStreamSynchronize(st));      // (the id path has just synchronised its only chunk)
+    if (any_copy || n_chunks > 2) DMF_CUDA(cudaStreamSynchronize(cs));
     return 0;
 }
 

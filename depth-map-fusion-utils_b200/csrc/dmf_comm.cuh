@@ -427,7 +427,7 @@ int sweep_run(dmf_comm* g, const SweepSpec& spec, const float* host_poses, const
         FwdPlan pl; DMF_TRY(plan_forward(mm.ctx, spec.fwd, pl));
         DMF_CUDA(cudaSetDevice(mm.ctx->device));
         DMF_TRY(ensure_tables(mm.ctx, pl.z0, spec.fwd->zdelta, pl.cstride, pl.rstride, mm.ctx->stream));
-        if (spec.fwd->grid_format == DMF_GRID_BYTE) DMF_TRY(ensure_bytes(mm.ctx, mm.ctx->stream));
+        if (pl.grid_format == DMF_GRID_BYTE) DMF_TRY(ensure_bytes(mm.ctx, mm.ctx->stream));
         if (spec.fwd->flags & DMF_FWD_CARVE) DMF_TRY(ensure_observed(mm.ctx, mm.ctx->stream));
         DMF_TRY(mm.ctx->d_kstart.reserve((size_t)(my_view_count(n_views, 0, g->world) + 1) * 8));
     }

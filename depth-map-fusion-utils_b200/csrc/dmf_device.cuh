@@ -20,6 +20,18 @@ __device__ __forceinline__ u64* counter_slot(u64* base) {
     return base + (b & (DMF_COUNTER_SLOTS - 1u)) * DMF_COUNTER_STRIDE;
 }
 
+// ---- checked build (-DDMF_CHECKED; libdmf_b200_checked.so, tests/test_fuzz_gpu.py) ------------------------------------------
+// compute-sanitizer is closed on the GPU pool this is developed on, so the kernels carry their own bounds checks: in the checked
+// build every COMPUTED index into a grid or table is compared against its limit before use; a violation is counted in counter
+// slot DMF_CNT_BOUNDS (and the index replaced by 0, so the run survives to report it).  The production build compiles the
+// checks out: its marches rely on the proofs in DESIGN.md (padded index space, slab guards), which the fuzz test holds the
+// checked build against.
+#ifdef DMF_CHECKED
+#define DMF_CHECK_IDX(idx, limit, counters) do { if ((unsigned long long)(idx) >= (unsigned long long)(limit)) { atomicAdd(counter_slot(counters) + 10, 1ull); (idx) = 0; } } while (0)
+#else
+#define DMF_CHECK_IDX(idx, limit, counters) do { } while (0)
+#endif
+
 // Thousands of rays of a view raise the same per-view flag.  A plain store per ray funnels ~10^4 same-address writes per
 // view into one L2 slice, which serialises them (measured on B200: 1.07 of 2.9 ms per 128 views, and the SMs of the die
 // that does not own the slice starve).  Read first: the line sits in L1, the flag only ever goes 0 -> 1, and a stale 0
@@ -116,6 +128,7 @@ struct VolDev {
     const float* __restrict__ normals;
     const u64* __restrict__ occ_ids;
     int n_occ;
+    unsigned n_cells; // pdim_x * pdim_y * pdim_z: entries of the padded grids
     int dim[3];      // xdim_, ydim_, zdim_
     int pdim[3];     // dim + 1
     int mdim[3];     // macro cells per axis = ceil(pdim / 8)

@@ -87,7 +87,10 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
     const int z_depth = a.z0 + hit_k * a.zdelta;
     if (active) {
         // 32-bit pixel index: the host entry points keep n_views * H * W below 2^32 per launch
-        const unsigned pix = ((unsigned)view * (unsigned)a.H + (unsigned)(ri * a.rstride)) * (unsigned)a.W + (unsigned)(ci * a.cstride);
+        unsigned pix = ((unsigned)view * (unsigned)a.H + (unsigned)(ri * a.rstride)) * (unsigned)a.W + (unsigned)(ci * a.cstride);
+#ifdef DMF_CHECKED
+        if (ri * a.rstride >= a.H || ci * a.cstride >= a.W) { atomicAdd(counter_slot(a.counters) + 10, 1ull); pix = 0; }
+#endif
         if (a.depth) a.depth[pix] = hit ? z_depth : -1;
         if (a.depth16) a.depth16[pix] = hit ? (unsigned short)z_depth : (unsigned short)0xFFFFu;
         if (a.hit_voxel) a.hit_voxel[pix] = hit ? voxel_id(hx, hy, hz) : ~0ull;
@@ -107,6 +110,7 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
         int occ = -1;
         if (hit) {
             occ = occupied_ordinal(v, hx, hy, hz);
+            DMF_CHECK_IDX(occ, v.n_occ, a.counters);
             if (a.found_any) raise_flag(a.found_any + view);
             bool good = false;
             if (MODE == 1 || MODE == 2) {
@@ -258,7 +262,8 @@ __global__ void __launch_bounds__(FWD_THREADS) k_forward(const FwdArgs a) {
                     iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
                 }
                 // voxels_[xid][yid][zid] != nullptr: indices are in [0,dim] here, the padded grid covers index == dim
-                const unsigned idx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+                unsigned idx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+                DMF_CHECK_IDX(idx, v.n_cells, a.counters);
                 if (CARVE) {
                     // read first: after the first few views of a sweep nearly every bit is already set, the word sits in
                     // L1/L2, and a stale 0 only costs a redundant (idempotent) atomicOr
@@ -700,8 +705,9 @@ __device__ __forceinline__ void carve_exact_sample(const FwdArgs& a, unsigned sp
     if (!(px > v.lo[0] && px < v.hi[0] && py > v.lo[1] && py < v.hi[1] && pz > v.lo[2] && pz < v.hi[2])) return;   // validPoints failed
     int ix, iy, iz;
     unsigned dummy0 = 0, dummy1 = 0;
-    const unsigned idx = probe_index<EXACT>(v, px, py, pz, v.inv32[0], v.inv32[1], v.inv32[2], v.c32[0], v.c32[1], v.c32[2],
-                                            v.err32[0], v.err32[1], v.err32[2], (unsigned)v.pdim[1], (unsigned)v.pdim[2], ix, iy, iz, dummy0, dummy1);
+    unsigned idx = probe_index<EXACT>(v, px, py, pz, v.inv32[0], v.inv32[1], v.inv32[2], v.c32[0], v.c32[1], v.c32[2],
+                                      v.err32[0], v.err32[1], v.err32[2], (unsigned)v.pdim[1], (unsigned)v.pdim[2], ix, iy, iz, dummy0, dummy1);
+    DMF_CHECK_IDX(idx, v.n_cells, a.counters);
     observe_voxel(a.observed, idx);
 }
 
@@ -895,6 +901,7 @@ __device__ __forceinline__ void carve_on_line_sign(const FwdArgs& a, unsigned sp
 #if DMF_CARVE_CLAMP
                     idx[u] = min(idx[u], last); idx[u + 1] = min(idx[u + 1], last);      // a seat belt, never active: the samples are inside
 #endif
+                    DMF_CHECK_IDX(idx[u], v.n_cells, a.counters); DMF_CHECK_IDX(idx[u + 1], v.n_cells, a.counters);
                 }
                 unsafe |= fail << j;
 #pragma unroll
@@ -1038,7 +1045,13 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
                 const unsigned bx = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb0, qa0), kM));
                 const unsigned by = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb1, qa1), kM));
                 const unsigned bz = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb2, qa2), kM));
+#ifdef DMF_CHECKED
+                unsigned lidx = bx * pnyz + (by * pnz + (bz - bias));
+                DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
+                const unsigned d = __ldg(gbytes + lidx);
+#else
                 const unsigned d = __ldg(gbytes + min(bx * pnyz + (by * pnz + (bz - bias)), last));   // (the clamp is a seat belt, never active)
+#endif
 #ifdef DMF_LINE_STATS
                 n_f64++;                                   // diagnostic build: F64_PATH counts line probes, EXACT_DIV exact ones
 #endif
@@ -1083,8 +1096,9 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
         if (!(px > v.lo[0] && px < v.hi[0] && py > v.lo[1] && py < v.hi[1] && pz > v.lo[2] && pz < v.hi[2])) { k++; continue; }   // validPoints failed
         n_inb++;
         int ix, iy, iz;
-        const unsigned idx = probe_index<EXACT>(v, px, py, pz, v.inv32[0], v.inv32[1], v.inv32[2], v.c32[0], v.c32[1], v.c32[2],
-                                                v.err32[0], v.err32[1], v.err32[2], pny, pnz, ix, iy, iz, n_f64, n_exact);
+        unsigned idx = probe_index<EXACT>(v, px, py, pz, v.inv32[0], v.inv32[1], v.inv32[2], v.c32[0], v.c32[1], v.c32[2],
+                                          v.err32[0], v.err32[1], v.err32[2], pny, pnz, ix, iy, iz, n_f64, n_exact);
+        DMF_CHECK_IDX(idx, v.n_cells, a.counters);
         const unsigned de = __ldg(gbytes + idx);
 #ifdef DMF_LINE_STATS
         if (de != 77u) t_exact += clock64() - te0;        // (depends on the load: the wait is inside the bracket)
@@ -1282,10 +1296,36 @@ __global__ void __launch_bounds__(ORD_THREADS) k_order_ids(const int* ray_occ, u
     for (int i = threadIdx.x; i < nw; i += ORD_THREADS) out_occ[(size_t)view * R + i] = ro[ta[i] & 0x1FFFFFu];
 }
 
-// compact per-view winner lists into one contiguous uint64 id array at host-computed offsets
-__global__ void k_gather_ids(const int* out_occ, const long long* offsets, const u64* occ_ids, u64* ids, int R) {
+// offsets[v] = sum of n[0..v) for the (few) views of a chunk, offsets[n_views] = total: one block, so that the id lists can be
+// laid out and gathered without a round trip to the host
+__global__ void __launch_bounds__(1024) k_ids_offsets(const int* __restrict__ n, int n_views, long long* __restrict__ offsets) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) { s_carry = 0; offsets[0] = 0; }
+    __syncthreads();
+    for (int base = 0; base < n_views; base += 1024) {
+        const int i = base + threadIdx.x;
+        const long long val = i < n_views ? (long long)n[i] : 0;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        long long x = val;
+        for (int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) { long long w = s_warp[lane]; for (int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; } s_warp[lane] = w; }
+        __syncthreads();
+        const long long incl = s_carry + (warp ? s_warp[warp - 1] : 0) + x;
+        if (i < n_views) offsets[i + 1] = incl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+}
+
+// compact per-view winner lists into one contiguous uint64 id array at the offsets above (entries beyond `cap` are dropped:
+// the host sees the total in offsets[n_views] and reports the overflow)
+__global__ void k_gather_ids(const int* out_occ, const long long* offsets, const u64* occ_ids, u64* ids, int R, long long cap) {
     const int view = blockIdx.y;
     const long long b = offsets[view], n = offsets[view + 1] - b;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        ids[b + i] = occ_ids[out_occ[(size_t)view * R + i]];
+        if (b + i < cap) ids[b + i] = occ_ids[out_occ[(size_t)view * R + i]];
 }

@@ -41,6 +41,21 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+// grow-only pinned host staging (small results leave the device through it: one asynchronous copy, one synchronisation)
+struct HostStage {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 // Host restatement of the data-model half of VoxelVolume (reference include/Volume.hpp:89-128,135-170,199-233);
 // used only to turn a point cloud into (occupied ids, normals CSR) -- the march itself never runs on the host.
 struct HostVolume {
@@ -141,6 +156,7 @@ struct dmf_ctx {
     dmf::DevBuf d_scan, d_dt_tmp, d_macro_dist[2], d_err;   // scan scratch, distance-transform ping-pong, macro-cell distances, error words
     dmf::DevBuf d_bricks /* bit grid words */, d_macro, d_prefix, d_rank2occ, d_bytes, d_noff, d_normals, d_occ_ids, d_centroid_hash;
     bool bytes_built = false;
+    int auto_uses = 0;                    // forward calls with DMF_GRID_AUTO since the volume was uploaded
     int reverse_format = DMF_GRID_BYTE;   // grid the reverse march probes (dmf_set_reverse_format)
     dmf::DevBuf d_view_mark, d_good_bits, d_first_view;
     // carve mode (DMF_FWD_CARVE): observed-voxel bit grid, same layout and word count as the occupancy bit grid; zeroed on first use
@@ -154,6 +170,7 @@ struct dmf_ctx {
     dmf::DevBuf d_poses[2], d_inv_poses, d_out[2][8], d_first_key, d_ray_key, d_ray_occ, d_tmp_a, d_tmp_b, d_out_occ, d_n_ids, d_offsets, d_ids;
     dmf::DevBuf d_misc[4];
     dmf::DevBuf d_counters;
+    dmf::HostStage stage;                             // pinned staging of the id-list calls
     AngleTest angle{};
     uint64_t launches = 0;
 };

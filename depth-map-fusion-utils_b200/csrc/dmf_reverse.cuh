@@ -171,7 +171,9 @@ __device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float
                 const float q0 = fmaf(s, qv0, qc0), q1 = fmaf(s, qv1, qc1), q2 = fmaf(s, qv2, qc2);
                 const float m0 = __fadd_rd(q0, kM), m1 = __fadd_rd(q1, kM), m2 = __fadd_rd(q2, kM);
                 const int ix = __float_as_int(m0) - 0x4B400000, iy = __float_as_int(m1) - 0x4B400000, iz = __float_as_int(m2) - 0x4B400000;
-                const unsigned d = __ldg(v.bytes + (((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz));
+                unsigned lidx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+                DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
+                const unsigned d = __ldg(v.bytes + lidx);
                 float adv = 1.0f;
                 if (d >= 2u) {
                     const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;

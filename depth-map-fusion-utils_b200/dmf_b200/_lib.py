@@ -106,7 +106,7 @@ SYMBOLS = {
     "dmf_synchronize": (C.c_int, [vp]),
 }
 
-COUNTER_NAMES = ("samples", "inbounds", "hits", "exact_div", "oob", "acos_ties", "launches", "runaway", "f64_path", "skipped", "rsv10", "rsv11")
+COUNTER_NAMES = ("samples", "inbounds", "hits", "exact_div", "oob", "acos_ties", "launches", "runaway", "f64_path", "skipped", "bounds", "rsv11")
 
 _lib = None
 

@@ -95,7 +95,7 @@ inline std::vector<Eigen::Affine3f> repositionCamerasSampled(const std::vector<E
     std::vector<float> poses(12 * n);
     for (size_t i = 0; i < n; i++) pose12(cameras[i], &poses[12 * i]);
     std::vector<int32_t> nearest(n, -1);
-    dmf_forward_params p = {DMF_MODE_MINIMUM, 1, 1, 1, DMF_GRID_BIT, 0};
+    dmf_forward_params p = {DMF_MODE_MINIMUM, 1, 1, 1, DMF_GRID_AUTO, 0};
     dmf_forward_out out = {};
     out.min_depth = nearest.data();
     must(dmf_forward(ctx, &p, poses.data(), (int)n, &out), "dmf_forward");

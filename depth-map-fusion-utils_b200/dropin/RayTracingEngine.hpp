@@ -135,7 +135,7 @@ inline std::pair<bool, std::vector<unsigned long long int>> forward_ids(Camera& 
 {
     dmf_ctx* ctx = sync(cam, volume);
     float pose[12]; pose12(T, pose);
-    dmf_forward_params p = {mode, zdelta, sparse ? 1 : 0, 1, DMF_GRID_BIT, 0};
+    dmf_forward_params p = {mode, zdelta, sparse ? 1 : 0, 1, DMF_GRID_AUTO, 0};
     std::vector<uint64_t> ids((size_t)cam.getHeight() * cam.getWidth() + 1);
     int64_t offsets[2] = {0, 0};
     int32_t found = 0;
@@ -151,7 +151,7 @@ inline void forward_marks(Camera& cam, Volume& volume, Eigen::Affine3f& T, int m
     dmf_ctx* ctx = sync(cam, volume);
     push_marks(ctx, volume);
     float pose[12]; pose12(T, pose);
-    dmf_forward_params p = {mode, zdelta, sparse ? 1 : 0, view, DMF_GRID_BIT, 0};
+    dmf_forward_params p = {mode, zdelta, sparse ? 1 : 0, view, DMF_GRID_AUTO, 0};
     dmf_forward_out out = {};
     must(dmf_forward(ctx, &p, pose, 1, &out), "dmf_forward");
     pull_marks(ctx, volume);
@@ -210,7 +210,7 @@ inline int RayTracingEngine::rayTraceAndGetMinimum(VoxelVolume& volume,Eigen::Af
 {
     dmf_ctx* ctx = dmf_dropin::sync(cam_, volume);
     float pose[12]; dmf_dropin::pose12(transformation, pose);
-    dmf_forward_params p = {DMF_MODE_MINIMUM, zdelta, sparse ? 1 : 0, 1, DMF_GRID_BIT, 0};
+    dmf_forward_params p = {DMF_MODE_MINIMUM, zdelta, sparse ? 1 : 0, 1, DMF_GRID_AUTO, 0};
     int32_t min_depth = -1;
     dmf_forward_out out = {};
     out.min_depth = &min_depth;

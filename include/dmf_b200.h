@@ -45,7 +45,9 @@ enum {
 /* occupancy format probed by the march */
 enum {
     DMF_GRID_BIT  = 0, /* linear bit grid, [x][y][z] z fastest, uint32 words (1/8 byte per voxel)  */
-    DMF_GRID_BYTE = 1  /* one byte per voxel, [x][y][z] z fastest like voxels_[x][y][z] (Volume.hpp:126) */
+    DMF_GRID_BYTE = 1, /* one byte per voxel, [x][y][z] z fastest like voxels_[x][y][z] (Volume.hpp:126): Chebyshev distance bytes  */
+    DMF_GRID_AUTO = 2  /* the library picks: the bit grid for the first forward call on a volume, the distance bytes once they exist
+                          (the reverse march builds them) or from the second call on (results are identical either way)          */
 };
 
 /* ---- lifetime --------------------------------------------------------------------------------- */
@@ -296,6 +298,7 @@ enum {
     DMF_CNT_RUNAWAY = 7,   /* reverse marches stopped by the step cap                                     */
     DMF_CNT_F64_PATH = 8,  /* probes whose float index filter was inconclusive and were redone in double           */
     DMF_CNT_SKIPPED = 9,   /* probes proven empty by the macro-cell traversal without being evaluated              */
+    DMF_CNT_BOUNDS = 10,   /* checked build only (-DDMF_CHECKED): computed grid/table indices that were out of range; must be 0 */
     DMF_CNT_COUNT = 12
 };
 int dmf_counters(dmf_ctx* ctx, uint64_t out[DMF_CNT_COUNT]);  /* cumulative; synchronises */
