@@ -122,7 +122,12 @@ int dmf_reverse(dmf_ctx* c, int fast, int viz, const float* poses, int n_views, 
             char* hs = (char*)c->stage.p;
             if (c->n_occ) {
                 DMF_TRY(c->d_out_occ.reserve((size_t)nv * c->n_occ * 4)); DMF_TRY(c->d_ids.reserve((size_t)cap_dev * 8));
-                k_bits_to_list<<<nv, 256, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_out_occ.as<int>(), c->d_n_ids.as<int>(), (int)c->n_occ);
+                const int nbb = (int)(((c->n_occ + 31) / 32 + BITS_TILE - 1) / BITS_TILE);
+                DMF_TRY(c->d_misc[2].reserve((size_t)nv * nbb * 4)); DMF_TRY(c->d_misc[3].reserve(std::max<size_t>((size_t)nv * nbb * 4, 64)));
+                k_bits_count<<<dim3(nbb, nv), BITS_TILE, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_misc[2].as<unsigned>(), nbb);
+                k_win_offsets<<<nv, 1024, 0, st>>>(c->d_misc[2].as<unsigned>(), c->d_misc[3].as<unsigned>(), c->d_n_ids.as<int>(), nbb);
+                k_bits_emit<<<dim3(nbb, nv), BITS_TILE, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_misc[3].as<unsigned>(), nbb, c->d_out_occ.as<int>(), (int)c->n_occ);
+                c->launches += 2;
                 k_ids_offsets<<<1, 1024, 0, st>>>(c->d_n_ids.as<int>(), nv, c->d_offsets.as<long long>());
                 k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->d_centroid_hash.as<u64>(), c->d_ids.as<u64>(), (int)c->n_occ, cap_dev);
                 c->launches += 3;

@@ -531,7 +531,6 @@ int dmf_create(dmf_ctx** out, int device) {
     }
     DMF_TRY(c->d_counters.reserve(DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
     DMF_CUDA(cudaMemset(c->d_counters.p, 0, DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
-    DMF_CUDA(cudaFuncSetAttribute(k_order_ids, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * ORD_THREADS * 4));
     c->angle = bisect_angle_test();
     *out = c;
     return 0;
@@ -832,7 +831,18 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
             k_win_count<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[0].as<unsigned>(), (int)R, (int)c->n_occ, nb);
             k_win_offsets<<<nv, 1024, 0, st>>>(c->d_misc[0].as<unsigned>(), c->d_misc[1].as<unsigned>(), c->d_n_ids.as<int>(), nb);
             k_win_compact<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[1].as<unsigned>(), c->d_tmp_a.as<unsigned>(), (int)R, (int)c->n_occ, nb);
-            k_order_ids<<<nv, ORD_THREADS, 32 * ORD_THREADS * 4, st>>>(ro, c->d_tmp_a.as<unsigned>(), c->d_tmp_b.as<unsigned>(), c->d_out_occ.as<int>(), c->d_n_ids.as<int>(), (int)R);
+            {   // discovery order: stable 2 x 5-bit radix sort of the compacted keys on their z-plane (bits 21..30), multi-block
+                const int nblk = (int)((std::min<size_t>(R, std::max<size_t>(c->n_occ, 1)) + ORD_TILE - 1) / ORD_TILE);    // winners per view <= min(rays, voxels)
+                DMF_TRY(c->d_misc[2].reserve((size_t)nv * 32 * nblk * 4));
+                unsigned* hist = c->d_misc[2].as<unsigned>();
+                k_ord_hist<<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, (int)R, nblk, 21);
+                k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk);
+                k_ord_scatter<false><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, c->d_tmp_b.as<unsigned>(), nullptr, nullptr, (int)R, nblk, 21);
+                k_ord_hist<<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, (int)R, nblk, 26);
+                k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk);
+                k_ord_scatter<true><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, nullptr, ro, c->d_out_occ.as<int>(), (int)R, nblk, 26);
+                c->launches += 5;
+            }
             k_ids_offsets<<<1, 1024, 0, st>>>(c->d_n_ids.as<int>(), nv, c->d_offsets.as<long long>());
             k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->vol.occ_ids, c->d_ids.as<u64>(), (int)R, cap_dev);
             c->launches += 6;

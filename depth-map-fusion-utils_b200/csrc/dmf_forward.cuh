@@ -1153,65 +1153,14 @@ __global__ void k_finish_min_depth(int* min_depth, int n) {
 // ---- discovery order -------------------------------------------------------------------------------------
 // The reference appends an id the first time a (z_depth, r, c)-ordered scan emits it (:484-488, :432-436).
 // A ray "wins" its voxel if its key (k<<21 | lattice index) equals first_key[occ]; the returned list is the
-// winners sorted by key.  Keys are unique and the input is already in lattice (r,c) order, so a stable
-// 2-pass (5+5 bit) LSD counting sort on k alone suffices.  One block per view; every thread owns a contiguous
-// run of the input so stability needs no intra-block ranking.
-constexpr int ORD_THREADS = 512;
-
-__device__ __forceinline__ unsigned block_exclusive_scan_512(unsigned val, unsigned* s_warp, unsigned& total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned x = val;
-    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned w = (lane < ORD_THREADS / 32) ? s_warp[lane] : 0;
-        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
-        s_warp[lane] = w;   // inclusive
-    }
-    __syncthreads();
-    unsigned base = warp ? s_warp[warp - 1] : 0;
-    total = s_warp[ORD_THREADS / 32 - 1];
-    __syncthreads();
-    return base + x - val;
-}
-
-// one stable counting-sort pass on digit = (key >> shift) & 31 over items src[0..n); PASS 0 filters winners.
-template <int PASS>
-__device__ void order_pass(const unsigned* src, const int* ray_occ, const unsigned* first_key, unsigned* dst, int n, int shift,
-                           unsigned (*s_off)[ORD_THREADS], unsigned* s_warp, unsigned& n_out) {
-    const int t = threadIdx.x;
-    const int chunk = (n + ORD_THREADS - 1) / ORD_THREADS;
-    const int b = min(n, t * chunk), e = min(n, b + chunk);
-    for (int d = 0; d < 32; d++) s_off[d][t] = 0;
-    for (int i = b; i < e; i++) {
-        unsigned key = src[i];
-        bool take = PASS ? true : (key != 0xFFFFFFFFu && first_key[ray_occ[i]] == key);
-        if (take) s_off[(key >> shift) & 31][t]++;
-    }
-    __syncthreads();
-    // exclusive scan over the (digit-major, thread-minor) linearisation: thread t owns entries [32t, 32t+32)
-    unsigned* lin = &s_off[0][0];
-    unsigned sum = 0;
-    for (int j = 0; j < 32; j++) sum += lin[32 * t + j];
-    unsigned total;
-    unsigned base = block_exclusive_scan_512(sum, s_warp, total);
-    for (int j = 0; j < 32; j++) { unsigned c = lin[32 * t + j]; lin[32 * t + j] = base; base += c; }
-    __syncthreads();
-    for (int i = b; i < e; i++) {
-        unsigned key = src[i];
-        bool take = PASS ? true : (key != 0xFFFFFFFFu && first_key[ray_occ[i]] == key);
-        if (take) dst[s_off[(key >> shift) & 31][t]++] = key;
-    }
-    n_out = total;
-    __syncthreads();
-}
+// winners sorted by key.  Keys are unique and the compaction below keeps lattice (r,c) order, so a stable
+// 2-pass (5+5 bit) LSD radix sort on k alone suffices (k_ord_*).
 
 // Stage 1 (multi-block, fully parallel over the lattice): stable compaction of the winners' keys in lattice order.
 //   k_win_count   blk_cnt[view][b] = winners among lattice entries [b*WIN_BLOCK, (b+1)*WIN_BLOCK)
 //   k_win_offsets per view: exclusive scan of blk_cnt -> blk_off, total -> n_win[view]
 //   k_win_compact tmp[view][blk_off + rank inside the block] = key
-constexpr int WIN_THREADS = 256, WIN_ITEMS = 8, WIN_BLOCK = WIN_THREADS * WIN_ITEMS;
+constexpr int WIN_THREADS = 256, WIN_ITEMS = 2, WIN_BLOCK = WIN_THREADS * WIN_ITEMS;      // (8 items per thread left a single view with 150 blocks on 148 SMs: 13 us of dependent gathers)
 
 __device__ __forceinline__ bool is_winner(const unsigned* rk, const int* ro, const unsigned* fk, int i, int R, unsigned& key) {
     if (i >= R) return false;
@@ -1279,21 +1228,80 @@ __global__ void __launch_bounds__(WIN_THREADS) k_win_compact(const unsigned* ray
     }
 }
 
-// Stage 2: one block per view sorts the (few) compacted winners by z-plane with the stable 2-pass counting sort.
-// tmp_a holds the compacted keys (n_win[view] of them); out_occ receives the winners' occupied ordinals in discovery order.
-__global__ void __launch_bounds__(ORD_THREADS) k_order_ids(const int* ray_occ, unsigned* tmp_a, unsigned* tmp_b, int* out_occ, const int* n_win, int R) {
-    extern __shared__ unsigned s_dyn[];
-    unsigned (*s_off)[ORD_THREADS] = (unsigned (*)[ORD_THREADS])s_dyn;
+// Stage 2, multi-block (round 1 sorted each view in ONE block: 110-195 us for the ~24 k winners of one VGA view, the longest
+// kernel of a single-view call): a stable LSD radix sort of the compacted keys on their z-plane bits, two
+// passes of 5 bits (keys are unique and arrive in lattice order, so stability on k alone gives (k, r, c) order).  Per pass:
+//   k_ord_hist    per block of ORD_TILE keys: histogram of the 32 digit values           -> hist[view][digit][block]
+//   k_ord_scan    per view: exclusive scan of hist in (digit-major, block-minor) order   -> same array, in place
+//   k_ord_scatter per block: stable rank of every key among equal digits of the block (warp match + per-warp counts), scatter
+constexpr int ORD_TILE = 1024;                    // keys per block = threads per block
+__global__ void __launch_bounds__(ORD_TILE) k_ord_hist(const unsigned* __restrict__ keys, const int* __restrict__ n_win, unsigned* __restrict__ hist, int R, int nblk, int shift) {
+    __shared__ unsigned s_h[32];
+    const int view = blockIdx.y, nw = n_win[view];
+    if ((int)(blockIdx.x * ORD_TILE) >= nw) { if (threadIdx.x < 32) hist[((size_t)view * 32 + threadIdx.x) * nblk + blockIdx.x] = 0u; return; }
+    if (threadIdx.x < 32) s_h[threadIdx.x] = 0u;
+    __syncthreads();
+    const int i = blockIdx.x * ORD_TILE + threadIdx.x;
+    const unsigned digit = i < nw ? (keys[(size_t)view * R + i] >> shift) & 31u : 32u;
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    if (digit < 32u && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&s_h[digit], (unsigned)__popc(peers));
+    __syncthreads();
+    if (threadIdx.x < 32) hist[((size_t)view * 32 + threadIdx.x) * nblk + blockIdx.x] = s_h[threadIdx.x];
+}
+__global__ void __launch_bounds__(1024) k_ord_scan(unsigned* __restrict__ hist, int nblk) {
     __shared__ unsigned s_warp[32];
-    const int view = blockIdx.x;
-    const int* ro = ray_occ + (size_t)view * R;
-    unsigned* ta = tmp_a + (size_t)view * R;
-    unsigned* tb = tmp_b + (size_t)view * R;
-    const int nw = n_win[view];
-    unsigned n1 = 0, n2 = 0;
-    order_pass<1>(ta, nullptr, nullptr, tb, nw, 21, s_off, s_warp, n1);   // low 5 bits of k
-    order_pass<1>(tb, nullptr, nullptr, ta, nw, 26, s_off, s_warp, n2);   // high 5 bits of k
-    for (int i = threadIdx.x; i < nw; i += ORD_THREADS) out_occ[(size_t)view * R + i] = ro[ta[i] & 0x1FFFFFu];
+    __shared__ unsigned s_carry;
+    unsigned* h = hist + (size_t)blockIdx.x * 32 * nblk;
+    const int n = 32 * nblk;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned val = i < n ? h[i] : 0u;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        unsigned x = val;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) { unsigned w = s_warp[lane]; for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; } s_warp[lane] = w; }
+        __syncthreads();
+        const unsigned excl = s_carry + (warp ? s_warp[warp - 1] : 0u) + x - val;
+        if (i < n) h[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + val;
+        __syncthreads();
+    }
+}
+// FINAL: instead of the sorted keys write the winners' occupied ordinals (ray_occ of the lattice index in the key's low 21 bits)
+template <bool FINAL>
+__global__ void __launch_bounds__(ORD_TILE) k_ord_scatter(const unsigned* __restrict__ keys, const int* __restrict__ n_win, const unsigned* __restrict__ hist,
+                                                          unsigned* __restrict__ dst, const int* __restrict__ ray_occ, int* __restrict__ out_occ, int R, int nblk, int shift) {
+    __shared__ unsigned s_cnt[32][33];            // [warp][digit] -> exclusive prefix over the warps of this block
+    const int view = blockIdx.y, nw = n_win[view];
+    if ((int)(blockIdx.x * ORD_TILE) >= nw) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * ORD_TILE + threadIdx.x;
+    const unsigned key = i < nw ? keys[(size_t)view * R + i] : 0u;
+    const unsigned digit = i < nw ? (key >> shift) & 31u : 32u;
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const unsigned rank_in_warp = (unsigned)__popc(peers & ((1u << lane) - 1u));
+    s_cnt[warp][lane] = 0u;
+    __syncwarp();
+    if (digit < 32u && lane == __ffs(peers) - 1) s_cnt[warp][digit] = (unsigned)__popc(peers);
+    __syncthreads();
+    {   // thread (d = warp, w = lane): exclusive scan over the warps w of digit d's counts
+        const unsigned c = s_cnt[lane][warp];
+        unsigned x = c;
+        for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        __syncthreads();
+        s_cnt[lane][warp] = x - c;
+    }
+    __syncthreads();
+    if (digit < 32u) {
+        const unsigned pos = hist[((size_t)view * 32 + digit) * nblk + blockIdx.x] + s_cnt[warp][digit] + rank_in_warp;
+        if (FINAL) out_occ[(size_t)view * R + pos] = ray_occ[(size_t)view * R + (key & 0x1FFFFFu)];
+        else dst[(size_t)view * R + pos] = key;
+    }
 }
 
 // offsets[v] = sum of n[0..v) for the (few) views of a chunk, offsets[n_views] = total: one block, so that the id lists can be

@@ -434,31 +434,34 @@ __global__ void __launch_bounds__(128) k_segments_collide(const VolDev v, const 
     flush_counters(counters, n_samples, n_inb, n_hits, n_exact, 0u, 0u, 0u, n_f64, n_skip);
 }
 
-// visibility bitset -> occupied ordinals in ascending order (= emission order of reverseRayTraceFast), one block per view
-__global__ void __launch_bounds__(256) k_bits_to_list(const unsigned* vis, int vis_words32, int n_occ, int* out_occ, int* n_out, int stride) {
-    __shared__ unsigned s_warp[8];
-    __shared__ unsigned s_base;
-    const int view = blockIdx.x;
-    const unsigned* bits = vis + (size_t)view * vis_words32;
-    const int nwords = (n_occ + 31) / 32;
-    const int chunk = (nwords + 255) / 256;
-    const int b = min(nwords, (int)threadIdx.x * chunk), e = min(nwords, b + chunk);
-    unsigned cnt = 0;
-    for (int w = b; w < e; w++) cnt += __popc(bits[w]);
-    // block exclusive scan (256 threads)
+// visibility bitset -> occupied ordinals in ascending order (= emission order of reverseRayTraceFast).
+// Multi-block (a single view's 140 k voxels in one block took 15-29 us): blocks of BITS_TILE words count, one block
+// per view scans the counts (k_win_offsets), the blocks emit.
+constexpr int BITS_TILE = 256;                    // 32-bit words per block = threads per block (8192 voxels)
+__global__ void __launch_bounds__(BITS_TILE) k_bits_count(const unsigned* __restrict__ vis, int vis_words32, int n_occ, unsigned* __restrict__ blk_cnt, int nb) {
+    __shared__ unsigned s_warp[BITS_TILE / 32];
+    const int view = blockIdx.y, w = blockIdx.x * BITS_TILE + threadIdx.x, nwords = (n_occ + 31) / 32;
+    unsigned c = w < nwords ? (unsigned)__popc(vis[(size_t)view * vis_words32 + w]) : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned t = 0; for (int i = 0; i < BITS_TILE / 32; i++) t += s_warp[i]; blk_cnt[(size_t)view * nb + blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(BITS_TILE) k_bits_emit(const unsigned* __restrict__ vis, int vis_words32, int n_occ, const unsigned* __restrict__ blk_off, int nb,
+                                                        int* __restrict__ out_occ, int stride) {
+    __shared__ unsigned s_warp[BITS_TILE / 32];
+    const int view = blockIdx.y, w = blockIdx.x * BITS_TILE + threadIdx.x, nwords = (n_occ + 31) / 32;
+    unsigned m = w < nwords ? vis[(size_t)view * vis_words32 + w] : 0u;
+    const unsigned c = (unsigned)__popc(m);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned x = cnt;
+    unsigned x = c;
     for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
     if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    if (threadIdx.x == 0) { unsigned run = 0; for (int i = 0; i < 8; i++) { unsigned tmp = s_warp[i]; s_warp[i] = run; run += tmp; } s_base = run; }
-    __syncthreads();
-    unsigned pos = s_warp[warp] + x - cnt;
-    for (int w = b; w < e; w++) {
-        unsigned m = bits[w];
-        while (m) { int bit = __ffs(m) - 1; m &= m - 1; out_occ[(size_t)view * stride + pos++] = w * 32 + bit; }
-    }
-    if (threadIdx.x == 0) n_out[view] = (int)s_base;
+    unsigned before = 0;
+    for (int q = 0; q < warp; q++) before += s_warp[q];
+    unsigned pos = blk_off[(size_t)view * nb + blockIdx.x] + before + x - c;
+    while (m) { const int bit = __ffs(m) - 1; m &= m - 1; out_occ[(size_t)view * stride + pos++] = w * 32 + bit; }
 }
 
 // ---- K3: rayTraceVolume ---------------------------------------------------------------------------------------

@@ -300,7 +300,7 @@ class RayTracingEngine:
         ids = offs = None
         if "ids" in want and mode in (MODE_POINTS, MODE_GOOD_POINTS):
             cap = n * min(len(volume.occupied_cells_), H * W) + 1
-            ids, offs = np.zeros(cap, np.uint64), np.zeros(n + 1, np.int64)
+            ids, offs = np.empty(cap, np.uint64), np.zeros(n + 1, np.int64)
             o.ids, o.ids_offsets, o.ids_capacity = _vptr(ids), _vptr(offs), cap
         p = ForwardParams(mode, int(zdelta), int(bool(sparse)), int(view_id0), self.grid_format, (0 if self.skip_empty else FWD_NO_SKIP) | (FWD_CARVE if carve else 0))
         check(self.ctx.lib.dmf_forward(self.ctx.h, C.byref(p), _ptr(poses, C.c_float), n, C.byref(o)))
@@ -342,7 +342,7 @@ class RayTracingEngine:
         ids = offs = None
         if "ids" in want:
             cap = n * (2 * len(volume.occupied_cells_) + 64) + 1
-            ids, offs = np.zeros(cap, np.uint64), np.zeros(n + 1, np.int64)
+            ids, offs = np.empty(cap, np.uint64), np.zeros(n + 1, np.int64)
             o.ids, o.ids_offsets, o.ids_capacity = _vptr(ids), _vptr(offs), cap
         check(self.ctx.lib.dmf_reverse(self.ctx.h, int(bool(fast)), int(bool(viz)), _ptr(poses, C.c_float), n, C.byref(o)))
         if ids is not None:

@@ -14,6 +14,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <memory>
 #include <utility>
 #include <vector>
 #include <Eigen/Dense>
@@ -136,13 +138,16 @@ inline std::pair<bool, std::vector<unsigned long long int>> forward_ids(Camera& 
     dmf_ctx* ctx = sync(cam, volume);
     float pose[12]; pose12(T, pose);
     dmf_forward_params p = {mode, zdelta, sparse ? 1 : 0, 1, DMF_GRID_AUTO, 0};
-    std::vector<uint64_t> ids((size_t)cam.getHeight() * cam.getWidth() + 1);
+    // a view returns each voxel at most once and at most one id per pixel; the buffer is left uninitialised (zero-filling
+    // 2.4 MB per call cost more than the march of one VGA view)
+    const size_t cap = std::min((size_t)cam.getHeight() * cam.getWidth(), volume.occupied_cells_.size()) + 1;
+    std::unique_ptr<uint64_t[]> ids(new uint64_t[cap]);
     int64_t offsets[2] = {0, 0};
     int32_t found = 0;
     dmf_forward_out out = {};
-    out.found_any = &found; out.ids = ids.data(); out.ids_offsets = offsets; out.ids_capacity = ids.size();
+    out.found_any = &found; out.ids = ids.get(); out.ids_offsets = offsets; out.ids_capacity = cap;
     must(dmf_forward(ctx, &p, pose, 1, &out), "dmf_forward");
-    return std::make_pair(found != 0, std::vector<unsigned long long int>(ids.begin(), ids.begin() + offsets[1]));
+    return std::make_pair(found != 0, std::vector<unsigned long long int>(ids.get(), ids.get() + offsets[1]));
 }
 
 template <class Volume>
@@ -163,14 +168,15 @@ inline std::pair<bool, std::vector<unsigned long long int>> reverse_ids(Camera& 
     dmf_ctx* ctx = sync(cam, volume);
     if (viz) push_marks(ctx, volume);
     float pose[12]; pose12(T, pose);
-    std::vector<uint64_t> ids(2 * volume.occupied_cells_.size() + 65);
+    const size_t cap = 2 * volume.occupied_cells_.size() + 65;      // (the drifting whole-grid scan may visit a voxel twice)
+    std::unique_ptr<uint64_t[]> ids(new uint64_t[cap]);
     int64_t offsets[2] = {0, 0};
     int32_t found = 0;
     dmf_reverse_out out = {};
-    out.found_any = &found; out.ids = ids.data(); out.ids_offsets = offsets; out.ids_capacity = ids.size();
+    out.found_any = &found; out.ids = ids.get(); out.ids_offsets = offsets; out.ids_capacity = cap;
     must(dmf_reverse(ctx, fast ? 1 : 0, viz ? 1 : 0, pose, 1, &out), "dmf_reverse");
     if (viz) pull_marks(ctx, volume);
-    return std::make_pair(found != 0, std::vector<unsigned long long int>(ids.begin(), ids.begin() + offsets[1]));
+    return std::make_pair(found != 0, std::vector<unsigned long long int>(ids.get(), ids.get() + offsets[1]));
 }
 
 }  // namespace dmf_dropin
