@@ -50,7 +50,12 @@ int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_v
     if (fast) {
         if (!c->n_occ) return 0;
         dim3 grid((unsigned)((c->n_occ + 127) / 128), n_views);
-        if (c->reverse_format == DMF_GRID_BYTE) k_reverse<true, 1><<<grid, 128, 0, st>>>(a); else k_reverse<true, 0><<<grid, 128, 0, st>>>(a);
+        // distance bytes: the ray-pool kernel (lanes pull rays from a shared queue); DMF_REVERSE_NO_POOL=1 selects the one-thread-
+        // per-voxel kernel it replaced (same results and counters; the A/B baseline)
+        static const bool no_pool = std::getenv("DMF_REVERSE_NO_POOL") != nullptr;
+        if (c->reverse_format == DMF_GRID_BYTE && !no_pool) k_reverse_pool<<<dim3((unsigned)((c->n_occ + RP_BLOCK_VOX - 1) / RP_BLOCK_VOX), n_views), RP_THREADS, 0, st>>>(a);
+        else if (c->reverse_format == DMF_GRID_BYTE) k_reverse<true, 1><<<grid, 128, 0, st>>>(a);
+        else k_reverse<true, 0><<<grid, 128, 0, st>>>(a);
     } else {
         size_t total = (size_t)a.nax[0] * a.nax[1] * a.nax[2];
         if (!total) return 0;

@@ -359,6 +359,239 @@ __global__ void __launch_bounds__(128, REV_MIN_BLOCKS) k_reverse(const RevArgs a
     if (FAST && a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)view * a.vis_stride32), view, gridDim.x);
 }
 
+// ---- K2 with a ray pool: reverseRayTraceFast on distance bytes, the default ---------------------------------------------------
+// k_reverse<true,1> gives every occupied voxel a thread for its whole life: prologue (centroid, inverse transform, double-precision
+// deProjectPoint: 56 % of the voxels of a shell scene end here, outside the image), march, epilogue (normal test).  The warp then
+// waits for its longest march: ncu (profiles/r01_reverse_ncu_summary.txt) measured 14.8 of 32 lanes active, 11 in the line loop
+// that carries 61 % of the instructions.  Here a block takes RP_ROUNDS x RP_ROUND consecutive voxels and works in phases:
+//   P1  (all lanes busy)  every thread runs the prologue of its voxels of the round and pushes the rays that survive it -- with
+//       their line set-up and slab interval already computed -- into a queue in shared memory;
+//   P2  (the march)       lanes PULL rays from the queue: a lane whose march ends fetches the next ray at once, so the warp keeps
+//       stepping with (nearly) all lanes until the queue is dry; then the block refills it (P1 of the next round) while the lanes
+//       keep their unfinished rays in registers.  Only the last round drains;
+//   P3  (all lanes busy)  the voxels whose ray reached the volume boundary unoccluded get the depth window and the normal test.
+// The per-voxel results are collected in shared-memory bitsets (the block owns its 64 words of every row) and leave as plain
+// 32-bit stores.  The march itself is march_collides, one probe per loop iteration; samples / inbounds / skipped are counted
+// probe for probe as there, so the counters (and of course the bitsets) are identical to k_reverse<true,*>.
+#ifndef DMF_RP_MIN_BLOCKS
+#define DMF_RP_MIN_BLOCKS 8
+#endif
+#ifndef DMF_RP_ROUNDS
+#define DMF_RP_ROUNDS 4
+#endif
+constexpr int RP_THREADS = 128, RP_ROUND = 512, RP_ROUNDS = DMF_RP_ROUNDS, RP_BLOCK_VOX = RP_ROUND * RP_ROUNDS;
+struct RevRay { float cx, cy, cz, vx, vy, vz; int s_in, s_out; unsigned occ, pad; };
+
+__global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(const RevArgs a) {
+    __shared__ RevRay s_q[RP_ROUND];
+    __shared__ int s_head, s_tail;
+    __shared__ unsigned s_unocc[RP_BLOCK_VOX / 32], s_emit[RP_BLOCK_VOX / 32];
+    const VolDev& v = a.vol;
+    const int view = blockIdx.y;
+    const unsigned vox0 = blockIdx.x * (unsigned)RP_BLOCK_VOX;
+    const int lane = threadIdx.x & 31;
+    const float* T = a.poses + 12 * (size_t)view;
+    const float* I = a.inv_poses + 12 * (size_t)view;
+    for (int w = threadIdx.x; w < RP_BLOCK_VOX / 32; w += RP_THREADS) { s_unocc[w] = 0u; s_emit[w] = 0u; }
+    if (threadIdx.x == 0) { s_head = 0; s_tail = 0; }
+    unsigned n_samples = 0, n_inb = 0, n_hits = 0, n_exact = 0, n_ties = 0, n_runaway = 0, n_f64 = 0, n_skip = 0;
+
+    const float lo0 = v.lo[0], lo1 = v.lo[1], lo2 = v.lo[2], hi0 = v.hi[0], hi1 = v.hi[1], hi2 = v.hi[2];
+    const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2], cc0 = v.c32[0], cc1 = v.c32[1], cc2 = v.c32[2];
+    const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
+    const bool skip_ok = fmaxf(v.rev_eps[0], fmaxf(v.rev_eps[1], v.rev_eps[2])) <= 0.1f;
+    const float kM = 12582912.0f, e_safe = v.rev_esafe;
+    const int d0 = 50;                                              // the march of reverseRayTraceFast starts at 50 mm (:172)
+    const float tx = __ldg(T + 3), ty = __ldg(T + 7), tz = __ldg(T + 11);
+
+    // the ray a lane is marching (kept across refills)
+    bool have = false;
+    float cx = 0, cy = 0, cz = 0, vx = 0, vy = 0, vz = 0, qc0 = 0, qc1 = 0, qc2 = 0, qv0 = 0, qv1 = 0, qv2 = 0, sf = 0, rq = 0;
+    int depth = 0, s_in = 1, s_out = 0;
+    unsigned occ = 0; u64 chash = 0; bool fast_div = true;
+
+    for (int round = 0; round < RP_ROUNDS; round++) {
+        __syncthreads();                                            // the queue is dry (or this is the first round): refill from the start
+        if (threadIdx.x == 0) { s_head = 0; s_tail = 0; }
+        __syncthreads();
+        // ---- P1: prologue of this round's voxels, all lanes busy ----
+        for (int j = 0; j < RP_ROUND / RP_THREADS; j++) {
+            const unsigned o = vox0 + (unsigned)(round * RP_ROUND + j * RP_THREADS) + threadIdx.x;
+            bool live = o < (unsigned)v.n_occ;
+            RevRay r;
+            if (live) {
+                int xid, yid, zid;
+                occ_centroid(v, (int)o, xid, yid, zid, r.cx, r.cy, r.cz);
+                const float xx = affine_row(__ldg(I + 0), __ldg(I + 1), __ldg(I + 2), __ldg(I + 3), r.cx, r.cy, r.cz);
+                const float yy = affine_row(__ldg(I + 4), __ldg(I + 5), __ldg(I + 6), __ldg(I + 7), r.cx, r.cy, r.cz);
+                const float zz = affine_row(__ldg(I + 8), __ldg(I + 9), __ldg(I + 10), __ldg(I + 11), r.cx, r.cy, r.cz);
+                int pr, pc;
+                camera_pixel(a, xx, yy, zz, pr, pc);
+                live = pr >= 0 && pr < a.H && pc >= 0 && pc < a.W;                          // validPixel
+            }
+            if (live) {
+                r.vx = __fsub_rn(tx, r.cx); r.vy = __fsub_rn(ty, r.cy); r.vz = __fsub_rn(tz, r.cz);
+                const float n2 = sum3(__fmul_rn(r.vx, r.vx), __fmul_rn(r.vy, r.vy), __fmul_rn(r.vz, r.vz));
+                if (n2 > 0.0f) { const float sn = __fsqrt_rn(n2); r.vx = __fdiv_rn(r.vx, sn); r.vy = __fdiv_rn(r.vy, sn); r.vz = __fdiv_rn(r.vz, sn); }
+                // the slab in which the line is >= 0.25 voxel inside [0, min(ext, dim)] (as march_collides)
+                r.s_in = 1; r.s_out = 0;
+                if (skip_ok) {
+                    const float c0 = fmaf(r.cx, in0, cc0), c1 = fmaf(r.cy, in1, cc1), c2 = fmaf(r.cz, in2, cc2);
+                    const float w0 = (r.vx * 0.001f) * in0, w1 = (r.vy * 0.001f) * in1, w2 = (r.vz * 0.001f) * in2;
+                    float t0 = -1e30f, t1 = 1e30f;
+                    const float qc[3] = {c0, c1, c2}, qv[3] = {w0, w1, w2};
+#pragma unroll
+                    for (int ax = 0; ax < 3; ax++) {
+                        const float rr = fabsf(qv[ax]) > 1e-12f ? __fdividef(1.0f, qv[ax]) : 1e30f;
+                        const float ta = (0.25f - qc[ax]) * rr, tb = (fminf(v.ext[ax], (float)v.dim[ax]) - 0.25f - qc[ax]) * rr;
+                        t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+                    }
+                    if (t0 <= t1) {
+                        r.s_in = (int)fminf(fmaxf(ceilf(t0) + 1.0f, (float)d0), 1.0e9f);
+                        r.s_out = (int)fminf(fmaxf(floorf(t1) - 1.0f, -1.0f), 1.0e9f);
+                    }
+                }
+                r.occ = o; r.pad = 0u;
+            }
+            // warp-aggregated push
+            const unsigned m = __ballot_sync(0xffffffffu, live);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_tail, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (live) s_q[base + __popc(m & ((1u << lane) - 1u))] = r;
+        }
+        __syncthreads();
+        const int tail = s_tail;
+        const bool last_round = round == RP_ROUNDS - 1;
+        bool dry = false;                                                           // this lane has seen the queue empty in this round
+        // ---- P2: the march; lanes pull rays ----
+        for (;;) {
+            if (!have && !dry) {
+                const int i = atomicAdd(&s_head, 1);
+                dry = i >= tail;
+                if (!dry) {
+                    const RevRay r = s_q[i];
+                    cx = r.cx; cy = r.cy; cz = r.cz; vx = r.vx; vy = r.vy; vz = r.vz; s_in = r.s_in; s_out = r.s_out; occ = r.occ;
+                    chash = __ldg(a.centroid_hash + occ);
+                    qc0 = fmaf(cx, in0, cc0); qc1 = fmaf(cy, in1, cc1); qc2 = fmaf(cz, in2, cc2);
+                    qv0 = (vx * 0.001f) * in0; qv1 = (vy * 0.001f) * in1; qv2 = (vz * 0.001f) * in2;
+                    fast_div = fminf(fabsf(vx), fminf(fabsf(vy), fabsf(vz))) >= 7.888609052210118e-31f;
+                    const float step = fmaxf(fabsf(vx) * fabsf(in0), fmaxf(fabsf(vy) * fabsf(in1), fabsf(vz) * fabsf(in2))) * 0.001f;
+                    rq = 1.0f / fmaxf(step, 1e-3f);
+                    depth = d0; sf = (float)d0;
+                    have = true;
+                }
+            }
+            const unsigned busy = __ballot_sync(0xffffffffu, have);
+            if (busy == 0u) break;                                                  // nothing in flight in this warp and the queue is dry
+            if (!last_round && busy != 0xffffffffu) break;                          // the queue is dry: refill it, in-flight rays stay in registers
+            if (!have) continue;
+            // ---- one probe of march_collides ----
+            int result = -1;                                                         // -1: goes on, 0: reached the boundary unoccluded, 1: occluded
+            if (depth - d0 > a.step_cap) { n_runaway++; result = 0; }
+            else {
+                bool exact = true;
+                if (skip_ok && depth >= s_in && depth <= s_out) {
+                    const float q0 = fmaf(sf, qv0, qc0), q1 = fmaf(sf, qv1, qc1), q2 = fmaf(sf, qv2, qc2);
+                    const float m0 = __fadd_rd(q0, kM), m1 = __fadd_rd(q1, kM), m2 = __fadd_rd(q2, kM);
+                    const int ix = __float_as_int(m0) - 0x4B400000, iy = __float_as_int(m1) - 0x4B400000, iz = __float_as_int(m2) - 0x4B400000;
+                    unsigned lidx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+                    DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
+                    const unsigned d = __ldg(v.bytes + lidx);
+                    if (d >= 2u) {
+                        const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
+                        const float adv = fminf(__fadd_rd(fmaf(df - 1.25f, rq, 1.0f), kM) - kM, (float)a.step_cap + 1.0f);
+                        // march_collides leaves its line loop once s passes s_out (or the cap) and counts up to (int)s: the same here
+                        sf += adv;
+                        const unsigned n = (unsigned)((int)sf - depth);
+                        n_samples += n; n_inb += n; n_skip += n;
+                        depth = (int)sf;
+                        exact = false;
+                    } else {
+                        const float f0 = q0 - (m0 - kM), f1 = q1 - (m1 - kM), f2 = q2 - (m2 - kM);
+                        if (fminf(f0, fminf(f1, f2)) >= e_safe && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e_safe) {
+                            exact = false;
+                            n_samples++; n_inb++; n_skip++;
+                            if (d == 0u && hash_coords(ix, iy, iz) != chash) result = 1;      // an occupied voxel other than the origin
+                            else { sf += 1.0f; depth++; }
+                        }
+                    }
+                }
+                if (exact) {
+                    const float ax = __fmul_rn(vx, sf), ay = __fmul_rn(vy, sf), az = __fmul_rn(vz, sf);
+                    float qx, qy, qz;
+                    if (fast_div) { qx = div1000_short(ax); qy = div1000_short(ay); qz = div1000_short(az); }
+                    else { qx = __fdiv_rn(ax, 1000.0f); qy = __fdiv_rn(ay, 1000.0f); qz = __fdiv_rn(az, 1000.0f); }
+                    const float px = __fadd_rn(cx, qx), py = __fadd_rn(cy, qy), pz = __fadd_rn(cz, qz);
+                    n_samples++;
+                    if (!(px > lo0 && px < hi0 && py > lo1 && py < hi1 && pz > lo2 && pz < hi2)) result = 0;      // validPoints == false: break
+                    else {
+                        n_inb++;
+                        bool unsafe = false;
+                        int ix = voxel_index_f32(px, in0, cc0, v.err32[0], unsafe);
+                        int iy = voxel_index_f32(py, in1, cc1, v.err32[1], unsafe);
+                        int iz = voxel_index_f32(pz, in2, cc2, v.err32[2], unsafe);
+                        if (unsafe) {
+                            n_f64++;
+                            ix = voxel_index(px, v.vmin[0], v.delta[0], v.inv[0], v.c0[0], v.eps[0], n_exact);
+                            iy = voxel_index(py, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], n_exact);
+                            iz = voxel_index(pz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], n_exact);
+                        }
+                        int n = 0;
+                        if (hash_coords(ix, iy, iz) != chash) {                    // hash == centroid_hash: same voxel as the origin, continue
+                            if (!coords_valid(v, ix, iy, iz)) result = 0;          // validCoords == false: break
+                            else {
+                                const unsigned d = __ldg(v.bytes + (((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz));
+                                if (d == 0u) result = 1;
+                                else if (skip_ok && d >= 2u) {
+                                    const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
+                                    n = min(__float_as_int(__fadd_rd((df - 1.25f) * rq, kM)) - 0x4B400000, a.step_cap);
+                                    n_samples += (unsigned)n; n_inb += (unsigned)n; n_skip += (unsigned)n;
+                                }
+                            }
+                        }
+                        if (result < 0) { depth += n + 1; sf += (float)(n + 1); }
+                    }
+                }
+            }
+            if (result >= 0) {
+                if (result == 0) { const unsigned lv = occ - vox0; atomicOr(&s_unocc[lv >> 5], 1u << (lv & 31)); n_hits++; }
+                have = false;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- P3: depth window + normal test of the unoccluded voxels; results out ----
+    for (int j = 0; j < RP_BLOCK_VOX / RP_THREADS; j++) {
+        const unsigned lv = (unsigned)(j * RP_THREADS) + threadIdx.x, o = vox0 + lv;
+        if (!((s_unocc[lv >> 5] >> (lv & 31)) & 1u)) continue;
+        int xid, yid, zid; float ccx, ccy, ccz;
+        occ_centroid(v, (int)o, xid, yid, zid, ccx, ccy, ccz);
+        const float zz = affine_row(__ldg(I + 8), __ldg(I + 9), __ldg(I + 10), __ldg(I + 11), ccx, ccy, ccz);
+        if (a.viz) a.view_mark[o] = 1;                                                   // :205
+        if ((double)zz >= 0.20 && (double)zz <= 1.0) {                                   // k_ZMin, k_ZMax (:206)
+            float dx = __fsub_rn(tx, ccx), dy = __fsub_rn(ty, ccy), dz = __fsub_rn(tz, ccz);
+            const float n2 = sum3(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz));
+            if (n2 > 0.0f) { const float sn = __fsqrt_rn(n2); dx = __fdiv_rn(dx, sn); dy = __fdiv_rn(dy, sn); dz = __fdiv_rn(dz, sn); }
+            if (any_normal_faces(v, a.angle, (int)o, dx, dy, dz, n_ties)) atomicOr(&s_emit[lv >> 5], 1u << (lv & 31));
+        }
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < RP_BLOCK_VOX / 32; w += RP_THREADS) {
+        const unsigned gw = blockIdx.x * (unsigned)(RP_BLOCK_VOX / 32) + (unsigned)w;
+        if (gw * 32u >= (unsigned)v.n_occ) break;
+        const unsigned mu = s_unocc[w], me = s_emit[w];
+        if (mu && a.found_any) raise_flag(a.found_any + view);
+        if (a.unocc && mu) a.unocc[(size_t)view * a.vis_words32 + gw] = mu;              // the block owns these words of the (zeroed) rows
+        if (me) {
+            if (a.viz) atomicOr(a.good_bits + gw, me);                                   // :215 (shared by all views)
+            if (a.vis) a.vis[(size_t)view * a.vis_stride32 + gw] = me;
+        }
+    }
+    flush_counters(a.counters, n_samples, n_inb, n_hits, n_exact, 0u, n_ties, n_runaway, n_f64, n_skip);
+    if (a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)view * a.vis_stride32), view, gridDim.x);
+}
+
 // ---- K7: willCollide (tests/CameraPathGen.cpp:128-156 and the unguarded copies in CameraMotionTSP.cpp:236-261,
 // CameraMotionPlanner.cpp:246-271), one thread per segment a->b: 1 mm float march `a + v*double(depth)/1000.0` while
 // depth <= |a-b|*1000; samples outside the volume are skipped (continue), an occupied voxel ends the march.
