@@ -405,9 +405,8 @@ __global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(
     const float tx = __ldg(T + 3), ty = __ldg(T + 7), tz = __ldg(T + 11);
 
     // the ray a lane is marching (kept across refills)
-    bool have = false;
-    float cx = 0, cy = 0, cz = 0, vx = 0, vy = 0, vz = 0, qc0 = 0, qc1 = 0, qc2 = 0, qv0 = 0, qv1 = 0, qv2 = 0, sf = 0, rq = 0;
-    int depth = 0, s_in = 1, s_out = 0;
+    bool have = false, on_line = false;
+    float cx = 0, cy = 0, cz = 0, vx = 0, vy = 0, vz = 0, qc0 = 0, qc1 = 0, qc2 = 0, qv0 = 0, qv1 = 0, qv2 = 0, sf = 0, rq = 0, s_inf = 1.0f, s_outf = 0.0f;
     unsigned occ = 0; u64 chash = 0; bool fast_div = true;
 
     for (int round = 0; round < RP_ROUNDS; round++) {
@@ -465,59 +464,16 @@ __global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(
         const bool last_round = round == RP_ROUNDS - 1;
         bool dry = false;                                                           // this lane has seen the queue empty in this round
         // ---- P2: the march; lanes pull rays ----
+        // Two nested loops.  The inner one is the line loop of march_collides and nothing else (one vote + ~25 instructions per
+        // probe); it runs for as long as at least `quorum` lanes can follow their line.  Everything rare -- fetching the next
+        // ray, an exact step (outside the slab, or next to a voxel face), ending a ray -- happens in the outer loop, where the
+        // lanes that do not need it wait; the vote bounds how many can be waiting while the inner loop runs.
         for (;;) {
-            if (!have && !dry) {
-                const int i = atomicAdd(&s_head, 1);
-                dry = i >= tail;
-                if (!dry) {
-                    const RevRay r = s_q[i];
-                    cx = r.cx; cy = r.cy; cz = r.cz; vx = r.vx; vy = r.vy; vz = r.vz; s_in = r.s_in; s_out = r.s_out; occ = r.occ;
-                    chash = __ldg(a.centroid_hash + occ);
-                    qc0 = fmaf(cx, in0, cc0); qc1 = fmaf(cy, in1, cc1); qc2 = fmaf(cz, in2, cc2);
-                    qv0 = (vx * 0.001f) * in0; qv1 = (vy * 0.001f) * in1; qv2 = (vz * 0.001f) * in2;
-                    fast_div = fminf(fabsf(vx), fminf(fabsf(vy), fabsf(vz))) >= 7.888609052210118e-31f;
-                    const float step = fmaxf(fabsf(vx) * fabsf(in0), fmaxf(fabsf(vy) * fabsf(in1), fabsf(vz) * fabsf(in2))) * 0.001f;
-                    rq = 1.0f / fmaxf(step, 1e-3f);
-                    depth = d0; sf = (float)d0;
-                    have = true;
-                }
-            }
-            const unsigned busy = __ballot_sync(0xffffffffu, have);
-            if (busy == 0u) break;                                                  // nothing in flight in this warp and the queue is dry
-            if (!last_round && busy != 0xffffffffu) break;                          // the queue is dry: refill it, in-flight rays stay in registers
-            if (!have) continue;
-            // ---- one probe of march_collides ----
-            int result = -1;                                                         // -1: goes on, 0: reached the boundary unoccluded, 1: occluded
-            if (depth - d0 > a.step_cap) { n_runaway++; result = 0; }
-            else {
-                bool exact = true;
-                if (skip_ok && depth >= s_in && depth <= s_out) {
-                    const float q0 = fmaf(sf, qv0, qc0), q1 = fmaf(sf, qv1, qc1), q2 = fmaf(sf, qv2, qc2);
-                    const float m0 = __fadd_rd(q0, kM), m1 = __fadd_rd(q1, kM), m2 = __fadd_rd(q2, kM);
-                    const int ix = __float_as_int(m0) - 0x4B400000, iy = __float_as_int(m1) - 0x4B400000, iz = __float_as_int(m2) - 0x4B400000;
-                    unsigned lidx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
-                    DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
-                    const unsigned d = __ldg(v.bytes + lidx);
-                    if (d >= 2u) {
-                        const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
-                        const float adv = fminf(__fadd_rd(fmaf(df - 1.25f, rq, 1.0f), kM) - kM, (float)a.step_cap + 1.0f);
-                        // march_collides leaves its line loop once s passes s_out (or the cap) and counts up to (int)s: the same here
-                        sf += adv;
-                        const unsigned n = (unsigned)((int)sf - depth);
-                        n_samples += n; n_inb += n; n_skip += n;
-                        depth = (int)sf;
-                        exact = false;
-                    } else {
-                        const float f0 = q0 - (m0 - kM), f1 = q1 - (m1 - kM), f2 = q2 - (m2 - kM);
-                        if (fminf(f0, fminf(f1, f2)) >= e_safe && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e_safe) {
-                            exact = false;
-                            n_samples++; n_inb++; n_skip++;
-                            if (d == 0u && hash_coords(ix, iy, iz) != chash) result = 1;      // an occupied voxel other than the origin
-                            else { sf += 1.0f; depth++; }
-                        }
-                    }
-                }
-                if (exact) {
+            if (have && !on_line) {
+                // ---- one exact step of march_collides (or the end of the ray) ----
+                int result = -1;                                                     // -1: goes on, 0: reached the boundary unoccluded, 1: occluded
+                if (sf - (float)d0 > (float)a.step_cap) { n_runaway++; result = 0; }
+                else {
                     const float ax = __fmul_rn(vx, sf), ay = __fmul_rn(vy, sf), az = __fmul_rn(vz, sf);
                     float qx, qy, qz;
                     if (fast_div) { qx = div1000_short(ax); qy = div1000_short(ay); qz = div1000_short(az); }
@@ -550,14 +506,64 @@ __global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(
                                 }
                             }
                         }
-                        if (result < 0) { depth += n + 1; sf += (float)(n + 1); }
+                        if (result < 0) sf += (float)(n + 1);
+                    }
+                }
+                if (result >= 0) {
+                    if (result == 0) { const unsigned lv = occ - vox0; atomicOr(&s_unocc[lv >> 5], 1u << (lv & 31)); n_hits++; }
+                    have = false;
+                }
+            }
+            if (!have && !dry) {
+                const int i = atomicAdd(&s_head, 1);
+                dry = i >= tail;
+                if (!dry) {
+                    const RevRay r = s_q[i];
+                    cx = r.cx; cy = r.cy; cz = r.cz; vx = r.vx; vy = r.vy; vz = r.vz; occ = r.occ;
+                    // the line is followed for s in [s_in, s_out] and never beyond the step cap (there the exact step reports the runaway)
+                    s_inf = (float)r.s_in; s_outf = fminf((float)r.s_out, (float)(d0 + a.step_cap));
+                    chash = __ldg(a.centroid_hash + occ);
+                    qc0 = fmaf(cx, in0, cc0); qc1 = fmaf(cy, in1, cc1); qc2 = fmaf(cz, in2, cc2);
+                    qv0 = (vx * 0.001f) * in0; qv1 = (vy * 0.001f) * in1; qv2 = (vz * 0.001f) * in2;
+                    fast_div = fminf(fabsf(vx), fminf(fabsf(vy), fabsf(vz))) >= 7.888609052210118e-31f;
+                    const float step = fmaxf(fabsf(vx) * fabsf(in0), fmaxf(fabsf(vy) * fabsf(in1), fabsf(vz) * fabsf(in2))) * 0.001f;
+                    rq = 1.0f / fmaxf(step, 1e-3f);
+                    sf = (float)d0;
+                    have = true;
+                }
+            }
+            const unsigned busy = __ballot_sync(0xffffffffu, have);
+            if (busy == 0u) break;                                                  // nothing in flight in this warp and the queue is dry
+            if (!last_round && busy != 0xffffffffu) break;                          // the queue is dry: refill it, in-flight rays stay in registers
+            on_line = have && skip_ok && sf >= s_inf && sf <= s_outf;
+            const int quorum = max(1, (3 * __popc(busy)) >> 2);                      // keep at least 3/4 of the lanes that hold a ray stepping
+            float adv_sum = 0.0f;                                                    // samples this lane advanced in this run of the line loop
+            while (__popc(__ballot_sync(0xffffffffu, on_line)) >= quorum) {
+                if (on_line) {
+                    const float q0 = fmaf(sf, qv0, qc0), q1 = fmaf(sf, qv1, qc1), q2 = fmaf(sf, qv2, qc2);
+                    const float m0 = __fadd_rd(q0, kM), m1 = __fadd_rd(q1, kM), m2 = __fadd_rd(q2, kM);
+                    const int ix = __float_as_int(m0) - 0x4B400000, iy = __float_as_int(m1) - 0x4B400000, iz = __float_as_int(m2) - 0x4B400000;
+                    unsigned lidx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+                    DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
+                    const unsigned d = __ldg(v.bytes + lidx);
+                    if (d >= 2u) {
+                        const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
+                        const float adv = fminf(__fadd_rd(fmaf(df - 1.25f, rq, 1.0f), kM) - kM, (float)a.step_cap + 1.0f);
+                        sf += adv; adv_sum += adv;
+                        on_line = sf <= s_outf;
+                    } else {
+                        const float f0 = q0 - (m0 - kM), f1 = q1 - (m1 - kM), f2 = q2 - (m2 - kM);
+                        if (fminf(f0, fminf(f1, f2)) >= e_safe && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e_safe) {
+                            adv_sum += 1.0f;                                         // resolved on the line: an in-bounds step
+                            if (d == 0u && hash_coords(ix, iy, iz) != chash) { have = false; on_line = false; }      // an occupied voxel other than the origin: occluded
+                            else { sf += 1.0f; on_line = sf <= s_outf; }
+                        } else on_line = false;                                      // next to a face: this sample takes the exact step
                     }
                 }
             }
-            if (result >= 0) {
-                if (result == 0) { const unsigned lv = occ - vox0; atomicOr(&s_unocc[lv >> 5], 1u << (lv & 31)); n_hits++; }
-                have = false;
-            }
+            { const unsigned n = (unsigned)adv_sum; n_samples += n; n_inb += n; n_skip += n; }
+            on_line = false;                                                         // whoever still holds a ray takes an exact step (or is re-admitted) next
+            if (have && skip_ok && sf >= s_inf && sf <= s_outf) on_line = true;
         }
     }
     __syncthreads();
