@@ -50,9 +50,12 @@ int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_v
     if (fast) {
         if (!c->n_occ) return 0;
         dim3 grid((unsigned)((c->n_occ + 127) / 128), n_views);
-        // distance bytes: the ray-pool kernel (lanes pull rays from a shared queue); DMF_REVERSE_NO_POOL=1 selects the one-thread-
-        // per-voxel kernel it replaced (same results and counters; the A/B baseline)
-        static const bool no_pool = std::getenv("DMF_REVERSE_NO_POOL") != nullptr;
+        // DMF_REVERSE_POOL=1 selects the ray-pool kernel (lanes pull rays from a shared-memory queue, dmf_reverse.cuh): same results and
+        // counters, 26 of 32 lanes stepping instead of 11 -- and SLOWER (2.06 vs 1.53 ms per 128 views at S512, 6.4 vs 3.8 ms at
+        // S1024, profiles/r02_reverse_pool_ab.txt): the march is bound by the latency of its dependent byte loads, which the
+        // one-thread-per-voxel kernel hides with 64 resident warps at 32 registers; the pool needs 64 registers (32 warps).  Kept as
+        // the measured alternative, not the default.
+        static const bool no_pool = std::getenv("DMF_REVERSE_POOL") == nullptr;
         if (c->reverse_format == DMF_GRID_BYTE && !no_pool) k_reverse_pool<<<dim3((unsigned)((c->n_occ + RP_BLOCK_VOX - 1) / RP_BLOCK_VOX), n_views), RP_THREADS, 0, st>>>(a);
         else if (c->reverse_format == DMF_GRID_BYTE) k_reverse<true, 1><<<grid, 128, 0, st>>>(a);
         else k_reverse<true, 0><<<grid, 128, 0, st>>>(a);

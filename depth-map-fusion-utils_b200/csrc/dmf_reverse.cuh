@@ -359,7 +359,8 @@ __global__ void __launch_bounds__(128, REV_MIN_BLOCKS) k_reverse(const RevArgs a
     if (FAST && a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)view * a.vis_stride32), view, gridDim.x);
 }
 
-// ---- K2 with a ray pool: reverseRayTraceFast on distance bytes, the default ---------------------------------------------------
+// ---- K2 with a ray pool: reverseRayTraceFast on distance bytes (DMF_REVERSE_POOL=1; measured slower than k_reverse, see the
+// launch site in dmf_abi_rest.cuh -- kept as the recorded alternative of VERDICT r1 item 6) ------------------------------------
 // k_reverse<true,1> gives every occupied voxel a thread for its whole life: prologue (centroid, inverse transform, double-precision
 // deProjectPoint: 56 % of the voxels of a shell scene end here, outside the image), march, epilogue (normal test).  The warp then
 // waits for its longest march: ncu (profiles/r01_reverse_ncu_summary.txt) measured 14.8 of 32 lanes active, 11 in the line loop
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(
     const float tx = __ldg(T + 3), ty = __ldg(T + 7), tz = __ldg(T + 11);
 
     // the ray a lane is marching (kept across refills)
-    bool have = false, on_line = false;
+    bool have = false, on_line = false, need_exact = false;           // need_exact: the current sample lies next to a voxel face (line inconclusive)
     float cx = 0, cy = 0, cz = 0, vx = 0, vy = 0, vz = 0, qc0 = 0, qc1 = 0, qc2 = 0, qv0 = 0, qv1 = 0, qv2 = 0, sf = 0, rq = 0, s_inf = 1.0f, s_outf = 0.0f;
     unsigned occ = 0; u64 chash = 0; bool fast_div = true;
 
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(
                         if (result < 0) sf += (float)(n + 1);
                     }
                 }
+                need_exact = false;
                 if (result >= 0) {
                     if (result == 0) { const unsigned lv = occ - vox0; atomicOr(&s_unocc[lv >> 5], 1u << (lv & 31)); n_hits++; }
                     have = false;
@@ -529,13 +531,13 @@ __global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(
                     const float step = fmaxf(fabsf(vx) * fabsf(in0), fmaxf(fabsf(vy) * fabsf(in1), fabsf(vz) * fabsf(in2))) * 0.001f;
                     rq = 1.0f / fmaxf(step, 1e-3f);
                     sf = (float)d0;
-                    have = true;
+                    have = true; need_exact = false;
                 }
             }
             const unsigned busy = __ballot_sync(0xffffffffu, have);
             if (busy == 0u) break;                                                  // nothing in flight in this warp and the queue is dry
             if (!last_round && busy != 0xffffffffu) break;                          // the queue is dry: refill it, in-flight rays stay in registers
-            on_line = have && skip_ok && sf >= s_inf && sf <= s_outf;
+            on_line = have && !need_exact && skip_ok && sf >= s_inf && sf <= s_outf;
             const int quorum = max(1, (3 * __popc(busy)) >> 2);                      // keep at least 3/4 of the lanes that hold a ray stepping
             float adv_sum = 0.0f;                                                    // samples this lane advanced in this run of the line loop
             while (__popc(__ballot_sync(0xffffffffu, on_line)) >= quorum) {
@@ -557,13 +559,13 @@ __global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(
                             adv_sum += 1.0f;                                         // resolved on the line: an in-bounds step
                             if (d == 0u && hash_coords(ix, iy, iz) != chash) { have = false; on_line = false; }      // an occupied voxel other than the origin: occluded
                             else { sf += 1.0f; on_line = sf <= s_outf; }
-                        } else on_line = false;                                      // next to a face: this sample takes the exact step
+                        } else { on_line = false; need_exact = true; }              // next to a face: this sample takes the exact step
                     }
                 }
             }
             { const unsigned n = (unsigned)adv_sum; n_samples += n; n_inb += n; n_skip += n; }
-            on_line = false;                                                         // whoever still holds a ray takes an exact step (or is re-admitted) next
-            if (have && skip_ok && sf >= s_inf && sf <= s_outf) on_line = true;
+            // whoever still holds a ray either stays on its line (it only lost the vote) or takes an exact step next
+            on_line = have && !need_exact && skip_ok && sf >= s_inf && sf <= s_outf;
         }
     }
     __syncthreads();
