@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-skip", action="store_true", help="evaluate every probe (brute-force kernel)")
     ap.add_argument("--two-probe", action="store_true", help="byte grid: the previous skipping kernel (k_forward_dist) instead of the line-first one")
+    ap.add_argument("--count-in-timed", action="store_true", help="keep the DMF_CNT_* probe counters on in the timed launches")
     ap.add_argument("--cpu-threads", type=int, default=0, help="reference arm / all-core baseline: host threads (default: every CPU this process may run on)")
     return ap.parse_args()
 
@@ -399,16 +400,20 @@ def run_config2(args):
     d_points = torch.empty((V, H, W, 3), dtype=torch.float32, device=dev)
     d_voxel = torch.empty((V, H, W), dtype=torch.int64, device=dev)
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    params = ForwardParams(D.MODE_POINTS, sc.zdelta, 0, 1, fmt, (1 if args.no_skip else 0) | (2 if args.two_probe else 0))
+    base_flags = (1 if args.no_skip else 0) | (2 if args.two_probe else 0)
+    # timed launches run without the DMF_CNT_* probe counters (instrumentation the reference does not have); one identical untimed
+    # step with the counters on supplies the per-step probe counts reported below
+    params = ForwardParams(D.MODE_POINTS, sc.zdelta, 0, 1, fmt, base_flags | (0 if args.count_in_timed else D.FWD_NO_COUNTERS))
+    params_counted = ForwardParams(D.MODE_POINTS, sc.zdelta, 0, 1, fmt, base_flags)
     o = ForwardOut()
     o.depth_mm, o.points, o.hit_voxel = d_depth.data_ptr(), d_points.data_ptr(), d_voxel.data_ptr()
     outs = (C.POINTER(ForwardOut) * 1)(C.pointer(o))
     poses_dev = ptr_array(d_poses.data_ptr())
 
-    def step_dev():
+    def step_dev(p=None):
         st = torch.cuda.current_stream().cuda_stream
         assert st != 0
-        check(lib.dmf_sweep_forward_dev(comm.h, C.byref(params), poses_dev, n_total, outs, ptr_array(st)))
+        check(lib.dmf_sweep_forward_dev(comm.h, C.byref(p or params), poses_dev, n_total, outs, ptr_array(st)))
 
     for _ in range(args.warmup):
         step_dev()
@@ -432,11 +437,15 @@ def run_config2(args):
     torch.cuda.synchronize(); rig.barrier()
     wall = time.perf_counter() - t_wall
     dev_ms = rig.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    launches_timed = ctx.counters()["launches"]
+    ctx.reset_counters()
+    step_dev(params_counted); torch.cuda.synchronize()                  # the counted step (untimed): probe counts of ONE step
     cnt = ctx.counters()
     rays_total = args.steps * V * H * W * world
     value = rays_total / (dev_ms * 1e-3)
-    inbounds_total, samples_total, launches_total, skipped_total, f64_total, exact_total = rig.sum_over_ranks(
-        [cnt["inbounds"], cnt["samples"], cnt["launches"], cnt["skipped"], cnt["f64_path"], cnt["exact_div"]])
+    inb1, samp1, launches_total, skip1, f641, exact1 = rig.sum_over_ranks(
+        [cnt["inbounds"], cnt["samples"], launches_timed, cnt["skipped"], cnt["f64_path"], cnt["exact_div"]])
+    inbounds_total, samples_total, skipped_total, f64_total, exact_total = (x * args.steps for x in (inb1, samp1, skip1, f641, exact1))
 
     # ---- e2e: the host-buffer sweep.  Poses from pinned host memory in, the routine's result (visibility row + found flag per view)
     # back in pinned host memory, every step; H2D and D2H inside the timed region -----------------------------------------------
@@ -608,7 +617,7 @@ def run_config2(args):
         peak, peak_src = measured_peak()
         # algorithmic bytes of one march launch: 1/8 B (bit grid) or 1 B (byte grid) per in-bounds sample,
         # + 24 B per cast ray (int32 depth, float3 point, uint64 hit id), + n_occ/8 B visibility and 48 B pose per view
-        per_launch_inb = cnt["inbounds"] / args.steps
+        per_launch_inb = cnt["inbounds"]
         grid_b = 0.125 if fmt == D.GRID_BIT else 1.0
         alg_bytes = per_launch_inb * grid_b + V * H * W * 24 + V * (vw * 8 + 48)
         hot = float(np.mean(hot_ms)) if hot_ms else dev_ms / args.steps
@@ -623,6 +632,7 @@ def run_config2(args):
                        "mode": "rayTraceAndGetPoints", "grid_format": args.grid,
                        "outputs": "depth_mm+points+hit_voxel per pixel in HBM, visibility row + found flag per view gathered on every GPU", "n_occupied": n_occ,
                        "l2": "flushed between timed iterations (256 MiB fill, untimed)" if flush is not None else "not flushed",
+                       "probe_counters": "on in the timed launches" if args.count_in_timed else "off in the timed launches (DMF_FWD_NO_COUNTERS: instrumentation the reference does not have); counted in one identical untimed step",
                        "parallelism": f"C-ABI group of {world} GPU(s) (dmf_comm_init_rank), volume replicated GPU to GPU, exchange of the visibility rows: {exch}",
                        "host": rig.numa},
             "voxel_updates_per_s": inbounds_total / (dev_ms * 1e-3),

@@ -48,13 +48,14 @@ def run_config34(args, B):
     fusion = args.config == 3
     mode = D.MODE_CLASSIFY if fusion else D.MODE_POINTS
     flags = D.FWD_CARVE if fusion else 0
-    params = ForwardParams(mode, sc.zdelta, 0, 1, fmt, flags)
+    params = ForwardParams(mode, sc.zdelta, 0, 1, fmt, flags | (0 if args.count_in_timed else D.FWD_NO_COUNTERS))   # timed launches: probe counters off
+    params_counted = ForwardParams(mode, sc.zdelta, 0, 1, fmt, flags)
     d_poses = torch.from_numpy(rig.my_poses).to(dev)
     poses_dev = B.ptr_array(d_poses.data_ptr())
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step_dev():
-        check(lib.dmf_sweep_forward_dev(comm.h, C.byref(params), poses_dev, n_total, None, B.ptr_array(torch.cuda.current_stream().cuda_stream)))
+    def step_dev(p=None):
+        check(lib.dmf_sweep_forward_dev(comm.h, C.byref(p or params), poses_dev, n_total, None, B.ptr_array(torch.cuda.current_stream().cuda_stream)))
 
     for _ in range(args.warmup):
         step_dev()
@@ -76,8 +77,12 @@ def run_config34(args, B):
             hot_ms.append(ctx.last_hot_kernel_ms())
     torch.cuda.synchronize(); rig.barrier()
     dev_ms = rig.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    launches_timed = ctx.counters()["launches"]
+    ctx.reset_counters()
+    step_dev(params_counted); torch.cuda.synchronize()                  # one identical untimed step with the probe counters on
     cnt = ctx.counters()
-    inbounds_total, samples_total, launches_total, skipped_total = rig.sum_over_ranks([cnt["inbounds"], cnt["samples"], cnt["launches"], cnt["skipped"]])
+    inb1, samp1, launches_total, skip1 = rig.sum_over_ranks([cnt["inbounds"], cnt["samples"], launches_timed, cnt["skipped"]])
+    inbounds_total, samples_total, skipped_total = inb1 * args.steps, samp1 * args.steps, skip1 * args.steps
     value = args.steps * V * H * W * world / (dev_ms * 1e-3)
     parity, extra = {}, {}
 
@@ -155,7 +160,7 @@ def run_config34(args, B):
 
     if rank == 0:
         peak, peak_src = B.measured_peak()
-        per_launch_inb = cnt["inbounds"] / args.steps
+        per_launch_inb = cnt["inbounds"]
         # 1 B distance byte (+ 1/8 B observed bit in carve mode) per in-bounds sample; per view the visibility row + pose
         alg_bytes = per_launch_inb * (1.125 if fusion else 1.0) + V * (vw * 8 + 48)
         hot = float(np.mean(hot_ms)) if hot_ms else dev_ms / args.steps

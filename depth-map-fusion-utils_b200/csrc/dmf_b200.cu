@@ -423,12 +423,17 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     a.found_any = out.found_any; a.min_depth = out.min_depth;
     a.first_key = first_key; a.ray_key = ray_key; a.ray_occ = ray_occ;
     a.first_view = c->d_first_view.as<int>(); a.good_bits = c->d_good_bits.as<unsigned>(); a.view_mark = c->d_view_mark.as<int>();
-    a.counters = c->d_counters.as<u64>();
+    a.counters = (p->flags & DMF_FWD_NO_COUNTERS) ? nullptr : c->d_counters.as<u64>();
     a.observed = carve ? c->d_observed.as<unsigned>() : nullptr;
     a.dcx = c->d_dcx.as<float>(); a.dcy = c->d_dcy.as<float>(); a.clearance = c->d_clearance.as<float>();
     a.dcx_max = c->dcx_max; a.dcy_max = c->dcy_max;
-    DMF_TRY(c->d_kstart.reserve((size_t)n_views * 8));
+    DMF_TRY(c->d_kstart.reserve((size_t)n_views * 8 + 64 + (size_t)n_views * 64));
     a.kstart = c->d_kstart.as<int>(); a.veps = c->d_kstart.as<float>() + n_views;
+    a.viewrec = (float4*)(((uintptr_t)(c->d_kstart.as<char>() + (size_t)n_views * 8) + 63) & ~(uintptr_t)63);       // 64-byte records behind the two arrays
+    a.z0m = (float)pl.z0 * 0.001f; a.zdm = (float)p->zdelta * 0.001f; a.Sf = (float)c->S;
+    a.pnyz = (unsigned)c->vol.pdim[1] * (unsigned)c->vol.pdim[2];
+    a.bias = 0x4B400000u * (a.pnyz + (unsigned)c->vol.pdim[2] + 1u);
+    a.last = a.pnyz * (unsigned)c->vol.pdim[0] - 1u;
     const bool skip = !(p->flags & DMF_FWD_NO_SKIP);
     const bool byte_skip = skip && pl.grid_format == DMF_GRID_BYTE;
     const bool two_probe = (p->flags & DMF_FWD_TWO_PROBE) != 0;

@@ -429,7 +429,7 @@ int sweep_run(dmf_comm* g, const SweepSpec& spec, const float* host_poses, const
         DMF_TRY(ensure_tables(mm.ctx, pl.z0, spec.fwd->zdelta, pl.cstride, pl.rstride, mm.ctx->stream));
         if (pl.grid_format == DMF_GRID_BYTE) DMF_TRY(ensure_bytes(mm.ctx, mm.ctx->stream));
         if (spec.fwd->flags & DMF_FWD_CARVE) DMF_TRY(ensure_observed(mm.ctx, mm.ctx->stream));
-        DMF_TRY(mm.ctx->d_kstart.reserve((size_t)(my_view_count(n_views, 0, g->world) + 1) * 8));
+        DMF_TRY(mm.ctx->d_kstart.reserve((size_t)(my_view_count(n_views, 0, g->world) + 1) * 72 + 64));
     }
     else for (auto& mm : g->m) { DMF_CUDA(cudaSetDevice(mm.ctx->device)); DMF_TRY(mm.ctx->d_inv_poses.reserve((size_t)(my_view_count(n_views, 0, g->world) + 1) * 48)); }
     const size_t rw = g->last_row_words, vw = g->last_vis_words;

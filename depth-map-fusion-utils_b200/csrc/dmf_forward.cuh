@@ -27,6 +27,12 @@ struct FwdArgs {
     float dcx_max, dcy_max;            // max |dcx|, |dcy| (for the per-view error bound)
     const int* __restrict__ kstart;    // [n_views] probes 0..kstart-1 of EVERY ray of the view are provably in-bounds misses (k_view_start); -1 = view must not skip
     float* veps;                       // [n_views] the view's bound on |reference sample - line point| in voxels (k_view_start)
+    // k_forward_line reads everything it needs per view from ONE 64-byte record (k_view_start writes it): rows 0..2 = the pose,
+    // row 3 = {e_safe = veps + 2^-10, kstart as int bits, 0, 0}: four 16-byte loads from L1 instead of a shared-memory copy + barrier
+    float4* viewrec;                   // [n_views][4]
+    // loop constants the host folds once (the kernel runs at 32 registers and would otherwise re-derive them from the constant bank per probe)
+    float z0m, zdm, Sf;                // z0 * 0.001, zdelta * 0.001, (float)S
+    unsigned pnyz, bias, last;         // pdim_y * pdim_z;  0x4B400000 * (pnyz + pdim_z + 1) (the three shifter offsets, folded);  n_cells - 1
     // outputs (may be null)
     int* depth;                        // [n_views][H][W]
     unsigned short* depth16;           // [n_views][H][W]  same, 0xFFFF = none
@@ -91,12 +97,14 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
 #ifdef DMF_CHECKED
         if (ri * a.rstride >= a.H || ci * a.cstride >= a.W) { atomicAdd(counter_slot(a.counters) + 10, 1ull); pix = 0; }
 #endif
-        if (a.depth) a.depth[pix] = hit ? z_depth : -1;
-        if (a.depth16) a.depth16[pix] = hit ? (unsigned short)z_depth : (unsigned short)0xFFFFu;
-        if (a.hit_voxel) a.hit_voxel[pix] = hit ? voxel_id(hx, hy, hz) : ~0ull;
+        // streaming stores (evict-first): the per-pixel outputs are never read back by the march and must not push the distance
+        // bytes out of the L2 (135 MB of bytes against 126 MB of L2: every output line kept is a grid line lost)
+        if (a.depth) __stcs(a.depth + pix, hit ? z_depth : -1);
+        if (a.depth16) __stcs(a.depth16 + pix, hit ? (unsigned short)z_depth : (unsigned short)0xFFFFu);
+        if (a.hit_voxel) __stcs(a.hit_voxel + pix, hit ? voxel_id(hx, hy, hz) : ~0ull);
         if (a.points) {
             float* const pp = a.points + 3ull * pix;
-            pp[0] = hit ? hpx : 0.f; pp[1] = hit ? hpy : 0.f; pp[2] = hit ? hpz : 0.f;
+            __stcs(pp, hit ? hpx : 0.f); __stcs(pp + 1, hit ? hpy : 0.f); __stcs(pp + 2, hit ? hpz : 0.f);
         }
     }
     unsigned ties = 0;
@@ -148,26 +156,21 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
         }
     }
 
-    // ---- counters: warp reduce -> shared; the LAST warp of the block to get here flushes them with a few global atomics.
+    // ---- counters.  Instrumentation the reference does not have: a.counters == null (DMF_FWD_NO_COUNTERS) compiles to one
+    // uniform branch.  Otherwise: warp reduce (REDUX), then lane j adds counter j -- ONE vector RED over the few non-zero lanes
+    // into one 128-byte line of the 256 counter replicas (round 1 issued up to seven scalar atomics from lane 0, each with its
+    // own test and address: ~100 of the ~900 warp-instructions of a ray-warp of k_forward_line).
     // No block barrier: warps whose rays ended early must not sit on a barrier waiting for the longest ray of the block.
-    const unsigned c0 = __reduce_add_sync(0xffffffffu, n_samples), c1 = __reduce_add_sync(0xffffffffu, n_inb);
-    const unsigned c2 = __reduce_add_sync(0xffffffffu, hit ? 1u : 0u), c9 = __reduce_add_sync(0xffffffffu, n_skip);
-    const unsigned c358 = __reduce_add_sync(0xffffffffu, n_exact | ties | n_f64);      // almost always 0: reduce individually only then
-    unsigned c3 = 0, c5 = 0, c8 = 0;
-    if (c358) { c3 = __reduce_add_sync(0xffffffffu, n_exact); c5 = __reduce_add_sync(0xffffffffu, ties); c8 = __reduce_add_sync(0xffffffffu, n_f64); }
-#ifndef DMF_NO_COUNTERS
-    if (lane == 0) {
-        // one warp, a handful of result-less atomics (RED) into one of the 256 counter replicas: nothing to wait for
-        u64* const gcnt = counter_slot(a.counters);
-        if (c0) atomicAdd(gcnt + 0, (unsigned long long)c0);
-        if (c1) atomicAdd(gcnt + 1, (unsigned long long)c1);
-        if (c2) atomicAdd(gcnt + 2, (unsigned long long)c2);
-        if (c9) atomicAdd(gcnt + 9, (unsigned long long)c9);
-        if (c3) atomicAdd(gcnt + 3, (unsigned long long)c3);
-        if (c5) atomicAdd(gcnt + 5, (unsigned long long)c5);
-        if (c8) atomicAdd(gcnt + 8, (unsigned long long)c8);
+    if (a.counters) {
+        const unsigned c0 = __reduce_add_sync(0xffffffffu, n_samples), c1 = __reduce_add_sync(0xffffffffu, n_inb);
+        const unsigned c2 = __reduce_add_sync(0xffffffffu, hit ? 1u : 0u), c9 = __reduce_add_sync(0xffffffffu, n_skip);
+        const unsigned c358 = __reduce_add_sync(0xffffffffu, n_exact | ties | n_f64);      // almost always 0: reduce individually only then
+        unsigned c3 = 0, c5 = 0, c8 = 0;
+        if (c358) { c3 = __reduce_add_sync(0xffffffffu, n_exact); c5 = __reduce_add_sync(0xffffffffu, ties); c8 = __reduce_add_sync(0xffffffffu, n_f64); }
+        unsigned mine = lane == 0 ? c0 : (lane == 1 ? c1 : (lane == 2 ? c2 : (lane == 9 ? c9 : 0u)));
+        if (c358) mine = lane == 3 ? c3 : (lane == 5 ? c5 : (lane == 8 ? c8 : mine));
+        if (mine) atomicAdd(a.counters + ((((unsigned)view * 37u + (unsigned)ri * 5u + (unsigned)(ci >> 3)) & (DMF_COUNTER_SLOTS - 1u)) * DMF_COUNTER_STRIDE + (unsigned)lane), (unsigned long long)mine);
     }
-#endif
     (void)s_cnt;
 }
 
@@ -487,8 +490,14 @@ __global__ void k_view_start(const FwdArgs a, int n_views, int* __restrict__ kst
         }
     }
     // -1: the view's error bound is too large (or the pose is not finite): k_forward_line must evaluate every sample exactly
-    kstart[view] = (emax <= 0.1f && v.bytes != nullptr) ? max(k0, 0) : -1;
+    const int ks = (emax <= 0.1f && v.bytes != nullptr) ? max(k0, 0) : -1;
+    kstart[view] = ks;
     if (a.veps) a.veps[view] = emax;
+    if (a.viewrec) {
+        float4* r = a.viewrec + 4 * (size_t)view;
+        r[0] = make_float4(m[0][0], m[0][1], m[0][2], m[0][3]); r[1] = make_float4(m[1][0], m[1][1], m[1][2], m[1][3]); r[2] = make_float4(m[2][0], m[2][1], m[2][2], m[2][3]);
+        r[3] = make_float4(emax + 0.0009765625f, __int_as_float(ks), 0.f, 0.f);          // eps_q of the view + 2^-10 voxel of slack
+    }
 }
 
 // ---- K1 on distance bytes: k_forward_dist ---------------------------------------------------------------------
@@ -668,9 +677,11 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
 constexpr int LINE_MIN_BLOCKS = 16;
 constexpr float LINE_EXACT_FLAG = 1048576.0f;      // 2^20, far above any sample index or jump (<= 254 * 1000 + 1)
 
-__device__ __forceinline__ float4 lds_f4_volatile(unsigned smem_addr) {
+// a 16-byte read of the per-view record at the point of use (volatile: the compiler must not keep the 12 pose floats live through the
+// loops -- the kernel runs at 32 registers); the line sits in L1 and every lane reads the same address
+__device__ __forceinline__ float4 ldg_f4_volatile(const float4* p) {
     float4 r;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(smem_addr));
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -694,11 +705,11 @@ __device__ __forceinline__ void observe_voxel(unsigned* __restrict__ obs, unsign
 
 // sample k of pixel (ci, ri) evaluated the reference's way (as k_forward does); marks its voxel if it passes validPoints
 template <bool EXACT>
-__device__ __forceinline__ void carve_exact_sample(const FwdArgs& a, unsigned sp, int ci, int ri, int k) {
+__device__ __forceinline__ void carve_exact_sample(const FwdArgs& a, const float4* sp, int ci, int ri, int k) {
     const VolDev& v = a.vol;
     const float xf = __ldg(a.xtab + ((unsigned)k * (unsigned)a.Wc + (unsigned)ci)), yf = __ldg(a.ytab + ((unsigned)k * (unsigned)a.Hc + (unsigned)ri));
     const float zf = __ldg(a.ztab + k);
-    const float4 r0 = lds_f4_volatile(sp), r1 = lds_f4_volatile(sp + 16), r2 = lds_f4_volatile(sp + 32);
+    const float4 r0 = ldg_f4_volatile(sp), r1 = ldg_f4_volatile(sp + 1), r2 = ldg_f4_volatile(sp + 2);
     const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, xf), __fmul_rn(r0.y, yf)), __fmul_rn(r0.z, zf)), r0.w);
     const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, xf), __fmul_rn(r1.y, yf)), __fmul_rn(r1.z, zf)), r1.w);
     const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, xf), __fmul_rn(r2.y, yf)), __fmul_rn(r2.z, zf)), r2.w);
@@ -744,7 +755,7 @@ constexpr int CARVE_MLP = DMF_CARVE_MLP;          // samples whose observed-word
 constexpr int CARVE_MIN_BLOCKS = DMF_CARVE_MIN_BLOCKS;
 
 template <bool EXACT>
-__device__ __forceinline__ void carve_on_line(const FwdArgs& a, unsigned sp, int ci, int ri, int k_first, int k_last, int kin, int kout,
+__device__ __forceinline__ void carve_on_line(const FwdArgs& a, const float4* sp, int ci, int ri, int k_first, int k_last, int kin, int kout,
                                               float qa0, float qa1, float qa2, float qb0, float qb1, float qb2, float esafe) {
     const VolDev& v = a.vol;
     const int b0 = max(kin, k_first), b1 = min(kout, k_last);
@@ -850,7 +861,7 @@ __device__ __forceinline__ void carve_on_line(const FwdArgs& a, unsigned sp, int
 // (Branching on "a face test failed" per group does NOT pay: 1.2 % of the samples fail, i.e. some lane of nearly every warp --
 // measured 10.3 ms against 9.5 ms.  The failures stay deferred to the end of the chunk as in carve_on_line.)
 template <bool EXACT>
-__device__ __forceinline__ void carve_on_line_sign(const FwdArgs& a, unsigned sp, int ci, int ri, int k_first, int k_last, int kin, int kout,
+__device__ __forceinline__ void carve_on_line_sign(const FwdArgs& a, const float4* sp, int ci, int ri, int k_first, int k_last, int kin, int kout,
                                                    float qa0, float qa1, float qa2, float qb0, float qb1, float qb2, float esafe) {
     const VolDev& v = a.vol;
     const int b0 = max(kin, k_first), b1 = min(kout, k_last);
@@ -936,44 +947,43 @@ __device__ __forceinline__ void carve_on_line_sign(const FwdArgs& a, unsigned sp
 
 template <int MODE, bool EXACT, bool CARVE>
 __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_MIN_BLOCKS) k_forward_line(const FwdArgs a) {
-    __shared__ __align__(16) float s_pose[12];
-    __shared__ float s_adv[256];
-    __shared__ int s_qbmax;
-    __shared__ float s_esafe;
+    // No shared memory, no barrier: everything a block needs per view comes from the view's 64-byte record (k_view_start), read
+    // with four 16-byte loads that hit L1; "samples advanced after a probe with byte d" is computed per probe from the RAY's own
+    // slope (5 FMA-pipe instructions) instead of a per-block 256-entry table (round 1: table build + two barriers + a shared
+    // atomicMax per ray, and an LDS in the dependent chain of every probe).
     const int view = blockIdx.z + a.view0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int ci = blockIdx.x * SKIP_TILE_W + (warp & 1) * 8 + (lane & 7);
     int ri = blockIdx.y * SKIP_TILE_H + (warp >> 1) * 4 + (lane >> 3);
     const bool active = ci < a.Wc && ri < a.Hc;
     if (!active) { ci = 0; ri = 0; }
-    if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldg(a.poses + 12u * (unsigned)view + threadIdx.x);
-    if (threadIdx.x == 32) { s_qbmax = 0; s_esafe = __ldg(a.veps + view) + 0.0009765625f; }   // eps_q of the view + 2^-10 voxel of slack
 #ifdef DMF_LINE_STATS
     const long long t_begin = clock64();
     long long t_line = 0, t_exact = 0;
 #endif
-    __syncthreads();
-    const unsigned sp = (unsigned)__cvta_generic_to_shared(s_pose);
+    const float4* sp = a.viewrec + 4u * (unsigned)view;
     const VolDev& v = a.vol;
     const float kM = 12582912.0f;
     const int S = a.S;
 
     // ---- per ray: the line and the sample intervals ----
     float qa0, qa1, qa2, qb0, qb1, qb2;
+    float rq, c1;                                     // samples advanced after a probe with byte d >= 2: floor(d * rq + c1)
     int k = 0, kin = 1, kout = 0, s_end = S;
     int k_slab = 0;                                   // CARVE: first sample that can be in bounds (before the view-wide k0 skip)
     unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
-    const int ks = __ldg(a.kstart + view);            // -1: no skipping for this view; else leading probes no ray can hit
     {
-        const float4 r0 = lds_f4_volatile(sp), r1 = lds_f4_volatile(sp + 16), r2 = lds_f4_volatile(sp + 32);
+        const float4 r0 = ldg_f4_volatile(sp), r1 = ldg_f4_volatile(sp + 1), r2 = ldg_f4_volatile(sp + 2), r3 = ldg_f4_volatile(sp + 3);
+        const int ks = __float_as_int(r3.y);          // -1: no skipping for this view; else leading probes no ray can hit
         const float dcx = __ldg(a.dcx + ci), dcy = __ldg(a.dcy + ri);
         const float g0 = fmaf(r0.x, dcx, fmaf(r0.y, dcy, r0.z)), g1 = fmaf(r1.x, dcx, fmaf(r1.y, dcy, r1.z)), g2 = fmaf(r2.x, dcx, fmaf(r2.y, dcy, r2.z));
-        const float z0m = (float)a.z0 * 0.001f, zdm = (float)a.zdelta * 0.001f;
+        const float z0m = a.z0m, zdm = a.zdm;
         qa0 = fmaf(fmaf(z0m, g0, r0.w), v.inv32[0], v.c32[0]); qa1 = fmaf(fmaf(z0m, g1, r1.w), v.inv32[1], v.c32[1]); qa2 = fmaf(fmaf(z0m, g2, r2.w), v.inv32[2], v.c32[2]);
         qb0 = zdm * g0 * v.inv32[0]; qb1 = zdm * g1 * v.inv32[1]; qb2 = zdm * g2 * v.inv32[2];
         const float qbmax = fmaxf(fabsf(qb0), fmaxf(fabsf(qb1), fabsf(qb2)));
+        rq = rcp_approx(fmaxf(qbmax, 1e-3f)) * 0.999999f;                           // <= 1000; rounded down: never over-skips
+        c1 = fmaf(-1.25f, rq, 1.0f);
         if (ks >= 0) {
-            atomicMax(&s_qbmax, __float_as_int(qbmax));                            // non-negative floats order like their bit patterns
             // real-valued k intervals: [ti0, ti1] line >= 0.25 voxel inside on every axis; [to0, to1] line < 0.25 voxel outside.
             // Per axis the outer interval is the inner one widened by 0.5 voxel = 0.5 * |1/qb| samples on each side.  An axis the
             // ray is parallel to gets a huge finite "reciprocal": its interval becomes everything or nothing, as it should.
@@ -988,7 +998,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
                 to0 = fmaxf(to0, lo - w); to1 = fminf(to1, hi + w);
             }
             // the t's carry a few ulps of relative error: one sample of guard on each end (|t| that matter are < 2^20)
-            const float Sf = (float)S;
+            const float Sf = a.Sf;
             if (!(to0 <= to1)) { k = S; if (CARVE) k_slab = S; }                     // never inside: every sample fails validPoints
             else {
                 k = (int)fminf(fmaxf(floorf(to0) - 1.0f, 0.0f), Sf);
@@ -1005,18 +1015,6 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
         }
     }
     if (!active) { k = s_end = S; n_inb = n_skip = 0u; }      // (lanes outside a ragged lattice must not count the view-wide k0 either)
-    __syncthreads();
-    {
-        // s_adv[d] = 1 + number of samples skipped after a line probe with byte d, at the block's largest |QB|
-        const float rq = rcp_approx(fmaxf(__int_as_float(s_qbmax), 1e-3f)) * 0.999999f;     // <= 1000
-        const float c1 = fmaf(-1.25f, rq, 1.0f);
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int d = threadIdx.x + j * SKIP_THREADS;
-            s_adv[d] = d < 2 ? LINE_EXACT_FLAG : __fadd_rd(fmaf((float)d, rq, c1), kM) - kM;
-        }
-    }
-    __syncthreads();
     // opaque register copies: otherwise the compiler re-derives the pixel from %tid / %ctaid on every exact evaluation
     asm volatile("" : "+r"(ci), "+r"(ri));
 
@@ -1024,9 +1022,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
     float hpx = 0.f, hpy = 0.f, hpz = 0.f;
     const unsigned char* __restrict__ gbytes = v.bytes;
     const unsigned pny = (unsigned)v.pdim[1], pnz = (unsigned)v.pdim[2];
-    const unsigned pnyz = pny * pnz;
-    const unsigned bias = 0x4B400000u * (pnyz + pnz + 1u);                          // the three "- 0x4B400000" of the shifter, folded
-    const unsigned last = pnyz * (unsigned)v.pdim[0] - 1u;
+    const unsigned pnyz = a.pnyz, bias = a.bias, last = a.last;                      // folded on the host (FwdArgs)
     unsigned iter = 0;
     bool stop = false;
     while (k < s_end && !stop) {
@@ -1055,14 +1051,15 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
 #ifdef DMF_LINE_STATS
                 n_f64++;                                   // diagnostic build: F64_PATH counts line probes, EXACT_DIV exact ones
 #endif
-                float adv = s_adv[d];                      // this probe + the skipped ones; 2^20 when the probe must be evaluated exactly
+                // this probe + the skipped ones: floor((d - 1.25) / max|QB|) + 1 for d >= 2; 2^20 when the probe must be evaluated exactly
+                float adv = d >= 2u ? __fadd_rd(fmaf(__int_as_float(0x4B000000 | (int)d) - 8388608.0f, rq, c1), kM) - kM : LINE_EXACT_FLAG;
                 if (d == 1u) {
                     // Next to an occupied voxel or in the boundary layer, but this voxel itself is empty.  If the line point is
                     // at least e_safe (> eps_q) away from every face of its voxel, the reference's sample is in the same voxel:
                     // an in-bounds miss (the line is >= 0.25 voxel inside the volume here).  Otherwise evaluate exactly.
                     const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
                     const float f0 = q0 - (__fadd_rd(q0, kM) - kM), f1 = q1 - (__fadd_rd(q1, kM) - kM), f2 = q2 - (__fadd_rd(q2, kM) - kM);
-                    const float e = s_esafe;
+                    const float e = ldg_f4_volatile(sp + 3).x;     // e_safe = eps_q of the view + 2^-10 voxel of slack
                     if (fminf(f0, fminf(f1, f2)) >= e && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e) adv = 1.0f;
                 }
                 kf += adv;
@@ -1089,7 +1086,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
 #endif
         const float xf = __ldg(a.xtab + ((unsigned)k * (unsigned)a.Wc + (unsigned)ci)), yf = __ldg(a.ytab + ((unsigned)k * (unsigned)a.Hc + (unsigned)ri));
         const float zf = __ldg(a.ztab + k);
-        const float4 r0 = lds_f4_volatile(sp), r1 = lds_f4_volatile(sp + 16), r2 = lds_f4_volatile(sp + 32);
+        const float4 r0 = ldg_f4_volatile(sp), r1 = ldg_f4_volatile(sp + 1), r2 = ldg_f4_volatile(sp + 2);
         const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, xf), __fmul_rn(r0.y, yf)), __fmul_rn(r0.z, zf)), r0.w);
         const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, xf), __fmul_rn(r1.y, yf)), __fmul_rn(r1.z, zf)), r1.w);
         const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, xf), __fmul_rn(r2.y, yf)), __fmul_rn(r2.z, zf)), r2.w);
@@ -1109,14 +1106,14 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
     if (CARVE && MODE != 4 && active) {
         const int k_last = hit_k >= 0 ? hit_k : s_end - 1;                          // samples >= s_end are provably outside the volume
 #if DMF_CARVE_SIGN
-        carve_on_line_sign<EXACT>(a, sp, ci, ri, k_slab, k_last, kin, kout, qa0, qa1, qa2, qb0, qb1, qb2, s_esafe);
+        carve_on_line_sign<EXACT>(a, sp, ci, ri, k_slab, k_last, kin, kout, qa0, qa1, qa2, qb0, qb1, qb2, ldg_f4_volatile(sp + 3).x);
 #else
-        carve_on_line<EXACT>(a, sp, ci, ri, k_slab, k_last, kin, kout, qa0, qa1, qa2, qb0, qb1, qb2, s_esafe);
+        carve_on_line<EXACT>(a, sp, ci, ri, k_slab, k_last, kin, kout, qa0, qa1, qa2, qb0, qb1, qb2, ldg_f4_volatile(sp + 3).x);
 #endif
     }
     const unsigned n_samples = active ? (unsigned)((hit_k >= 0 || stop || (MODE == 4 && k < s_end)) ? min(k, S) : S) : 0u;
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-    if (MODE == 1 || MODE == 2) { t0 = s_pose[3]; t1 = s_pose[7]; t2 = s_pose[11]; }
+    if (MODE == 1 || MODE == 2) { const float* P = a.poses + 12u * (unsigned)view; t0 = __ldg(P + 3); t1 = __ldg(P + 7); t2 = __ldg(P + 11); }
     forward_epilogue<MODE>(a, nullptr, view, ci, ri, active, hit_k, hx, hy, hz, hpx, hpy, hpz, t0, t1, t2, n_samples, n_inb, n_exact, n_f64, n_skip);
     if (MODE != 4 && a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)(unsigned)view * a.vis_stride32), view, gridDim.x * gridDim.y);
 #ifdef DMF_LINE_STATS

@@ -24,7 +24,7 @@ from ._lib import DmfError, ForwardOut, ForwardParams, ReverseOut, check
 
 MODE_POINTS, MODE_GOOD_POINTS, MODE_CLASSIFY, MODE_MARK, MODE_MINIMUM = range(5)
 GRID_BIT, GRID_BYTE, GRID_AUTO = 0, 1, 2
-FWD_NO_SKIP, FWD_TWO_PROBE, FWD_CARVE = 1, 2, 4
+FWD_NO_SKIP, FWD_TWO_PROBE, FWD_CARVE, FWD_NO_COUNTERS = 1, 2, 4, 8
 NO_VOXEL = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 

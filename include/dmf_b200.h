@@ -125,6 +125,10 @@ typedef struct {
  * the samples on the line (exact evaluation only near voxel faces and the volume boundary); DMF_FWD_NO_SKIP or DMF_GRID_BIT
  * select the brute-force march that evaluates every sample the reference's way.  Not available in MINIMUM mode. */
 #define DMF_FWD_CARVE 4
+/* Do not update the DMF_CNT_* probe counters in this call.  They are instrumentation the reference does not have (the parity
+ * tests use them to show that skipping never changes which samples are visited); a production sweep saves the warp reductions
+ * and atomics.  Results are unaffected. */
+#define DMF_FWD_NO_COUNTERS 8
 
 /* Per-view outputs; any pointer may be NULL.  For the *_dev entry point these are device pointers. */
 typedef struct {
