@@ -211,7 +211,8 @@ int comm_free_arenas(dmf_comm* g) {
 int comm_reserve(dmf_comm* g, size_t gather_bytes, size_t stage_bytes) {
     gather_bytes = (gather_bytes + 255) / 256 * 256; stage_bytes = (stage_bytes + 255) / 256 * 256;
     if (g->m[0].arena && gather_bytes <= g->gather_cap && stage_bytes <= g->stage_cap) return 0;
-    const size_t gcap = std::max(gather_bytes + gather_bytes / 4, g->gather_cap), scap = std::max(stage_bytes, g->stage_cap);
+    // (capacities are kept as multiples of 256 so that asking again for what is there never looks like growth)
+    const size_t gcap = std::max((gather_bytes + gather_bytes / 4 + 255) / 256 * 256, g->gather_cap), scap = std::max(stage_bytes, g->stage_cap);
     comm_free_arenas(g);
     g->gather_cap = gcap; g->stage_cap = scap;
     g->seq = 0; g->rseq = 0; g->have_sweep = false;
