@@ -74,8 +74,10 @@ class Comm:
 
     def replicate_volume(self, root: int = 0):
         check(self.lib.dmf_comm_replicate_volume(self.h, root))
-        for c in self.contexts:
-            c._volume_token = None
+        first = self.info()["first_rank"]
+        for i, c in enumerate(self.contexts):
+            if first + i != root:
+                c._volume_token = None                           # this context now holds the root's volume, not what Python uploaded before
 
     def synchronize(self):
         check(self.lib.dmf_comm_synchronize(self.h))

@@ -101,3 +101,30 @@ def test_pose_file_wire_format(dmf, tmp_path):
     open(path, "w").write("1\n1,0,0\n0,1,0,0\n0,0,1,0\n")
     with pytest.raises(ValueError):
         read_camera_locations(path)
+
+
+def test_multi_gpu_entry_points_refuse_without_gpu(dmf):
+    """CPU tier: the group entry points exist, and without a GPU they fail with the library's message (no fallback, no crash)"""
+    lib = dmf.load()
+    if lib.dmf_device_count() > 0:
+        pytest.skip("a GPU is visible; the group is exercised by tests/test_multi_gpu.py and bench.py")
+    h = C.c_void_p()
+    assert lib.dmf_comm_init_all(C.byref(h), 0) != 0 and not h.value
+    assert b"no CPU fallback" in lib.dmf_last_error()
+    assert lib.dmf_comm_init_rank(C.byref(h), None, None, 0, 1) != 0
+    for bad in (lib.dmf_sweep_forward(None, None, None, 0, None), lib.dmf_sweep_reverse(None, 1, None, 0, None), lib.dmf_comm_fuse_observed(None), lib.dmf_comm_fuse_marks(None, 1)):
+        assert bad != 0
+
+
+def test_view_dealing_of_the_group_matches_the_python_sharding():
+    """view g on GPU g mod N (dmf_comm.cuh my_view_count / row0 + j * row_step) is sweep.shard_indices(..., "strided")"""
+    from dmf_b200.sweep import shard_indices
+    for n in (0, 1, 7, 37, 128, 1024):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for rank in range(world):
+                idx = shard_indices(n, rank, world, "strided")
+                assert len(idx) == ((n - rank + world - 1) // world if rank < n else 0)      # my_view_count
+                assert all(g % world == rank for g in idx)
+                seen.extend(idx.tolist())
+            assert sorted(seen) == list(range(n))
