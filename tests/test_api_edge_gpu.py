@@ -187,3 +187,81 @@ def test_gpu_integrated_volume_marches_identically(dmf, ctx):
         res.append((eng.forward_views(gv, poses, dmf.MODE_GOOD_POINTS, sc.zdelta, False, want=("depth", "visibility")), eng.reverse_views(gv, poses, want=("visibility",))))
     assert np.array_equal(res[0][0]["depth"], res[1][0]["depth"]) and np.array_equal(res[0][0]["visibility"], res[1][0]["visibility"])
     assert np.array_equal(res[0][1]["visibility"], res[1][1]["visibility"])
+
+
+def test_round2_api_additions(dmf, ctx):
+    """DMF_GRID_AUTO, DMF_FWD_NO_COUNTERS, the n argument of the marks calls, upload validation, dmf_volume_prepare_ms"""
+    from dmf_b200._lib import ForwardOut, ForwardParams
+    sc, gv = _vol(dmf, ctx, "S128")
+    K = dmf.scenes.REFERENCE_K
+    poses = dmf.scenes.poses_sphere_lookat(1.024, 40)[3::9]
+    res = {}
+    for fmt in (dmf.GRID_BIT, dmf.GRID_BYTE):
+        res[fmt] = dmf.RayTracingEngine(dmf.Camera(K), ctx, fmt).forward_views(gv, poses, dmf.MODE_POINTS, sc.zdelta, False)
+    # AUTO: bit grid on the first call after an upload, distance bytes once they exist / from the second call on -- same results
+    gv._dirty = True                                              # force a fresh upload: no distance bytes yet
+    auto = dmf.RayTracingEngine(dmf.Camera(K), ctx, dmf.GRID_AUTO)
+    for _ in range(3):
+        r = auto.forward_views(gv, poses, dmf.MODE_POINTS, sc.zdelta, False)
+        for key in ("depth", "voxel", "visibility", "found_any"):
+            assert np.array_equal(r[key], res[dmf.GRID_BIT][key]) and np.array_equal(r[key], res[dmf.GRID_BYTE][key]), key
+        assert all(np.array_equal(a, b) for a, b in zip(r["ids"], res[dmf.GRID_BYTE]["ids"]))
+    build_ms, bytes_ms = C.c_float(), C.c_float()
+    assert ctx.lib.dmf_volume_prepare_ms(ctx.h, C.byref(build_ms), C.byref(bytes_ms)) == 0
+    assert 0 < build_ms.value < 50 and 0 < bytes_ms.value < 200, (build_ms.value, bytes_ms.value)   # AUTO has built the bytes by now
+    # NO_COUNTERS: same outputs, counters untouched
+    eng = dmf.RayTracingEngine(dmf.Camera(K), ctx, dmf.GRID_BYTE)
+    eng._prepare(gv)
+    ctx.reset_counters()
+    p = ForwardParams(dmf.MODE_POINTS, sc.zdelta, 0, 1, dmf.GRID_BYTE, dmf.FWD_NO_COUNTERS)
+    depth = np.zeros((len(poses), 480, 640), np.int32)
+    o = ForwardOut(); o.depth_mm = depth.ctypes.data
+    pp = np.ascontiguousarray(poses)
+    assert ctx.lib.dmf_forward(ctx.h, C.byref(p), pp.ctypes.data_as(C.POINTER(C.c_float)), len(pp), C.byref(o)) == 0
+    assert np.array_equal(depth, res[dmf.GRID_BYTE]["depth"])
+    c = ctx.counters()
+    assert c["samples"] == 0 and c["inbounds"] == 0 and c["hits"] == 0
+    # marks: the caller's n must be the uploaded volume's
+    n = len(gv.occupied_cells_)
+    view, good = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.uint8)
+    assert ctx.lib.dmf_download_marks(ctx.h, view.ctypes.data_as(C.POINTER(C.c_int32)), good.ctypes.data_as(C.POINTER(C.c_uint8)), n + 1) != 0
+    assert b"voxels" in ctx.lib.dmf_last_error()
+    assert ctx.lib.dmf_download_marks(ctx.h, view.ctypes.data_as(C.POINTER(C.c_int32)), good.ctypes.data_as(C.POINTER(C.c_uint8)), n) == 0
+    # upload validation: a dim too small for bounds/delta, and a CSR that is not monotone
+    c2 = dmf.Context(0)
+    try:
+        bounds = np.array([0, 1, 0, 1, 0, 1], np.float64); delta = np.full(3, 1 / 64, np.float64)
+        ids = np.array([dmf.VoxelVolume.getHashId(1, 2, 3), dmf.VoxelVolume.getHashId(4, 5, 6)], np.uint64)
+        def up(dim, noff=None, nrm=None):
+            d = np.array(dim, np.int32)
+            return c2.lib.dmf_upload_volume(c2.h, bounds.ctypes.data_as(C.POINTER(C.c_double)), delta.ctypes.data_as(C.POINTER(C.c_double)), d.ctypes.data_as(C.POINTER(C.c_int)),
+                                            ids.ctypes.data_as(C.POINTER(C.c_uint64)), len(ids), None if noff is None else noff.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                            None if nrm is None else nrm.ctypes.data_as(C.POINTER(C.c_float)))
+        assert up([64, 64, 64]) == 0
+        assert up([60, 64, 64]) != 0 and b"inconsistent" in c2.lib.dmf_last_error()
+        assert up([64, 64, 64], np.array([0, 2, 1], np.uint32), np.zeros(6, np.float32)) != 0 and b"monotone" in c2.lib.dmf_last_error()
+        assert up([64, 64, 64], np.array([1, 1, 2], np.uint32), np.zeros(6, np.float32)) != 0
+        assert up([64, 64, 64], np.array([0, 1, 2], np.uint32), np.zeros(6, np.float32)) == 0
+    finally:
+        c2.close()
+
+
+def test_device_integration_equals_host_integration(dmf, ctx):
+    """dmf_volume_from_points_gpu (K0 -> structures built where the ids lie, no host round trip) == dmf_volume_from_points"""
+    sc = dmf.scenes.scene("S128-clutter")
+    K = dmf.scenes.REFERENCE_K
+    poses = dmf.scenes.poses_sphere_lookat(1.024, 40)[5::11]
+    out = []
+    for on_gpu in (False, True):
+        gv = dmf.VoxelVolume(ctx, integrate_on_gpu=on_gpu)
+        gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
+        eng = dmf.RayTracingEngine(dmf.Camera(K), ctx, dmf.GRID_BYTE)
+        r = eng.forward_views(gv, poses, dmf.MODE_GOOD_POINTS, sc.zdelta, False, want=("depth", "visibility", "ids"))
+        rv = eng.reverse_views(gv, poses, fast=True)
+        off, nrm = gv.normals_csr()
+        out.append((gv.occupied_cells_.copy(), off, nrm, r, rv))
+    a, b = out
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for key in ("depth", "visibility", "found_any"):
+        assert np.array_equal(a[3][key], b[3][key])
+    assert all(np.array_equal(x, y) for x, y in zip(a[3]["ids"], b[3]["ids"])) and all(np.array_equal(x, y) for x, y in zip(a[4]["ids"], b[4]["ids"]))
