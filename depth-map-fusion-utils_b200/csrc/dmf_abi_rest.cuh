@@ -136,9 +136,8 @@ int dmf_reverse(dmf_ctx* c, int fast, int viz, const float* poses, int n_views, 
                 k_win_offsets<<<nv, 1024, 0, st>>>(c->d_misc[2].as<unsigned>(), c->d_misc[3].as<unsigned>(), c->d_n_ids.as<int>(), nbb);
                 k_bits_emit<<<dim3(nbb, nv), BITS_TILE, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_misc[3].as<unsigned>(), nbb, c->d_out_occ.as<int>(), (int)c->n_occ);
                 c->launches += 2;
-                k_ids_offsets<<<1, 1024, 0, st>>>(c->d_n_ids.as<int>(), nv, c->d_offsets.as<long long>());
-                k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->d_centroid_hash.as<u64>(), c->d_ids.as<u64>(), (int)c->n_occ, cap_dev);
-                c->launches += 3;
+                k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->d_centroid_hash.as<u64>(), c->d_ids.as<u64>(), (int)c->n_occ, cap_dev, c->d_n_ids.as<int>());
+                c->launches += 2;
                 DMF_CUDA(cudaGetLastError());
                 DMF_CUDA(cudaMemcpyAsync(hs, c->d_offsets.p, off_bytes, cudaMemcpyDeviceToHost, st));
                 DMF_CUDA(cudaMemcpyAsync(hs + off_bytes + found_bytes, c->d_ids.p, first_ids * 8, cudaMemcpyDeviceToHost, st));

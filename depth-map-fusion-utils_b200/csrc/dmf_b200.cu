@@ -834,23 +834,24 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
             const long long cap_dev = (long long)nv * (long long)std::min<size_t>(R, std::max<size_t>(c->n_occ, 1));     // a view cannot return more ids than rays or voxels
             DMF_TRY(c->d_ids.reserve((size_t)std::max<long long>(cap_dev, 1) * 8));
             k_win_count<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[0].as<unsigned>(), (int)R, (int)c->n_occ, nb);
-            k_win_offsets<<<nv, 1024, 0, st>>>(c->d_misc[0].as<unsigned>(), c->d_misc[1].as<unsigned>(), c->d_n_ids.as<int>(), nb);
-            k_win_compact<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[1].as<unsigned>(), c->d_tmp_a.as<unsigned>(), (int)R, (int)c->n_occ, nb);
+            // (offsets of the compaction, of the radix passes and of the id lists are folded into their consumers: a single-view call is
+            // bound by launches and the gaps between them, not by work)
+            k_win_compact<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, nullptr, c->d_tmp_a.as<unsigned>(), (int)R, (int)c->n_occ, nb, c->d_misc[0].as<unsigned>(), c->d_n_ids.as<int>());
             {   // discovery order: stable 2 x 5-bit radix sort of the compacted keys on their z-plane (bits 21..30), multi-block
                 const int nblk = (int)((std::min<size_t>(R, std::max<size_t>(c->n_occ, 1)) + ORD_TILE - 1) / ORD_TILE);    // winners per view <= min(rays, voxels)
                 DMF_TRY(c->d_misc[2].reserve((size_t)nv * 32 * nblk * 4));
                 unsigned* hist = c->d_misc[2].as<unsigned>();
+                const bool fold = nblk <= 512;
                 k_ord_hist<<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, (int)R, nblk, 21);
-                k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk);
-                k_ord_scatter<false><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, c->d_tmp_b.as<unsigned>(), nullptr, nullptr, (int)R, nblk, 21);
+                if (fold) k_ord_scatter<false, true><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, c->d_tmp_b.as<unsigned>(), nullptr, nullptr, (int)R, nblk, 21);
+                else { k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk); k_ord_scatter<false, false><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, c->d_tmp_b.as<unsigned>(), nullptr, nullptr, (int)R, nblk, 21); }
                 k_ord_hist<<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, (int)R, nblk, 26);
-                k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk);
-                k_ord_scatter<true><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, nullptr, ro, c->d_out_occ.as<int>(), (int)R, nblk, 26);
-                c->launches += 5;
+                if (fold) k_ord_scatter<true, true><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, nullptr, ro, c->d_out_occ.as<int>(), (int)R, nblk, 26);
+                else { k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk); k_ord_scatter<true, false><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, nullptr, ro, c->d_out_occ.as<int>(), (int)R, nblk, 26); }
+                c->launches += fold ? 3 : 5;
             }
-            k_ids_offsets<<<1, 1024, 0, st>>>(c->d_n_ids.as<int>(), nv, c->d_offsets.as<long long>());
-            k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->vol.occ_ids, c->d_ids.as<u64>(), (int)R, cap_dev);
-            c->launches += 6;
+            k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->vol.occ_ids, c->d_ids.as<u64>(), (int)R, cap_dev, c->d_n_ids.as<int>());
+            c->launches += 3;
             DMF_CUDA(cudaGetLastError());
             // staging layout: [offsets (nv+1) x 8][found_any nv x 4, padded to 8][min_depth: unused here][first ids]
             const size_t off_bytes = (size_t)(nv + 1) * 8, found_bytes = ((size_t)nv * 4 + 7) / 8 * 8;

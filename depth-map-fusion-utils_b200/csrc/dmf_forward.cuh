@@ -1203,13 +1203,32 @@ __global__ void __launch_bounds__(1024) k_win_offsets(const unsigned* blk_cnt, u
     if (threadIdx.x == 0) n_win[view] = (int)s_carry;
 }
 
+// blk_off == nullptr: every block derives its offset from the raw counts blk_cnt itself (the sum over the blocks before it) and
+// the last block writes the view's total to n_win -- one launch less than k_win_offsets + this (single-view calls)
 __global__ void __launch_bounds__(WIN_THREADS) k_win_compact(const unsigned* ray_key, const int* ray_occ, const unsigned* first_key,
-                                                             const unsigned* blk_off, unsigned* tmp, int R, int n_occ, int nb) {
+                                                             const unsigned* blk_off, unsigned* tmp, int R, int n_occ, int nb,
+                                                             const unsigned* blk_cnt = nullptr, int* n_win = nullptr) {
     __shared__ unsigned s_warp[WIN_THREADS / 32];
+    __shared__ unsigned s_base0;
     const int view = blockIdx.y;
     const unsigned* rk = ray_key + (size_t)view * R; const int* ro = ray_occ + (size_t)view * R; const unsigned* fk = first_key + (size_t)view * n_occ;
     unsigned* out = tmp + (size_t)view * R;
-    unsigned base = blk_off[(size_t)view * nb + blockIdx.x];
+    if (!blk_off) {
+        unsigned bef = 0;
+        for (int b = threadIdx.x; b < (int)blockIdx.x; b += WIN_THREADS) bef += blk_cnt[(size_t)view * nb + b];
+        bef = __reduce_add_sync(0xffffffffu, bef);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = bef;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t = 0;
+            for (int q = 0; q < WIN_THREADS / 32; q++) t += s_warp[q];
+            s_base0 = t;
+            if ((int)blockIdx.x == nb - 1) n_win[view] = (int)(t + blk_cnt[(size_t)view * nb + blockIdx.x]);
+        }
+        __syncthreads();
+    }
+    unsigned base = blk_off ? blk_off[(size_t)view * nb + blockIdx.x] : s_base0;
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int j = 0; j < WIN_ITEMS; j++) {       // rows of WIN_THREADS consecutive lattice entries keep the lattice order
         unsigned key = 0;
@@ -1270,13 +1289,32 @@ __global__ void __launch_bounds__(1024) k_ord_scan(unsigned* __restrict__ hist, 
     }
 }
 // FINAL: instead of the sorted keys write the winners' occupied ordinals (ray_occ of the lattice index in the key's low 21 bits)
-template <bool FINAL>
+// FOLD: hist holds the RAW block histograms and every block derives its own 32 offsets from them (warp d sums digit d's row:
+// all blocks for the digit's total, the blocks before this one for its share) -- for the few hundred blocks of a VGA view this is
+// cheaper than a separate one-block scan kernel and the launch gap around it (single-view calls are bound by launches, not work)
+template <bool FINAL, bool FOLD>
 __global__ void __launch_bounds__(ORD_TILE) k_ord_scatter(const unsigned* __restrict__ keys, const int* __restrict__ n_win, const unsigned* __restrict__ hist,
                                                           unsigned* __restrict__ dst, const int* __restrict__ ray_occ, int* __restrict__ out_occ, int R, int nblk, int shift) {
     __shared__ unsigned s_cnt[32][33];            // [warp][digit] -> exclusive prefix over the warps of this block
+    __shared__ unsigned s_tot[32], s_base[32];
     const int view = blockIdx.y, nw = n_win[view];
     if ((int)(blockIdx.x * ORD_TILE) >= nw) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (FOLD) {
+        const unsigned* row = hist + ((size_t)view * 32 + warp) * nblk;          // warp d <-> digit d
+        unsigned tot = 0, bef = 0;
+        for (int b = lane; b < nblk; b += 32) { const unsigned h = row[b]; tot += h; if (b < (int)blockIdx.x) bef += h; }
+        tot = __reduce_add_sync(0xffffffffu, tot); bef = __reduce_add_sync(0xffffffffu, bef);
+        if (lane == 0) { s_tot[warp] = tot; s_base[warp] = bef; }
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned t = s_tot[lane];
+            unsigned x = t;
+            for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            s_base[lane] += x - t;                                                  // digits before this one + this digit's earlier blocks
+        }
+        __syncthreads();
+    }
     const int i = blockIdx.x * ORD_TILE + threadIdx.x;
     const unsigned key = i < nw ? keys[(size_t)view * R + i] : 0u;
     const unsigned digit = i < nw ? (key >> shift) & 31u : 32u;
@@ -1295,42 +1333,33 @@ __global__ void __launch_bounds__(ORD_TILE) k_ord_scatter(const unsigned* __rest
     }
     __syncthreads();
     if (digit < 32u) {
-        const unsigned pos = hist[((size_t)view * 32 + digit) * nblk + blockIdx.x] + s_cnt[warp][digit] + rank_in_warp;
+        const unsigned pos = (FOLD ? s_base[digit] : hist[((size_t)view * 32 + digit) * nblk + blockIdx.x]) + s_cnt[warp][digit] + rank_in_warp;
         if (FINAL) out_occ[(size_t)view * R + pos] = ray_occ[(size_t)view * R + (key & 0x1FFFFFu)];
         else dst[(size_t)view * R + pos] = key;
     }
 }
 
-// offsets[v] = sum of n[0..v) for the (few) views of a chunk, offsets[n_views] = total: one block, so that the id lists can be
-// laid out and gathered without a round trip to the host
-__global__ void __launch_bounds__(1024) k_ids_offsets(const int* __restrict__ n, int n_views, long long* __restrict__ offsets) {
-    __shared__ long long s_warp[32];
-    __shared__ long long s_carry;
-    if (threadIdx.x == 0) { s_carry = 0; offsets[0] = 0; }
-    __syncthreads();
-    for (int base = 0; base < n_views; base += 1024) {
-        const int i = base + threadIdx.x;
-        const long long val = i < n_views ? (long long)n[i] : 0;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        long long x = val;
-        for (int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) { long long w = s_warp[lane]; for (int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; } s_warp[lane] = w; }
-        __syncthreads();
-        const long long incl = s_carry + (warp ? s_warp[warp - 1] : 0) + x;
-        if (i < n_views) offsets[i + 1] = incl;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = incl;
-        __syncthreads();
-    }
-}
-
-// compact per-view winner lists into one contiguous uint64 id array at the offsets above (entries beyond `cap` are dropped:
+// compact per-view winner lists into one contiguous uint64 id array, view after view (entries beyond `cap` are dropped:
 // the host sees the total in offsets[n_views] and reports the overflow)
-__global__ void k_gather_ids(const int* out_occ, const long long* offsets, const u64* occ_ids, u64* ids, int R, long long cap) {
+// n_ids != nullptr: the offsets are not there yet -- every block sums the counts of the views before its own (a chunk has at most a
+// few thousand views) and block x == 0 of each view writes them for the host (k_ids_offsets folded in: one launch less)
+__global__ void k_gather_ids(const int* out_occ, long long* offsets, const u64* occ_ids, u64* ids, int R, long long cap, const int* n_ids = nullptr) {
     const int view = blockIdx.y;
-    const long long b = offsets[view], n = offsets[view + 1] - b;
+    __shared__ long long s_b;
+    if (n_ids) {
+        long long acc = 0;
+        for (int v = threadIdx.x; v < view; v += blockDim.x) acc += n_ids[v];
+        for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) s_b = 0;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0 && acc) atomicAdd((unsigned long long*)&s_b, (unsigned long long)acc);
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            offsets[view] = s_b;
+            if (view == (int)gridDim.y - 1) offsets[view + 1] = s_b + n_ids[view];
+        }
+    }
+    const long long b = n_ids ? s_b : offsets[view], n = n_ids ? (long long)n_ids[view] : offsets[view + 1] - b;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         if (b + i < cap) ids[b + i] = occ_ids[out_occ[(size_t)view * R + i]];
 }
