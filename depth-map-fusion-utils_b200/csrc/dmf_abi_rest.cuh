@@ -46,7 +46,7 @@ int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_v
     if (vis_stride32) a.vis_stride32 = vis_stride32;
     if (pub) a.pub = *pub;
     a.emit_list = d_emit_list; a.emit_count = d_emit_count; a.emit_cap = emit_cap;
-    DMF_CUDA(cudaEventRecord(c->ev_h0, st));
+    if (!c->capturing) DMF_CUDA(cudaEventRecord(c->ev_h0, st));
     if (fast) {
         if (!c->n_occ) return 0;
         dim3 grid((unsigned)((c->n_occ + 127) / 128), n_views);
@@ -67,8 +67,7 @@ int enqueue_reverse(dmf_ctx* c, int fast, int viz, const float* d_poses, int n_v
         dim3 grid((unsigned)gx, n_views);
         if (c->reverse_format == DMF_GRID_BYTE) k_reverse<false, 1><<<grid, 128, 0, st>>>(a); else k_reverse<false, 0><<<grid, 128, 0, st>>>(a);
     }
-    DMF_CUDA(cudaEventRecord(c->ev_h1, st));
-    c->hot_timed = true;
+    if (!c->capturing) { DMF_CUDA(cudaEventRecord(c->ev_h1, st)); c->hot_timed = true; }
     c->launches++;
     DMF_CUDA(cudaGetLastError());
     return 0;
@@ -117,32 +116,46 @@ int dmf_reverse(dmf_ctx* c, int fast, int viz, const float* poses, int n_views, 
             DMF_TRY(c->d_misc[0].reserve((size_t)nv * emit_cap * 16)); DMF_TRY(c->d_misc[1].reserve((size_t)nv * 4));
             d_emit = c->d_misc[0].as<u64>(); d_emit_count = c->d_misc[1].as<unsigned>();
         }
-        DMF_TRY(enqueue_reverse(c, fast, viz, c->d_poses[0].as<float>(), nv, d_vis, d_unocc, d_found, d_emit, d_emit_count, emit_cap, st));
+        const bool ids_fast = want_ids && fast;
+        if (!ids_fast) DMF_TRY(enqueue_reverse(c, fast, viz, c->d_poses[0].as<float>(), nv, d_vis, d_unocc, d_found, d_emit, d_emit_count, emit_cap, st));
         bool found_delivered = false;
-        if (want_ids && fast) {
+        long long cap_dev = 0; size_t off_bytes = 0, found_bytes = 0, first_ids = 0; char* hs = nullptr;
+        if (ids_fast) {
             // emission order of reverseRayTraceFast == occupied order: expand each view's bitset in ascending order.  Counts ->
             // offsets -> gather stay on the device; one copy of (offsets, found flags, first ids) into pinned staging, one sync.
-            const long long cap_dev = (long long)nv * (long long)std::max<size_t>(c->n_occ, 1);
-            const size_t off_bytes = (size_t)(nv + 1) * 8, found_bytes = ((size_t)nv * 4 + 7) / 8 * 8;
-            const size_t first_ids = (size_t)std::min<long long>(cap_dev, 128 * 1024);
+            cap_dev = (long long)nv * (long long)std::max<size_t>(c->n_occ, 1);
+            off_bytes = (size_t)(nv + 1) * 8; found_bytes = ((size_t)nv * 4 + 7) / 8 * 8;
+            first_ids = (size_t)std::min<long long>(cap_dev, 128 * 1024);
             DMF_TRY(c->stage.reserve(off_bytes + found_bytes + first_ids * 8));
             DMF_TRY(c->d_offsets.reserve((size_t)(nv + 1) * 8)); DMF_TRY(c->d_n_ids.reserve((size_t)nv * 4));
-            char* hs = (char*)c->stage.p;
+            hs = (char*)c->stage.p;
+            const int nbb = (int)(((c->n_occ + 31) / 32 + BITS_TILE - 1) / BITS_TILE);
             if (c->n_occ) {
                 DMF_TRY(c->d_out_occ.reserve((size_t)nv * c->n_occ * 4)); DMF_TRY(c->d_ids.reserve((size_t)cap_dev * 8));
-                const int nbb = (int)(((c->n_occ + 31) / 32 + BITS_TILE - 1) / BITS_TILE);
                 DMF_TRY(c->d_misc[2].reserve((size_t)nv * nbb * 4)); DMF_TRY(c->d_misc[3].reserve(std::max<size_t>((size_t)nv * nbb * 4, 64)));
-                k_bits_count<<<dim3(nbb, nv), BITS_TILE, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_misc[2].as<unsigned>(), nbb);
-                k_win_offsets<<<nv, 1024, 0, st>>>(c->d_misc[2].as<unsigned>(), c->d_misc[3].as<unsigned>(), c->d_n_ids.as<int>(), nbb);
-                k_bits_emit<<<dim3(nbb, nv), BITS_TILE, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_misc[3].as<unsigned>(), nbb, c->d_out_occ.as<int>(), (int)c->n_occ);
-                c->launches += 2;
-                k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->d_centroid_hash.as<u64>(), c->d_ids.as<u64>(), (int)c->n_occ, cap_dev, c->d_n_ids.as<int>());
-                c->launches += 2;
-                DMF_CUDA(cudaGetLastError());
-                DMF_CUDA(cudaMemcpyAsync(hs, c->d_offsets.p, off_bytes, cudaMemcpyDeviceToHost, st));
-                DMF_CUDA(cudaMemcpyAsync(hs + off_bytes + found_bytes, c->d_ids.p, first_ids * 8, cudaMemcpyDeviceToHost, st));
             }
-            DMF_CUDA(cudaMemcpyAsync(hs + off_bytes, d_found, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+            auto enqueue_all = [&]() -> int {
+                DMF_TRY(enqueue_reverse(c, fast, viz, c->d_poses[0].as<float>(), nv, d_vis, d_unocc, d_found, d_emit, d_emit_count, emit_cap, st));
+                if (c->n_occ) {
+                    k_bits_count<<<dim3(nbb, nv), BITS_TILE, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_misc[2].as<unsigned>(), nbb);
+                    k_win_offsets<<<nv, 1024, 0, st>>>(c->d_misc[2].as<unsigned>(), c->d_misc[3].as<unsigned>(), c->d_n_ids.as<int>(), nbb);
+                    k_bits_emit<<<dim3(nbb, nv), BITS_TILE, 0, st>>>(d_vis, (int)(vw * 2), (int)c->n_occ, c->d_misc[3].as<unsigned>(), nbb, c->d_out_occ.as<int>(), (int)c->n_occ);
+                    k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->d_centroid_hash.as<u64>(), c->d_ids.as<u64>(), (int)c->n_occ, cap_dev, c->d_n_ids.as<int>());
+                    c->launches += 4;
+                    DMF_CUDA(cudaGetLastError());
+                    DMF_CUDA(cudaMemcpyAsync(hs, c->d_offsets.p, off_bytes, cudaMemcpyDeviceToHost, st));
+                    DMF_CUDA(cudaMemcpyAsync(hs + off_bytes + found_bytes, c->d_ids.p, first_ids * 8, cudaMemcpyDeviceToHost, st));
+                }
+                DMF_CUDA(cudaMemcpyAsync(hs + off_bytes, d_found, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+                return 0;
+            };
+            if (n_views == 1 && !viz && !(out->visibility && vw) && !(out->unoccluded && vw)) {
+                // the shape of the drop-in's reverseRayTraceFast(volume, T, false): one captured graph from the second identical call on
+                struct { int H, W, fmt, bytes_built; float K[9]; unsigned long long n_occ, epoch; } k;
+                std::memset(&k, 0, sizeof k);
+                k.H = c->H; k.W = c->W; k.fmt = c->reverse_format; k.bytes_built = c->bytes_built ? 1 : 0; std::memcpy(k.K, c->K, sizeof k.K); k.n_occ = c->n_occ; k.epoch = c->volume_epoch;
+                DMF_TRY(run_maybe_graphed(c, c->graph_rev_ids, fnv1a(&k, sizeof k), st, enqueue_all));
+            } else DMF_TRY(enqueue_all());
             DMF_CUDA(cudaStreamSynchronize(st));
             if (!c->n_occ) std::memset(hs, 0, off_bytes);
             const long long* offs = (const long long*)hs;

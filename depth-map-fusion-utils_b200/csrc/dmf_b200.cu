@@ -35,6 +35,60 @@ inline unsigned blocks_for(size_t n, unsigned threads, unsigned cap = 148 * 16) 
     return (unsigned)std::max<size_t>(1, std::min<size_t>(b, cap));
 }
 
+inline unsigned long long fnv1a(const void* data, size_t n, unsigned long long h = 1469598103934665603ull) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+// Run `enqueue` (which only enqueues work on `st`: no allocation, no synchronisation once its buffers are sized) directly, or --
+// from the second call with the same key on -- as a captured CUDA graph.  See CallGraph.
+template <class F>
+int run_maybe_graphed(dmf_ctx* c, CallGraph& g, unsigned long long key, cudaStream_t st, F&& enqueue) {
+    static const bool off = std::getenv("DMF_NO_GRAPH") != nullptr;
+    if (off || g.disabled) return enqueue();
+    const unsigned long long gen = alloc_generation();
+    if (g.exec && g.key == key && g.gen == gen) {
+        DMF_CUDA(cudaEventRecord(c->ev_h0, st));
+        DMF_CUDA(cudaGraphLaunch(g.exec, st));
+        DMF_CUDA(cudaEventRecord(c->ev_h1, st));
+        c->hot_timed = true; c->launches += g.n_kernels;
+        return 0;
+    }
+    if (g.cand_key == key && g.cand_gen == gen) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); g.disabled = true; return enqueue(); }
+        const unsigned long long l0 = c->launches;
+        c->capturing = true;
+        const int rc = enqueue();
+        c->capturing = false;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (rc || e != cudaSuccess || !graph || alloc_generation() != gen) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            g.disabled = rc == 0 && alloc_generation() == gen;       // a capture that fails for no reason of ours: stop trying
+            g.cand_key = 0;
+            c->launches = l0;
+            if (rc) return rc;
+            return enqueue();                                         // nothing was executed by the aborted capture
+        }
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; g.disabled = true; c->launches = l0; return enqueue(); }
+        g.key = key; g.gen = gen; g.n_kernels = (unsigned)(c->launches - l0);
+        c->launches = l0;
+        DMF_CUDA(cudaEventRecord(c->ev_h0, st));
+        DMF_CUDA(cudaGraphLaunch(g.exec, st));
+        DMF_CUDA(cudaEventRecord(c->ev_h1, st));
+        c->hot_timed = true; c->launches += g.n_kernels;
+        return 0;
+    }
+    const int rc = enqueue();
+    g.cand_key = key; g.cand_gen = alloc_generation();                // (this call may have sized buffers: remember the generation after it)
+    return rc;
+}
+
 int fill_u32(dmf_ctx* c, cudaStream_t st, void* p, size_t n, unsigned val) {
     if (!n) return 0;
     k_fill_u32<<<blocks_for(n, 256), 256, 0, st>>>((unsigned*)p, n, val);
@@ -166,7 +220,7 @@ int build_volume_device(dmf_ctx* c, size_t n_occ, size_t n_normals) {
     v.noff = c->d_noff.as<unsigned>(); v.normals = c->d_normals.as<float>(); v.occ_ids = c->d_occ_ids.as<u64>();
     v.bytes = nullptr; v.n_occ = (int)n_occ; v.n_cells = (unsigned)nbits;
     c->n_occ = n_occ; c->n_normals = n_normals;
-    c->bytes_built = false; c->auto_uses = 0;
+    c->bytes_built = false; c->auto_uses = 0; c->volume_epoch++;
     c->n_grid_words = nwords; c->observed_ready = false;     // a new volume starts unobserved
 
     DMF_CUDA(cudaEventRecord(c->ev_p0, st));
@@ -438,7 +492,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     const bool byte_skip = skip && pl.grid_format == DMF_GRID_BYTE;
     const bool two_probe = (p->flags & DMF_FWD_TWO_PROBE) != 0;
     if (sub_views <= 0 || sub_views > n_views) sub_views = n_views;
-    DMF_CUDA(cudaEventRecord(c->ev_h0, st));
+    if (!c->capturing) DMF_CUDA(cudaEventRecord(c->ev_h0, st));
     if (byte_skip) { a.view0 = 0; k_view_start<<<(n_views + 127) / 128, 128, 0, st>>>(a, n_views, const_cast<int*>(a.kstart)); c->launches++; }
     const bool split = sub_views < n_views;
     if (split) { DMF_CUDA(cudaEventRecord(c->ev_fork, st)); DMF_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0)); }
@@ -459,8 +513,7 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
         if (after_sub) DMF_TRY((*after_sub)(v0, nv, ls));
     }
     if (split) { DMF_CUDA(cudaEventRecord(c->ev_join, c->aux_stream)); DMF_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0)); }
-    DMF_CUDA(cudaEventRecord(c->ev_h1, st));
-    c->hot_timed = true;
+    if (!c->capturing) { DMF_CUDA(cudaEventRecord(c->ev_h1, st)); c->hot_timed = true; }
     DMF_CUDA(cudaGetLastError());
     if (p->mode == DMF_MODE_CLASSIFY && c->n_occ && !c->defer_first_view) {
         k_apply_first_view<<<blocks_for(c->n_occ, 256, 1u << 30), 256, 0, st>>>(c->d_view_mark.as<int>(), c->d_first_view.as<int>(), (int)c->n_occ, view_id0);
@@ -550,6 +603,7 @@ void dmf_destroy(dmf_ctx* c) {
                       &c->d_poses[0], &c->d_poses[1], &c->d_inv_poses, &c->d_first_key, &c->d_ray_key, &c->d_ray_occ, &c->d_tmp_a, &c->d_tmp_b,
                       &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters,
                       &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err};
+    c->graph_fwd_ids.drop(); c->graph_rev_ids.drop();
     for (auto* b : bufs) b->release();
     c->stage.release();
     for (int i = 0; i < 2; i++) for (int j = 0; j < 8; j++) c->d_out[i][j].release();
@@ -821,7 +875,9 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
             DMF_TRY(c->d_first_key.reserve(std::max<size_t>((size_t)nv * c->n_occ, 1) * 4)); DMF_TRY(c->d_ray_key.reserve(nv * R * 4)); DMF_TRY(c->d_ray_occ.reserve(nv * R * 4));
             fk = c->d_first_key.as<unsigned>(); rk = c->d_ray_key.as<unsigned>(); ro = c->d_ray_occ.as<int>();
         }
-        DMF_TRY(enqueue_forward(c, p, pl, c->d_poses[b].as<float>(), nv, p->view_id0 + v0, d, fk, rk, ro, st));
+        if (!want_ids) DMF_TRY(enqueue_forward(c, p, pl, c->d_poses[b].as<float>(), nv, p->view_id0 + v0, d, fk, rk, ro, st));
+        // (declared here: used by the host code after the synchronisation below)
+        long long cap_dev = 0; size_t off_bytes = 0, found_bytes = 0, first_ids = 0; char* hs = nullptr;
         if (want_ids) {
             // The id lists leave the device without a host round trip in the middle: counts -> offsets -> gather all on the device,
             // then ONE copy of (offsets, found flags, the first ids) into pinned staging and one synchronisation.  Only a view list
@@ -830,37 +886,51 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
             DMF_TRY(c->d_tmp_a.reserve(nv * R * 4)); DMF_TRY(c->d_tmp_b.reserve(nv * R * 4)); DMF_TRY(c->d_out_occ.reserve(nv * R * 4));
             DMF_TRY(c->d_n_ids.reserve((size_t)nv * 4)); DMF_TRY(c->d_offsets.reserve((size_t)(nv + 1) * 8));
             const int nb = (int)((R + WIN_BLOCK - 1) / WIN_BLOCK);
-            DMF_TRY(c->d_misc[0].reserve((size_t)nv * nb * 4)); DMF_TRY(c->d_misc[1].reserve((size_t)nv * nb * 4));
-            const long long cap_dev = (long long)nv * (long long)std::min<size_t>(R, std::max<size_t>(c->n_occ, 1));     // a view cannot return more ids than rays or voxels
+            DMF_TRY(c->d_misc[0].reserve((size_t)nv * nb * 4));
+            cap_dev = (long long)nv * (long long)std::min<size_t>(R, std::max<size_t>(c->n_occ, 1));     // a view cannot return more ids than rays or voxels
             DMF_TRY(c->d_ids.reserve((size_t)std::max<long long>(cap_dev, 1) * 8));
-            k_win_count<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[0].as<unsigned>(), (int)R, (int)c->n_occ, nb);
-            // (offsets of the compaction, of the radix passes and of the id lists are folded into their consumers: a single-view call is
-            // bound by launches and the gaps between them, not by work)
-            k_win_compact<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, nullptr, c->d_tmp_a.as<unsigned>(), (int)R, (int)c->n_occ, nb, c->d_misc[0].as<unsigned>(), c->d_n_ids.as<int>());
-            {   // discovery order: stable 2 x 5-bit radix sort of the compacted keys on their z-plane (bits 21..30), multi-block
-                const int nblk = (int)((std::min<size_t>(R, std::max<size_t>(c->n_occ, 1)) + ORD_TILE - 1) / ORD_TILE);    // winners per view <= min(rays, voxels)
-                DMF_TRY(c->d_misc[2].reserve((size_t)nv * 32 * nblk * 4));
-                unsigned* hist = c->d_misc[2].as<unsigned>();
-                const bool fold = nblk <= 512;
-                k_ord_hist<<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, (int)R, nblk, 21);
-                if (fold) k_ord_scatter<false, true><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, c->d_tmp_b.as<unsigned>(), nullptr, nullptr, (int)R, nblk, 21);
-                else { k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk); k_ord_scatter<false, false><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, c->d_tmp_b.as<unsigned>(), nullptr, nullptr, (int)R, nblk, 21); }
-                k_ord_hist<<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, (int)R, nblk, 26);
-                if (fold) k_ord_scatter<true, true><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, nullptr, ro, c->d_out_occ.as<int>(), (int)R, nblk, 26);
-                else { k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk); k_ord_scatter<true, false><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, nullptr, ro, c->d_out_occ.as<int>(), (int)R, nblk, 26); }
-                c->launches += fold ? 3 : 5;
-            }
-            k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->vol.occ_ids, c->d_ids.as<u64>(), (int)R, cap_dev, c->d_n_ids.as<int>());
-            c->launches += 3;
-            DMF_CUDA(cudaGetLastError());
-            // staging layout: [offsets (nv+1) x 8][found_any nv x 4, padded to 8][min_depth: unused here][first ids]
-            const size_t off_bytes = (size_t)(nv + 1) * 8, found_bytes = ((size_t)nv * 4 + 7) / 8 * 8;
-            const size_t first_ids = (size_t)std::min<long long>(cap_dev, 128 * 1024);
+            const int nblk = (int)((std::min<size_t>(R, std::max<size_t>(c->n_occ, 1)) + ORD_TILE - 1) / ORD_TILE);    // winners per view <= min(rays, voxels)
+            DMF_TRY(c->d_misc[2].reserve((size_t)nv * 32 * nblk * 4));
+            // staging layout: [offsets (nv+1) x 8][found_any nv x 4, padded to 8][first ids]
+            off_bytes = (size_t)(nv + 1) * 8; found_bytes = ((size_t)nv * 4 + 7) / 8 * 8;
+            first_ids = (size_t)std::min<long long>(cap_dev, 128 * 1024);
             DMF_TRY(c->stage.reserve(off_bytes + found_bytes + first_ids * 8));
-            char* hs = (char*)c->stage.p;
-            DMF_CUDA(cudaMemcpyAsync(hs, c->d_offsets.p, off_bytes, cudaMemcpyDeviceToHost, st));
-            DMF_CUDA(cudaMemcpyAsync(hs + off_bytes, d.found_any, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
-            if (first_ids) DMF_CUDA(cudaMemcpyAsync(hs + off_bytes + found_bytes, c->d_ids.p, first_ids * 8, cudaMemcpyDeviceToHost, st));
+            hs = (char*)c->stage.p;
+            // everything from here to the copies into the staging area only ENQUEUES on st: as one captured graph for single-view calls
+            auto enqueue_all = [&]() -> int {
+                DMF_TRY(enqueue_forward(c, p, pl, c->d_poses[b].as<float>(), nv, p->view_id0 + v0, d, fk, rk, ro, st));
+                k_win_count<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, c->d_misc[0].as<unsigned>(), (int)R, (int)c->n_occ, nb);
+                // (offsets of the compaction, of the radix passes and of the id lists are folded into their consumers: a single-view call
+                // is bound by launches and the gaps between them, not by work)
+                k_win_compact<<<dim3(nb, nv), WIN_THREADS, 0, st>>>(rk, ro, fk, nullptr, c->d_tmp_a.as<unsigned>(), (int)R, (int)c->n_occ, nb, c->d_misc[0].as<unsigned>(), c->d_n_ids.as<int>());
+                {   // discovery order: stable 2 x 5-bit radix sort of the compacted keys on their z-plane (bits 21..30), multi-block
+                    unsigned* hist = c->d_misc[2].as<unsigned>();
+                    const bool fold = nblk <= 512;
+                    k_ord_hist<<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, (int)R, nblk, 21);
+                    if (fold) k_ord_scatter<false, true><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, c->d_tmp_b.as<unsigned>(), nullptr, nullptr, (int)R, nblk, 21);
+                    else { k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk); k_ord_scatter<false, false><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_a.as<unsigned>(), c->d_n_ids.as<int>(), hist, c->d_tmp_b.as<unsigned>(), nullptr, nullptr, (int)R, nblk, 21); }
+                    k_ord_hist<<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, (int)R, nblk, 26);
+                    if (fold) k_ord_scatter<true, true><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, nullptr, ro, c->d_out_occ.as<int>(), (int)R, nblk, 26);
+                    else { k_ord_scan<<<nv, 1024, 0, st>>>(hist, nblk); k_ord_scatter<true, false><<<dim3(nblk, nv), ORD_TILE, 0, st>>>(c->d_tmp_b.as<unsigned>(), c->d_n_ids.as<int>(), hist, nullptr, ro, c->d_out_occ.as<int>(), (int)R, nblk, 26); }
+                    c->launches += fold ? 3 : 5;
+                }
+                k_gather_ids<<<dim3(32, nv), 256, 0, st>>>(c->d_out_occ.as<int>(), c->d_offsets.as<long long>(), c->vol.occ_ids, c->d_ids.as<u64>(), (int)R, cap_dev, c->d_n_ids.as<int>());
+                c->launches += 3;
+                DMF_CUDA(cudaGetLastError());
+                DMF_CUDA(cudaMemcpyAsync(hs, c->d_offsets.p, off_bytes, cudaMemcpyDeviceToHost, st));
+                DMF_CUDA(cudaMemcpyAsync(hs + off_bytes, d.found_any, (size_t)nv * 4, cudaMemcpyDeviceToHost, st));
+                if (first_ids) DMF_CUDA(cudaMemcpyAsync(hs + off_bytes + found_bytes, c->d_ids.p, first_ids * 8, cudaMemcpyDeviceToHost, st));
+                return 0;
+            };
+            const bool per_pixel_or_vis = out->depth_mm || out->depth_u16 || out->points || out->hit_voxel || (out->visibility && vw);
+            if (n_views == 1 && !per_pixel_or_vis) {
+                // the shape of the drop-in's per-view calls: replayed as a captured graph from the second identical call on
+                struct { int mode, zdelta, sparse, flags, fmt, H, W, bytes_built; float K[9]; unsigned long long n_occ, epoch, R; const void* ids_out; } k;
+                std::memset(&k, 0, sizeof k);
+                k.mode = p->mode; k.zdelta = p->zdelta; k.sparse = p->sparse; k.flags = p->flags; k.fmt = pl.grid_format; k.H = c->H; k.W = c->W; k.bytes_built = c->bytes_built ? 1 : 0;
+                std::memcpy(k.K, c->K, sizeof k.K); k.n_occ = c->n_occ; k.epoch = c->volume_epoch; k.R = R;
+                DMF_TRY(run_maybe_graphed(c, c->graph_fwd_ids, fnv1a(&k, sizeof k), st, enqueue_all));
+            } else DMF_TRY(enqueue_all());
             DMF_CUDA(cudaStreamSynchronize(st));
             const long long* offs = (const long long*)hs;
             const long long total = offs[nv];

@@ -25,11 +25,16 @@ inline int fail(const char* fmt, ...) {
 #define DMF_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return dmf::fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define DMF_TRY(call) do { int r_ = (call); if (r_) return r_; } while (0)
 
+// Bumped whenever a device or pinned buffer of the library moves: a captured CUDA graph holds raw pointers, so it is only
+// replayed while this has not changed since its capture.
+inline unsigned long long& alloc_generation() { static unsigned long long g = 1; return g; }
+
 // grow-only device allocation
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return 0;
+        alloc_generation()++;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -37,7 +42,7 @@ struct DevBuf {
         cap = want;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) { cudaFree(p); alloc_generation()++; } p = nullptr; cap = 0; }
     template <class T> T* as() const { return (T*)p; }
 };
 
@@ -46,6 +51,7 @@ struct HostStage {
     void* p = nullptr; size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return 0;
+        alloc_generation()++;
         if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 4 + 4096;
         cudaError_t e = cudaMallocHost(&p, want);
@@ -127,6 +133,17 @@ inline AngleTest bisect_angle_test() {
     return t;
 }
 
+// A single-view call is a dozen small launches: replaying them as one captured CUDA graph removes the gaps between them.
+// A call shape (key) is run directly the first time (it sizes every buffer), captured the second time, replayed afterwards --
+// as long as no buffer of the library has moved (alloc_generation) and the key (mode, camera, volume epoch, ...) is the same.
+struct CallGraph {
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long key = 0, gen = 0, cand_key = 0, cand_gen = 0;
+    unsigned n_kernels = 0;
+    bool disabled = false;
+    void drop() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; key = cand_key = 0; }
+};
+
 struct TableKey {
     float K[9]; int H, W, z0, zdelta, cstride, rstride;
     bool operator==(const TableKey& o) const { return std::memcmp(this, &o, sizeof *this) == 0; }
@@ -171,6 +188,9 @@ struct dmf_ctx {
     dmf::DevBuf d_misc[4];
     dmf::DevBuf d_counters;
     dmf::HostStage stage;                             // pinned staging of the id-list calls
+    dmf::CallGraph graph_fwd_ids, graph_rev_ids;      // captured single-view id-list calls (dmf_forward / dmf_reverse with one pose)
+    bool capturing = false;                           // a stream capture is in progress: no timing-event records inside
+    unsigned long long volume_epoch = 0;              // bumped by every volume (re)build: part of the graph keys
     AngleTest angle{};
     uint64_t launches = 0;
 };
