@@ -47,7 +47,7 @@ template <class F>
 int run_maybe_graphed(dmf_ctx* c, CallGraph& g, unsigned long long key, cudaStream_t st, F&& enqueue) {
     static const bool off = std::getenv("DMF_NO_GRAPH") != nullptr;
     if (off || g.disabled) return enqueue();
-    const unsigned long long gen = alloc_generation();
+    const unsigned long long gen = alloc_generation().load();
     if (g.exec && g.key == key && g.gen == gen) {
         DMF_CUDA(cudaEventRecord(c->ev_h0, st));
         DMF_CUDA(cudaGraphLaunch(g.exec, st));
@@ -64,10 +64,10 @@ int run_maybe_graphed(dmf_ctx* c, CallGraph& g, unsigned long long key, cudaStre
         c->capturing = false;
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(st, &graph);
-        if (rc || e != cudaSuccess || !graph || alloc_generation() != gen) {
+        if (rc || e != cudaSuccess || !graph || alloc_generation().load() != gen) {
             cudaGetLastError();
             if (graph) cudaGraphDestroy(graph);
-            g.disabled = rc == 0 && alloc_generation() == gen;       // a capture that fails for no reason of ours: stop trying
+            g.disabled = rc == 0 && alloc_generation().load() == gen;       // a capture that fails for no reason of ours: stop trying
             g.cand_key = 0;
             c->launches = l0;
             if (rc) return rc;
@@ -85,7 +85,7 @@ int run_maybe_graphed(dmf_ctx* c, CallGraph& g, unsigned long long key, cudaStre
         return 0;
     }
     const int rc = enqueue();
-    g.cand_key = key; g.cand_gen = alloc_generation();                // (this call may have sized buffers: remember the generation after it)
+    g.cand_key = key; g.cand_gen = alloc_generation().load();         // (this call may have sized buffers: remember the generation after it)
     return rc;
 }
 

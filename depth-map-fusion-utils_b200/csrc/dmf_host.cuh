@@ -2,6 +2,7 @@
 // VoxelVolume used by dmf_volume_from_points, and the libm acosf bisection.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -27,7 +28,7 @@ inline int fail(const char* fmt, ...) {
 
 // Bumped whenever a device or pinned buffer of the library moves: a captured CUDA graph holds raw pointers, so it is only
 // replayed while this has not changed since its capture.
-inline unsigned long long& alloc_generation() { static unsigned long long g = 1; return g; }
+inline std::atomic<unsigned long long>& alloc_generation() { static std::atomic<unsigned long long> g{1}; return g; }   // (contexts may live on different host threads)
 
 // grow-only device allocation
 struct DevBuf {
