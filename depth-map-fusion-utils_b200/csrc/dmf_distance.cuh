@@ -1,11 +1,17 @@
 // dmf_distance.cuh -- builds the DMF_GRID_BYTE format: one byte per voxel of the padded index space holding
 //     0            the voxel is occupied
-//     d in 1..255  the voxel is empty and every voxel within Chebyshev (L-inf) index distance d-1 of it is empty AND
-//                  interior (all indices in [1, dim-2]), i.e. d = min(255, distance to the nearest "blocked" voxel),
-//                  blocked = occupied, or on the outermost voxel layer, or outside.  Empty voxels of the outermost layer
-//                  and of the padding plane hold 1.
+//     d in 1..255  the voxel is empty and every voxel of the grid within Chebyshev (L-inf) index distance d-1 of it is empty,
+//                  i.e. d = min(255, distance to the nearest OCCUPIED voxel).  The volume boundary is NOT a source.
 // A probe that lands in a voxel with value d >= 2 therefore proves that every later probe of the same ray whose position
-// differs by at most d-1 voxels (L-inf) is an in-bounds miss (k_forward_line, k_forward_dist, march_collides).
+// differs by at most d-1 voxels (L-inf) is a miss IF it is in bounds.  Who proves "in bounds":
+//   * the line-first marches (k_forward_line, march_collides' line loop) follow the ray only inside the slab interval in which the
+//     line is >= 0.25 voxel inside the volume on every axis, and clamp every jump to the end of that interval -- the ray's
+//     DIRECTION is known, so only the face it leaves through can end a jump, and the slab test already knows where that is;
+//   * everything else (k_view_start, k_forward_dist, k_forward_skip on bytes, the exact-step skips of march_collides and
+//     k_segments_collide) folds the voxel's distance to the outermost voxel layer in with byte_with_border() (dmf_device.cuh).
+// (Round 1 and the first half of round 2 made the outermost layer a source of the transform itself.  That cost the line marches
+// a geometric ramp of ~log2(distance) probes wherever a ray enters, leaves or starts near the boundary of the volume -- for a
+// camera 25 voxels inside the volume looking at an object 150 voxels away: 25, 50, 100 ... instead of one jump.)
 // The same passes build the macro-cell clearance field of the bit-grid march (k_forward_skip).
 //
 // Chebyshev distance is separable in the max-min sense:
@@ -13,22 +19,18 @@
 // so three 1-D passes are exact.  Pass z is a plain nearest-source distance along a line (one warp per line, ballots);
 // passes y and x evaluate  g(c) = min_i max(|c - i|, f(i))  along a line in O(n): one thread per line, two sweeps, each with
 // a monotonic queue (see dt_sweep).  Round 1 used a per-voxel window scan, O(n * distance): 50 ms at 512^3; this is ~2 ms.
-// The outermost voxel layer and the padding plane are sources of the transform itself (distance 0, re-encoded as 1 at the
-// end), so no separate "distance to the boundary" fold is needed and every search is bounded by the boundary distance.
 #pragma once
 #include "dmf_device.cuh"
 
 // ---- pass z on the voxel grid: out = min(255, distance along z to the nearest source of the same (x,y) line) ------------
-// source = occupied, or outermost layer / padding plane (x, y or z in {0, dim-1, dim}).  One warp per line, 32 voxels per
-// step: ballot of the sources, nearest set bit to the left by CLZ; then the same from the right end, folded with min.
+// source = occupied.  One warp per line, 32 voxels per step: ballot of the sources, nearest set bit to the left by CLZ; then
+// the same from the right end, folded with min.
 __global__ void __launch_bounds__(256) k_dt_z(const VolDev v, unsigned char* __restrict__ out) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned nlines = (unsigned)v.pdim[0] * (unsigned)v.pdim[1];
-    const unsigned nz = (unsigned)v.pdim[2], ny = (unsigned)v.pdim[1];
+    const unsigned nz = (unsigned)v.pdim[2];
     const unsigned nchunk = (nz + 31) / 32;
     for (unsigned line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); line < nlines; line += gridDim.x * (blockDim.x >> 5)) {
-        const unsigned x = line / ny, y = line % ny;
-        const bool line_blocked = x == 0u || (int)x >= v.dim[0] - 1 || y == 0u || (int)y >= v.dim[1] - 1;
         const size_t base = (size_t)line * nz;
         unsigned carry = 255u;                                    // distance from the voxel just left of the chunk to its nearest source
         for (unsigned ch = 0; ch < nchunk; ch++) {
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(256) k_dt_z(const VolDev v, unsigned char* __r
             bool src = false;
             if (z < nz) {
                 const size_t i = base + z;
-                src = line_blocked || z == 0u || (int)z >= v.dim[2] - 1 || (((__ldg(v.bits + (i >> 5)) >> (i & 31)) & 1u) != 0u);
+                src = ((__ldg(v.bits + (i >> 5)) >> (i & 31)) & 1u) != 0u;
             }
             const unsigned m = __ballot_sync(0xffffffffu, src);
             const unsigned ml = m & (0xffffffffu >> (31 - lane)); // sources at or left of this lane
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(256) k_dt_z(const VolDev v, unsigned char* __r
 //   * g(c) = min(c - holder, f of the oldest queued entry).
 // Every element is pushed and popped once: O(n) per line.  f < 256 strictly increasing bounds the queue by 256 entries, so
 // it is a 256-entry ring indexed by unsigned chars.  VIRTUAL_BORDER adds a source with f = 0 at index -1 (cells outside
-// the grid are blocked; the macro-cell field needs this, the voxel grid has its blocked layer inside the grid).
+// the grid are blocked; the macro-cell field needs this, the voxel grid has no boundary sources at all).
 // REVERSE walks c = n-1 .. 0 (sources at i >= c) and folds its result into what the forward sweep stored.
 template <bool REVERSE, bool VIRTUAL_BORDER, bool FINAL, class Encode>
 __device__ __forceinline__ void dt_sweep(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, size_t base, size_t stride, int n, Encode enc) {
@@ -107,14 +109,6 @@ __device__ __forceinline__ void dt_sweep(const unsigned char* __restrict__ in, u
 }
 
 struct EncodeNone { __device__ __forceinline__ unsigned operator()(size_t, unsigned g) const { return g; } };
-// final encoding of the voxel grid: sources that are not occupied voxels (boundary layer, padding plane) hold 1
-struct EncodeVoxel {
-    const unsigned* __restrict__ bits;
-    __device__ __forceinline__ unsigned operator()(size_t i, unsigned g) const {
-        if (g != 0u) return g;
-        return ((__ldg(bits + (i >> 5)) >> (i & 31)) & 1u) ? 0u : 1u;
-    }
-};
 
 // passes y and x over a dense [n0][n1][n2] byte array (n2 fastest): AXIS 1 walks n1, AXIS 0 walks n0; one thread per line,
 // neighbouring threads own neighbouring n2 positions, so every step of a warp reads and writes 32 consecutive bytes.

@@ -431,9 +431,9 @@ __global__ void __launch_bounds__(SKIP_THREADS, 8) k_forward_skip(const FwdArgs 
                 }
                 k++; kf += 1.0f;
             } else {
-                // distance bytes (dmf_distance.cuh): 0 = occupied; d >= 2 => every voxel within d-1 (L-inf) of this one is an
-                // empty interior voxel, so the samples whose line offset stays within d - 1.25 voxels are in-bounds misses
-                const unsigned d = __ldg(gbytes + idx);
+                // distance bytes (dmf_distance.cuh) with the border distance folded in: 0 = occupied; d >= 2 => every voxel within
+                // d-1 (L-inf) of this one is an empty interior voxel, so the samples whose line offset stays within d - 1.25 voxels are in-bounds misses
+                const unsigned d = byte_with_border(v, __ldg(gbytes + idx), ix, iy, iz);
                 if (d == 0u) {
                     hit_k = k; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz;
                     k++;
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, 8) k_forward_skip(const FwdArgs 
 
 // Per view: how many leading probes every ray may skip.  All rays leave from the camera centre t; probe k of any ray is
 // within z_k * G voxels (L-inf) of it, G = max_i (|m_i0|*max|dcx| + |m_i1|*max|dcy| + |m_i2|) / delta_i.  If the camera
-// sits in a voxel with distance byte d, everything within d-1 voxels of that voxel is empty and interior, so the probes
+// sits in a voxel with distance byte d (border distance folded in), everything within d-1 voxels of that voxel is empty and interior, so the probes
 // with z_k * G <= d - 1.25 are in-bounds misses for every ray (0.25 = 2 * eps_q + slack, as in k_forward_dist).
 __global__ void k_view_start(const FwdArgs a, int n_views, int* __restrict__ kstart) {
     const int view = blockIdx.x * blockDim.x + threadIdx.x;
@@ -483,7 +483,7 @@ __global__ void k_view_start(const FwdArgs a, int n_views, int* __restrict__ kst
         const int iy = voxel_index(ty, v.vmin[1], v.delta[1], v.inv[1], v.c0[1], v.eps[1], ne);
         const int iz = voxel_index(tz, v.vmin[2], v.delta[2], v.inv[2], v.c0[2], v.eps[2], ne);
         if (coords_valid(v, ix, iy, iz)) {
-            const float d = (float)v.bytes[linear_index(v, ix, iy, iz)];
+            const float d = (float)byte_with_border(v, v.bytes[linear_index(v, ix, iy, iz)], ix, iy, iz);
             // z_k = (z0 + k*zdelta) mm;  need z_k * 0.001 * G <= d - 1.25  for all k < k0
             const float zmax_mm = (d - 1.25f) / fmaxf(G, 1e-6f) * 1000.0f * 0.9999f;
             if (zmax_mm >= (float)a.z0) k0 = min(a.S, (int)floorf((zmax_mm - (float)a.z0) / (float)a.zdelta) + 1);
@@ -501,7 +501,7 @@ __global__ void k_view_start(const FwdArgs a, int n_views, int* __restrict__ kst
 }
 
 // ---- K1 on distance bytes: k_forward_dist ---------------------------------------------------------------------
-// DMF_GRID_BYTE march.  Every exactly evaluated probe reads its voxel's distance byte d (dmf_distance.cuh): 0 = hit;
+// DMF_GRID_BYTE march.  Every exactly evaluated probe reads its voxel's distance byte d (dmf_distance.cuh, border distance folded in): 0 = hit;
 // d >= 2 proves the next floor((d - 1.25) / max|QB|) probes are in-bounds misses (same error budget as k_forward_skip:
 // eps_q <= 0.1 voxel per probe, 0.25 voxel margin), so they are counted and skipped.  Two consecutive probes (k, k+1) are
 // evaluated per iteration so that their table and grid loads are in flight together; the second is used only if the
@@ -627,11 +627,11 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
             const bool inb_b = (k + 1 < S) && pxb > lo0 && pxb < hi0 && pyb > lo1 && pyb < hi1 && pzb > lo2 && pzb < hi2;
             int ixa, iya, iza, ixb = 0, iyb = 0, izb = 0;
             const unsigned idxa = probe_index<EXACT>(v, pxa, pya, pza, in0, in1, in2, cc0, cc1, cc2, er0, er1, er2, pny, pnz, ixa, iya, iza, n_f64, n_exact);
-            const unsigned da = __ldg(gbytes + idxa);
+            const unsigned da = byte_with_border(v, __ldg(gbytes + idxa), ixa, iya, iza);
             unsigned db = 1u;
             if (inb_b) {
                 const unsigned idxb = probe_index<EXACT>(v, pxb, pyb, pzb, in0, in1, in2, cc0, cc1, cc2, er0, er1, er2, pny, pnz, ixb, iyb, izb, n_f64, n_exact);
-                db = __ldg(gbytes + idxb);
+                db = byte_with_border(v, __ldg(gbytes + idxb), ixb, iyb, izb);
             }
             n_inb++;
             if (da == 0u) { hit_k = k; hx = ixa; hy = iya; hz = iza; hpx = pxa; hpy = pya; hpz = pza; k++; break; }
@@ -658,11 +658,13 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
 // ---- K1 on distance bytes, line-first: k_forward_line ------------------------------------------------------------
 // Same results as k_forward / k_forward_dist, probe for probe.  The ray is FIRST followed as the straight line
 // Q(k) = QA + k*QB in voxel units (3 FMAs, no table loads): the distance byte d of the line point's voxel decides.
-//   d >= 2: every voxel within d-1 (L-inf) of that voxel is empty and interior.  The reference's sample k lies within
-//           eps_q <= 0.1 voxel of Q(k) (error budget above k_forward_skip), i.e. in that voxel or one next to it: an
-//           in-bounds miss WITHOUT being evaluated; so are the next floor((d - 1.25) / max|QB|) samples.
-//   d <= 1: next to an occupied voxel or to the volume boundary: the sample is evaluated exactly (tables, the
-//           reference's float expression, the exact voxel index), as k_forward does.
+//   d >= 2: every voxel within d-1 (L-inf) of that voxel is empty.  The reference's sample k lies within
+//           eps_q <= 0.1 voxel of Q(k) (error budget above k_forward_skip), i.e. in that voxel or one next to it: a
+//           miss WITHOUT being evaluated; so are the next floor((d - 1.25) / max|QB|) samples -- as far as they stay inside
+//           [kin, kout], where the slab test proves them in bounds (the bytes hold the distance to the nearest OCCUPIED voxel and
+//           know nothing of the boundary: the jump is cut at kout + 1).
+//   d <= 1: next to an occupied voxel: the sample is evaluated exactly (tables, the reference's float expression, the
+//           exact voxel index), as k_forward does -- unless the line point is far enough from every face of its voxel.
 // The line is only consulted for k in [kin, kout], where it is >= 0.25 voxel inside the volume on every axis (slab test,
 // once per ray) so its voxel is addressable; samples that are provably outside (line > 0.25 voxel beyond a face) are
 // dropped without evaluation, and the thin bands in between are evaluated exactly.  Views whose eps_q exceeds 0.1 voxel
@@ -1038,6 +1040,30 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
                     const int cur = *((volatile int*)(a.min_depth + view));
                     if (a.z0 + (int)kf * a.zdelta > cur) { stop = true; break; }
                 }
+#if DMF_LINE_TEX
+                // the probe through the texture unit: point sampling floors the line point (to within 2^-8 voxel, which the 0.05 voxel of
+                // slack in the 1.25 absorbs: the sample is still in the fetched voxel or one next to it) -- 3 FMAs + TEX.  Bytes 0 and 1 are
+                // re-read from the linear grid at the exactly floored index, because what happens then depends on WHICH voxel it is.
+                const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
+                unsigned d = tex3D<unsigned char>((cudaTextureObject_t)v.bytes_tex, q2, q1, q0);
+#ifdef DMF_LINE_STATS
+                n_f64++;
+#endif
+                float adv;
+                if (d >= 2u) adv = __fadd_rd(fmaf(__int_as_float(0x4B000000 | (int)d) - 8388608.0f, rq, c1), kM) - kM;
+                else {
+                    const float s0 = __fadd_rd(q0, kM), s1 = __fadd_rd(q1, kM), s2 = __fadd_rd(q2, kM);
+                    unsigned lidx = (unsigned)__float_as_int(s0) * pnyz + ((unsigned)__float_as_int(s1) * pnz + ((unsigned)__float_as_int(s2) - bias));
+                    DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
+                    d = __ldg(gbytes + min(lidx, last));
+                    adv = d >= 2u ? __fadd_rd(fmaf(__int_as_float(0x4B000000 | (int)d) - 8388608.0f, rq, c1), kM) - kM : LINE_EXACT_FLAG;
+                    if (d == 1u) {
+                        const float f0 = q0 - (s0 - kM), f1 = q1 - (s1 - kM), f2 = q2 - (s2 - kM);
+                        const float e = ldg_f4_volatile(sp + 3).x;     // e_safe = eps_q of the view + 2^-10 voxel of slack
+                        if (fminf(f0, fminf(f1, f2)) >= e && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e) adv = 1.0f;
+                    }
+                }
+#else
                 const unsigned bx = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb0, qa0), kM));
                 const unsigned by = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb1, qa1), kM));
                 const unsigned bz = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb2, qa2), kM));
@@ -1054,7 +1080,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
                 // this probe + the skipped ones: floor((d - 1.25) / max|QB|) + 1 for d >= 2; 2^20 when the probe must be evaluated exactly
                 float adv = d >= 2u ? __fadd_rd(fmaf(__int_as_float(0x4B000000 | (int)d) - 8388608.0f, rq, c1), kM) - kM : LINE_EXACT_FLAG;
                 if (d == 1u) {
-                    // Next to an occupied voxel or in the boundary layer, but this voxel itself is empty.  If the line point is
+                    // Next to an occupied voxel, but this voxel itself is empty.  If the line point is
                     // at least e_safe (> eps_q) away from every face of its voxel, the reference's sample is in the same voxel:
                     // an in-bounds miss (the line is >= 0.25 voxel inside the volume here).  Otherwise evaluate exactly.
                     const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
@@ -1062,6 +1088,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
                     const float e = ldg_f4_volatile(sp + 3).x;     // e_safe = eps_q of the view + 2^-10 voxel of slack
                     if (fminf(f0, fminf(f1, f2)) >= e && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e) adv = 1.0f;
                 }
+#endif
                 kf += adv;
                 if (!(kf <= koutf)) break;
             }
@@ -1070,7 +1097,8 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
 #endif
             const bool need_exact = kf >= LINE_EXACT_FLAG;
             if (need_exact) kf -= LINE_EXACT_FLAG;
-            const int k2 = min((int)kf, s_end);
+            // the bytes know nothing of the volume's boundary: samples up to kout are in bounds by the slab test, later ones are not proven
+            const int k2 = min((int)kf, kout + 1);
             n_inb += (unsigned)(k2 - k); n_skip += (unsigned)(k2 - k);
             k = k2;
             if (!need_exact) continue;

@@ -117,8 +117,9 @@ __device__ __forceinline__ void camera_pixel(const RevArgs& a, float xx, float y
 
 // The 1 mm march from `centroid` towards (and past) the camera (:81-103, :172-200).  true = occluded.
 // FMT 0: bit grid, every step evaluated.  FMT 1: distance bytes -- a step that lands in a voxel with distance byte
-// d >= 2 proves that the next floor((d-1.25)/step) steps land in empty interior voxels (they cannot collide, cannot be the
-// origin voxel, cannot leave the volume), so they are counted and skipped; results and counters are unchanged.
+// d >= 2 proves that the next floor((d-1.25)/step) steps land in empty voxels (they cannot collide, cannot be the origin voxel;
+// they cannot leave the volume because the line loop cuts every jump at the end of its slab interval and the exact step folds
+// the border distance in, byte_with_border), so they are counted and skipped; results and counters are unchanged.
 // Samples are c + (v*depth)/1000 in float: within 3 roundings (< rev_eps voxels) of the line c + depth*(v/1000).
 template <int FMT>
 __device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float cy, float cz, float vx, float vy, float vz, u64 chash, int d0,
@@ -190,6 +191,7 @@ __device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float
                 s += adv;
                 if (!(s <= s_outf) || s > s_capf) break;
             }
+            s = fminf(s, s_outf + 1.0f);            // the bytes know nothing of the boundary: steps up to s_out are in bounds by the slab test, later ones are not proven
             const int nd = (int)s;
             const unsigned n = (unsigned)(nd - depth);
             n_samples += n; n_inb += n; n_skip += n;
@@ -222,7 +224,7 @@ __device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float
             if (FMT == 0) {
                 if ((__ldg(v.bits + (idx >> 5)) >> (idx & 31)) & 1u) return true;
             } else {
-                const unsigned d = __ldg(v.bytes + idx);
+                const unsigned d = byte_with_border(v, __ldg(v.bytes + idx), ix, iy, iz);
                 if (d == 0u) return true;
                 if (skip_ok && d >= 2u) {
                     const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(
                         if (hash_coords(ix, iy, iz) != chash) {                    // hash == centroid_hash: same voxel as the origin, continue
                             if (!coords_valid(v, ix, iy, iz)) result = 0;          // validCoords == false: break
                             else {
-                                const unsigned d = __ldg(v.bytes + (((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz));
+                                const unsigned d = byte_with_border(v, __ldg(v.bytes + (((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz)), ix, iy, iz);
                                 if (d == 0u) result = 1;
                                 else if (skip_ok && d >= 2u) {
                                     const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(RP_THREADS, DMF_RP_MIN_BLOCKS) k_reverse_pool(
                     const unsigned d = __ldg(v.bytes + lidx);
                     if (d >= 2u) {
                         const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
-                        const float adv = fminf(__fadd_rd(fmaf(df - 1.25f, rq, 1.0f), kM) - kM, (float)a.step_cap + 1.0f);
+                        const float adv = fminf(fminf(__fadd_rd(fmaf(df - 1.25f, rq, 1.0f), kM) - kM, (float)a.step_cap + 1.0f), s_outf + 1.0f - sf);   // (never past the slab interval)
                         sf += adv; adv_sum += adv;
                         on_line = sf <= s_outf;
                     } else {
@@ -657,7 +659,7 @@ __global__ void __launch_bounds__(128) k_segments_collide(const VolDev v, const 
                     if (FMT == 0) {
                         if ((__ldg(v.bits + (idx >> 5)) >> (idx & 31)) & 1u) { collided = true; break; }
                     } else {
-                        const unsigned d = __ldg(v.bytes + idx);
+                        const unsigned d = byte_with_border(v, __ldg(v.bytes + idx), ix, iy, iz);
                         if (d == 0u) { collided = true; break; }
                         if (skip_ok && d >= 2u) {
                             const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
