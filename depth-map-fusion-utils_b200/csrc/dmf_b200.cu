@@ -70,8 +70,9 @@ int run_maybe_graphed(dmf_ctx* c, CallGraph& g, unsigned long long key, cudaStre
             g.disabled = rc == 0 && alloc_generation().load() == gen;       // a capture that fails for no reason of ours: stop trying
             g.cand_key = 0;
             c->launches = l0;
-            if (rc) return rc;
-            return enqueue();                                         // nothing was executed by the aborted capture
+            // nothing was executed by the aborted capture.  A failure INSIDE it may just be an operation that cannot be captured (a table
+            // rebuild after an intervening call with other parameters synchronises the device): run the call plainly, it reports real errors
+            return enqueue();
         }
         e = cudaGraphInstantiate(&g.exec, graph, 0);
         cudaGraphDestroy(graph);
@@ -531,7 +532,14 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     const bool two_probe = (p->flags & DMF_FWD_TWO_PROBE) != 0;
     if (sub_views <= 0 || sub_views > n_views) sub_views = n_views;
     if (!c->capturing) DMF_CUDA(cudaEventRecord(c->ev_h0, st));
+    a.tile_k = nullptr; a.tiles_x = (c->Wc + TILE_RAYS - 1) / TILE_RAYS; a.tiles_per_view = a.tiles_x * ((c->Hc + TILE_RAYS - 1) / TILE_RAYS);
     if (byte_skip) { a.view0 = 0; k_view_start<<<(n_views + 127) / 128, 128, 0, st>>>(a, n_views, const_cast<int*>(a.kstart)); c->launches++; }
+    if (byte_skip && !two_probe && c->tile_march) {                          // the line-first kernel runs: cone pre-march of its 4x4-ray tiles
+        DMF_TRY(c->d_tile_k.reserve((size_t)n_views * a.tiles_per_view * 4));
+        k_tile_start<<<dim3((a.tiles_per_view + 127) / 128, n_views), 128, 0, st>>>(a, c->d_tile_k.as<int>());
+        a.tile_k = c->d_tile_k.as<int>();
+        c->launches++;
+    }
     const bool split = sub_views < n_views;
     if (split) { DMF_CUDA(cudaEventRecord(c->ev_fork, st)); DMF_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0)); }
     int n_launch = 0;
@@ -628,6 +636,7 @@ int dmf_create(dmf_ctx** out, int device) {
     DMF_TRY(c->d_counters.reserve(DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
     DMF_CUDA(cudaMemset(c->d_counters.p, 0, DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
     c->angle = bisect_angle_test();
+    if (const char* e = std::getenv("DMF_TILE_MARCH")) c->tile_march = e[0] != '0';
     *out = c;
     return 0;
 }
@@ -640,7 +649,7 @@ void dmf_destroy(dmf_ctx* c) {
                       &c->d_view_mark, &c->d_good_bits, &c->d_first_view, &c->d_observed, &c->d_axis[0], &c->d_axis[1], &c->d_axis[2], &c->d_xtab, &c->d_ytab, &c->d_ztab, &c->d_kstart,
                       &c->d_poses[0], &c->d_poses[1], &c->d_inv_poses, &c->d_first_key, &c->d_ray_key, &c->d_ray_occ, &c->d_tmp_a, &c->d_tmp_b,
                       &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters,
-                      &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err};
+                      &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err, &c->d_tile_k};
     c->graph_fwd_ids.drop(); c->graph_rev_ids.drop();
     drop_bytes_texture(c);
     for (auto* b : bufs) b->release();
@@ -968,6 +977,10 @@ int dmf_forward(dmf_ctx* c, const dmf_forward_params* p, const float* poses, int
                 std::memset(&k, 0, sizeof k);
                 k.mode = p->mode; k.zdelta = p->zdelta; k.sparse = p->sparse; k.flags = p->flags; k.fmt = pl.grid_format; k.H = c->H; k.W = c->W; k.bytes_built = c->bytes_built ? 1 : 0;
                 std::memcpy(k.K, c->K, sizeof k.K); k.n_occ = c->n_occ; k.epoch = c->volume_epoch; k.R = R;
+                // whatever may allocate or synchronise happens before a capture can start (another call may have replaced the tables since)
+                DMF_TRY(ensure_tables(c, pl.z0, p->zdelta, pl.cstride, pl.rstride, st));
+                if (pl.grid_format == DMF_GRID_BYTE) DMF_TRY(ensure_bytes(c, st));
+                if (p->flags & DMF_FWD_CARVE) DMF_TRY(ensure_observed(c, st));
                 DMF_TRY(run_maybe_graphed(c, c->graph_fwd_ids, fnv1a(&k, sizeof k), st, enqueue_all));
             } else DMF_TRY(enqueue_all());
             DMF_CUDA(cudaStreamSynchronize(st));
@@ -1015,7 +1028,8 @@ int dmf_counters(dmf_ctx* c, uint64_t out[DMF_CNT_COUNT]) {
     // diagnostic build: k_forward_line logs blocks / block-cycles / warp-cycles per SM into the unused tail of each slot
     for (int s = 0; s < 160; s++) {
         const uint64_t* q = &all[(size_t)s * DMF_COUNTER_STRIDE];
-        if (q[12]) std::fprintf(stderr, "sm %3d blocks %7llu  warp-cycles/warp %8.0f  line %8.0f  exact %8.0f\n", s, (unsigned long long)q[12], q[13] / (4.0 * q[12]), q[14] / (4.0 * q[12]), q[15] / (4.0 * q[12]));
+        if (q[12]) std::fprintf(stderr, "sm %3d blocks %7llu  warp-cycles/warp %8.0f  prologue %8.0f  march loop %8.0f (line %8.0f  exact %8.0f)\n", s, (unsigned long long)q[12], q[13] / (4.0 * q[12]),
+                                q[11] / (4.0 * q[12]), q[10] / (4.0 * q[12]), q[14] / (4.0 * q[12]), q[15] / (4.0 * q[12]));
     }
 #endif
     return 0;

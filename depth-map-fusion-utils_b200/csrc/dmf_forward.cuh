@@ -33,6 +33,9 @@ struct FwdArgs {
     // loop constants the host folds once (the kernel runs at 32 registers and would otherwise re-derive them from the constant bank per probe)
     float z0m, zdm, Sf;                // z0 * 0.001, zdelta * 0.001, (float)S
     unsigned pnyz, bias, last;         // pdim_y * pdim_z;  0x4B400000 * (pnyz + pdim_z + 1) (the three shifter offsets, folded);  n_cells - 1
+    // cone pre-march (k_tile_start): per view and 4x4 tile of lattice rays, every IN-BOUNDS sample k < tile_k of every ray of the tile is a miss
+    const int* __restrict__ tile_k;    // [n_views][tiles_y][tiles_x], null = none
+    int tiles_x, tiles_per_view;
     // outputs (may be null)
     int* depth;                        // [n_views][H][W]
     unsigned short* depth16;           // [n_views][H][W]  same, 0xFFFF = none
@@ -655,6 +658,68 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
     if (a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)(unsigned)view * a.vis_stride32), view, gridDim.x * gridDim.y);
 }
 
+// ---- cone pre-march of 4x4-ray tiles: k_tile_start ------------------------------------------------------------------
+// The 16 rays of a 4x4 tile of the lattice leave the camera within a fraction of a degree of each other: up to the depth at which
+// the tile's footprint is a voxel or two wide they all cross the same empty space, and k_forward_line would make each of them
+// discover that for itself -- ~8 dependent probes per ray on the bench sweep, half of them far from any surface and therefore the
+// ones that miss L1 and L2.  Here ONE thread marches the tile's centre line Qc(k) on the distance bytes for all 16 rays:
+//   every sample k' of every ray of the tile lies within  rho(k') = A * z_k' + 3 * eps_q(view)  voxels (L-inf) of Qc(k'), where
+//   A = max_i |1/delta_i| * (|m_i0| * hw_x + |m_i1| * hw_y) and hw = half the tile's extent in (c-cx)/fx, (r-cy)/fy -- the rays'
+//   lines differ from the centre line by z * M * (ddx, ddy, 0) exactly, and each of {sample vs its line, its line in float, the
+//   centre line in float} is within eps_q(view) (k_view_start; the budget above k_forward_skip);
+//   a probe at k reads the byte d of the voxel V of Qc(k) (clamped into the grid; `disp` = how far it had to move): every grid
+//   voxel within d-1 of V is empty, and a point within R < d-1 of a point of V is in such a voxel.  Samples k .. k+n of all rays are
+//   within  disp + rho(k) + n * (max|QBc| + A * zdelta)  of Qc(k)'s clamped point, so they are misses (if they are in bounds at all)
+//   for  n = floor((d - 1 - 2^-8 - disp - rho(k)) / (max|QBc| + A * zdelta)), rounded down.
+// The march ends at the first probe that cannot advance; tile_k = that k: every IN-BOUNDS sample k' < tile_k of every ray of the
+// tile is a miss.  (Whether a sample is in bounds is still each ray's own business: k_forward_line only uses tile_k inside its slab
+// interval.)  It starts at the view's kstart (k_view_start: the probes before it are misses for every ray of the view); views
+// flagged kstart = -1 (eps_q > 0.1, non-finite poses) get tile_k = 0.  One thread per tile, 1/16 of the rays.
+constexpr int TILE_RAYS = 4;
+__global__ void __launch_bounds__(128) k_tile_start(const FwdArgs a, int* __restrict__ tile_k) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)a.tiles_per_view) return;
+    const unsigned view = blockIdx.y;
+    const VolDev& v = a.vol;
+    const float4* sp = a.viewrec + 4u * view;
+    const float4 r0 = sp[0], r1 = sp[1], r2 = sp[2], r3 = sp[3];
+    const int ks = __float_as_int(r3.y);
+    int kt = 0;
+    if (ks >= 0) {
+        const int tx = (int)(t % (unsigned)a.tiles_x), ty = (int)(t / (unsigned)a.tiles_x);
+        const int c0 = tx * TILE_RAYS, c1 = min(c0 + TILE_RAYS - 1, a.Wc - 1), q0 = ty * TILE_RAYS, q1 = min(q0 + TILE_RAYS - 1, a.Hc - 1);
+        const float xl = __ldg(a.dcx + c0), xh = __ldg(a.dcx + c1), yl = __ldg(a.dcy + q0), yh = __ldg(a.dcy + q1);
+        const float xc = 0.5f * (xl + xh), yc = 0.5f * (yl + yh);
+        const float hwx = fmaxf(fabsf(xl - xc), fabsf(xh - xc)) * 1.00001f, hwy = fmaxf(fabsf(yl - yc), fabsf(yh - yc)) * 1.00001f;
+        const float g0 = fmaf(r0.x, xc, fmaf(r0.y, yc, r0.z)), g1 = fmaf(r1.x, xc, fmaf(r1.y, yc, r1.z)), g2 = fmaf(r2.x, xc, fmaf(r2.y, yc, r2.z));
+        const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2];
+        const float qa0 = fmaf(fmaf(a.z0m, g0, r0.w), in0, v.c32[0]), qa1 = fmaf(fmaf(a.z0m, g1, r1.w), in1, v.c32[1]), qa2 = fmaf(fmaf(a.z0m, g2, r2.w), in2, v.c32[2]);
+        const float qb0 = a.zdm * g0 * in0, qb1 = a.zdm * g1 * in1, qb2 = a.zdm * g2 * in2;
+        const float A = fmaxf(fabsf(in0) * (fabsf(r0.x) * hwx + fabsf(r0.y) * hwy), fmaxf(fabsf(in1) * (fabsf(r1.x) * hwx + fabsf(r1.y) * hwy),
+                                                                                        fabsf(in2) * (fabsf(r2.x) * hwx + fabsf(r2.y) * hwy))) * 1.0001f;
+        const float grow = fmaxf(fabsf(qb0), fmaxf(fabsf(qb1), fabsf(qb2))) * 1.0001f + A * a.zdm * 1.0001f;     // growth of the bound per sample
+        const float rgrow = 0.9999f / fmaxf(grow, 1e-3f);
+        const float fixed = 1.0f + 0.00390625f + 3.0f * r3.x;                       // 1 + 2^-8 + 3 * (eps_q(view) + 2^-10)
+        const float kM = 12582912.0f;
+        const unsigned pnz = (unsigned)v.pdim[2];
+        float kf = (float)min(ks, a.S);
+        for (int it = 0; it < 64 && kf < a.Sf; it++) {
+            const float p0 = fmaf(kf, qb0, qa0), p1 = fmaf(kf, qb1, qa1), p2 = fmaf(kf, qb2, qa2);
+            const float l0 = fminf(fmaxf(p0, 0.0f), v.ext[0]), l1 = fminf(fmaxf(p1, 0.0f), v.ext[1]), l2 = fminf(fmaxf(p2, 0.0f), v.ext[2]);
+            const float disp = fmaxf(fabsf(p0 - l0), fmaxf(fabsf(p1 - l1), fabsf(p2 - l2)));
+            const unsigned bx = (unsigned)__float_as_int(__fadd_rd(l0, kM)), by = (unsigned)__float_as_int(__fadd_rd(l1, kM)), bz = (unsigned)__float_as_int(__fadd_rd(l2, kM));
+            unsigned lidx = bx * a.pnyz + (by * pnz + (bz - a.bias));
+            DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
+            const float d = (float)__ldg(v.bytes + min(lidx, a.last));
+            const float room = d - fixed - disp - A * fmaf(kf, a.zdm, a.z0m);
+            if (!(room >= 0.0f)) break;                                              // (NaN ends the march too)
+            kf += floorf(room * rgrow) + 1.0f;
+        }
+        kt = (int)fminf(kf, a.Sf);
+    }
+    tile_k[view * (unsigned)a.tiles_per_view + t] = kt;
+}
+
 // ---- K1 on distance bytes, line-first: k_forward_line ------------------------------------------------------------
 // Same results as k_forward / k_forward_dist, probe for probe.  The ray is FIRST followed as the straight line
 // Q(k) = QA + k*QB in voxel units (3 FMAs, no table loads): the distance byte d of the line point's voxel decides.
@@ -967,6 +1032,9 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
     const VolDev& v = a.vol;
     const float kM = 12582912.0f;
     const int S = a.S;
+    // the tile's cone pre-march (k_tile_start): in-bounds samples before kt are misses for every ray of the 4x4 tile
+    int kt = 0;
+    if (a.tile_k) kt = __ldg(a.tile_k + ((unsigned)view * (unsigned)a.tiles_per_view + (unsigned)(ri / TILE_RAYS) * (unsigned)a.tiles_x + (unsigned)(ci / TILE_RAYS)));
 
     // ---- per ray: the line and the sample intervals ----
     float qa0, qa1, qa2, qb0, qb1, qb2;
@@ -999,16 +1067,20 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
                 ti0 = fmaxf(ti0, lo); ti1 = fminf(ti1, hi);
                 to0 = fmaxf(to0, lo - w); to1 = fminf(to1, hi + w);
             }
-            // the t's carry a few ulps of relative error: one sample of guard on each end (|t| that matter are < 2^20)
+            // The t's carry a relative error below 2^-21 (MUFU.RCP, one subtraction, one product), i.e. < 2^-9 sample for |t| <= 2^12 -- and
+            // S <= 1000, so larger |t| only meet the clamps.  Guard g(t) = 2^-6 + |t| * 2^-18 samples on each end: with the exact bounds t*,
+            // samples k < ceil(to0 - g) are < to0* (outside), k >= floor(to1 + g) + 1 are > to1* (outside), and ceil(ti0 + g) <= k <=
+            // floor(ti1 - g) are inside [ti0*, ti1*].  (Round 1 used a whole sample of guard per end: 4-5 exactly evaluated samples in the
+            // band where a ray leaves the volume instead of 1-2 -- a third of all exact evaluations of the bench sweep.)
             const float Sf = a.Sf;
             if (!(to0 <= to1)) { k = S; if (CARVE) k_slab = S; }                     // never inside: every sample fails validPoints
             else {
-                k = (int)fminf(fmaxf(floorf(to0) - 1.0f, 0.0f), Sf);
+                k = (int)fminf(fmaxf(ceilf(to0 - fmaf(fabsf(to0), 3.814697265625e-06f, 0.015625f)), 0.0f), Sf);
                 if (CARVE) k_slab = k;
-                s_end = (int)fminf(fmaxf(ceilf(to1) + 2.0f, 0.0f), Sf);
+                s_end = (int)fminf(fmaxf(floorf(to1 + fmaf(fabsf(to1), 3.814697265625e-06f, 0.015625f)) + 1.0f, 0.0f), Sf);
                 if (ti0 <= ti1) {
-                    kin = (int)fminf(fmaxf(ceilf(ti0) + 1.0f, 0.0f), Sf);
-                    kout = (int)fminf(fmaxf(floorf(ti1) - 1.0f, -1.0f), Sf - 1.0f);
+                    kin = (int)fminf(fmaxf(ceilf(ti0 + fmaf(fabsf(ti0), 3.814697265625e-06f, 0.015625f)), 0.0f), Sf);
+                    kout = (int)fminf(fmaxf(floorf(ti1 - fmaf(fabsf(ti1), 3.814697265625e-06f, 0.015625f)), -1.0f), Sf - 1.0f);
                 }
             }
             const int k0 = min(ks, S);
@@ -1027,13 +1099,18 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
     const unsigned pnyz = a.pnyz, bias = a.bias, last = a.last;                      // folded on the host (FwdArgs)
     unsigned iter = 0;
     bool stop = false;
+#ifdef DMF_LINE_STATS
+    const long long t_loop0 = clock64();
+#endif
     while (k < s_end && !stop) {
         if (k >= kin && k <= kout) {
             // ---- follow the line ----
 #ifdef DMF_LINE_STATS
             const long long tl0 = clock64();
 #endif
-            float kf = (float)k;
+            // k .. kout are in bounds (slab test); those before kt are misses (cone pre-march of the tile): the first probe goes to kt,
+            // or to kout if the tile's march got even further (one probe that could be saved, but no second loop shape)
+            float kf = (float)max(k, min(kt, kout));
             const float koutf = (float)kout;
             for (;;) {
                 if (MODE == 4 && (iter++ & 7u) == 0u) {   // rayTraceAndGetMinimum: planes behind the current minimum cannot matter
@@ -1131,6 +1208,9 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
         if (de == 0u) { hit_k = k; hx = ix; hy = iy; hz = iz; hpx = px; hpy = py; hpz = pz; k++; break; }
         k++;
     }
+#ifdef DMF_LINE_STATS
+    const long long t_loop1 = clock64();
+#endif
     if (CARVE && MODE != 4 && active) {
         const int k_last = hit_k >= 0 ? hit_k : s_end - 1;                          // samples >= s_end are provably outside the volume
 #if DMF_CARVE_SIGN
@@ -1150,6 +1230,7 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
         u64* slot = a.counters + (size_t)smid * DMF_COUNTER_STRIDE;
         const unsigned long long dt = (unsigned long long)(clock64() - t_begin);
         atomicAdd(slot + 13, dt); atomicAdd(slot + 14, (unsigned long long)t_line); atomicAdd(slot + 15, (unsigned long long)t_exact);
+        atomicAdd(slot + 11, (unsigned long long)(t_loop0 - t_begin)); atomicAdd(slot + 10, (unsigned long long)(t_loop1 - t_loop0));   // prologue, whole march loop
         if (warp == 0) atomicAdd(slot + 12, 1ull);
     }
 #endif

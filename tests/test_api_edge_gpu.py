@@ -265,3 +265,30 @@ def test_device_integration_equals_host_integration(dmf, ctx):
     for key in ("depth", "visibility", "found_any"):
         assert np.array_equal(a[3][key], b[3][key])
     assert all(np.array_equal(x, y) for x, y in zip(a[3]["ids"], b[3]["ids"])) and all(np.array_equal(x, y) for x, y in zip(a[4]["ids"], b[4]["ids"]))
+
+
+def test_graph_replay_survives_intervening_calls(dmf):
+    """The single-view id-list call is replayed as a captured CUDA graph from its second identical call on.  A call with other
+    parameters in between (other z tables: MINIMUM starts at 5 mm and strides 10 px) must neither break the capture -- a table
+    rebuild synchronises the device, which cannot be captured -- nor change a result."""
+    c = dmf.Context(0)
+    try:
+        sc, gv = _vol(dmf, c)
+        pose = np.ascontiguousarray(dmf.scenes.pose_p1(1.024)[0])
+        for grid in (dmf.GRID_BYTE, dmf.GRID_BIT):
+            eng = dmf.RayTracingEngine(dmf.Camera(dmf.scenes.REFERENCE_K), c, grid)
+            found0, ids0 = eng.rayTraceAndGetPoints(gv, pose, 8, False)
+            for _ in range(3):
+                zmin = eng.rayTraceAndGetMinimum(gv, pose, 1, True)          # replaces the tables between two identical id-list calls
+                found, ids = eng.rayTraceAndGetPoints(gv, pose, 8, False)
+                assert found == found0 and np.array_equal(ids, ids0)
+                found, ids = eng.rayTraceAndGetPoints(gv, pose, 8, False)    # (and two in a row: candidate -> capture -> replay)
+                assert found == found0 and np.array_equal(ids, ids0)
+            assert zmin > 0
+            v0, r0 = eng.reverseRayTraceFast(gv, pose, False)
+            for _ in range(3):
+                eng.rayTraceAndGetMinimum(gv, pose, 1, True)
+                v, r = eng.reverseRayTraceFast(gv, pose, False)
+                assert v == v0 and np.array_equal(r, r0)
+    finally:
+        c.close()

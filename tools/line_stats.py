@@ -12,7 +12,7 @@ want = tuple(w for w in (sys.argv[3] if len(sys.argv) > 3 else "depth").split(",
 sc = D.scenes.scene(name)
 ctx = D.Context.default(0)
 gv = D.VoxelVolume(ctx); gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
-poses = D.scenes.bench_poses(float(sc.bounds[1]), nv)
+poses = np.ascontiguousarray(D.scenes.poses_sphere_lookat(1.0, 1024)[::1024 // nv]) if 1024 % nv == 0 else D.scenes.bench_poses(float(sc.bounds[1]), nv)   # the bench step's view mix
 eng = D.RayTracingEngine(D.Camera(D.scenes.REFERENCE_K), ctx, D.GRID_BYTE)
 eng.forward_views(gv, poses, 0, sc.zdelta, False, want=want)
 ctx.reset_counters()
