@@ -532,12 +532,13 @@ int enqueue_forward(dmf_ctx* c, const dmf_forward_params* p, const FwdPlan& pl, 
     const bool two_probe = (p->flags & DMF_FWD_TWO_PROBE) != 0;
     if (sub_views <= 0 || sub_views > n_views) sub_views = n_views;
     if (!c->capturing) DMF_CUDA(cudaEventRecord(c->ev_h0, st));
-    a.tile_k = nullptr; a.tiles_x = (c->Wc + TILE_RAYS - 1) / TILE_RAYS; a.tiles_per_view = a.tiles_x * ((c->Hc + TILE_RAYS - 1) / TILE_RAYS);
+    a.tile_rec = nullptr; a.tiles_x = (c->Wc + TILE_RAYS - 1) / TILE_RAYS; a.tiles_per_view = a.tiles_x * ((c->Hc + TILE_RAYS - 1) / TILE_RAYS);
     if (byte_skip) { a.view0 = 0; k_view_start<<<(n_views + 127) / 128, 128, 0, st>>>(a, n_views, const_cast<int*>(a.kstart)); c->launches++; }
-    if (byte_skip && !two_probe && c->tile_march) {                          // the line-first kernel runs: cone pre-march of its 4x4-ray tiles
-        DMF_TRY(c->d_tile_k.reserve((size_t)n_views * a.tiles_per_view * 4));
-        k_tile_start<<<dim3((a.tiles_per_view + 127) / 128, n_views), 128, 0, st>>>(a, c->d_tile_k.as<int>());
-        a.tile_k = c->d_tile_k.as<int>();
+    if (byte_skip && !two_probe) {                                           // the line-first kernel runs: per-tile sample intervals + cone pre-march
+        if (c->S > 4095) return fail("internal: %d samples per ray exceed the 12-bit fields of the tile records", c->S);
+        DMF_TRY(c->d_tile_rec.reserve((size_t)n_views * a.tiles_per_view * 8));
+        k_tile_start<<<dim3((a.tiles_per_view + 127) / 128, n_views), 128, 0, st>>>(a, c->d_tile_rec.as<u64>());
+        a.tile_rec = c->d_tile_rec.as<u64>();
         c->launches++;
     }
     const bool split = sub_views < n_views;
@@ -636,7 +637,6 @@ int dmf_create(dmf_ctx** out, int device) {
     DMF_TRY(c->d_counters.reserve(DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
     DMF_CUDA(cudaMemset(c->d_counters.p, 0, DMF_COUNTER_SLOTS * DMF_COUNTER_STRIDE * 8));
     c->angle = bisect_angle_test();
-    if (const char* e = std::getenv("DMF_TILE_MARCH")) c->tile_march = e[0] != '0';
     *out = c;
     return 0;
 }
@@ -649,7 +649,7 @@ void dmf_destroy(dmf_ctx* c) {
                       &c->d_view_mark, &c->d_good_bits, &c->d_first_view, &c->d_observed, &c->d_axis[0], &c->d_axis[1], &c->d_axis[2], &c->d_xtab, &c->d_ytab, &c->d_ztab, &c->d_kstart,
                       &c->d_poses[0], &c->d_poses[1], &c->d_inv_poses, &c->d_first_key, &c->d_ray_key, &c->d_ray_occ, &c->d_tmp_a, &c->d_tmp_b,
                       &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters,
-                      &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err, &c->d_tile_k};
+                      &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err, &c->d_tile_rec};
     c->graph_fwd_ids.drop(); c->graph_rev_ids.drop();
     drop_bytes_texture(c);
     for (auto* b : bufs) b->release();

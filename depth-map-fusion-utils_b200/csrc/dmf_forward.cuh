@@ -33,8 +33,9 @@ struct FwdArgs {
     // loop constants the host folds once (the kernel runs at 32 registers and would otherwise re-derive them from the constant bank per probe)
     float z0m, zdm, Sf;                // z0 * 0.001, zdelta * 0.001, (float)S
     unsigned pnyz, bias, last;         // pdim_y * pdim_z;  0x4B400000 * (pnyz + pdim_z + 1) (the three shifter offsets, folded);  n_cells - 1
-    // cone pre-march (k_tile_start): per view and 4x4 tile of lattice rays, every IN-BOUNDS sample k < tile_k of every ray of the tile is a miss
-    const int* __restrict__ tile_k;    // [n_views][tiles_y][tiles_x], null = none
+    // k_tile_start: one 64-bit record per view and 4x4 tile of lattice rays -- the sample intervals of the tile's rays (slab test, conservative
+    // for all 16) and the result of the tile's cone pre-march; five 12-bit fields, see tile_pack()
+    const u64* __restrict__ tile_rec;  // [n_views][tiles_y][tiles_x]
     int tiles_x, tiles_per_view;
     // outputs (may be null)
     int* depth;                        // [n_views][H][W]
@@ -658,25 +659,43 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
     if (a.pub.enabled) publish_view_row(a.pub, reinterpret_cast<u64*>(a.vis + (size_t)(unsigned)view * a.vis_stride32), view, gridDim.x * gridDim.y);
 }
 
-// ---- cone pre-march of 4x4-ray tiles: k_tile_start ------------------------------------------------------------------
-// The 16 rays of a 4x4 tile of the lattice leave the camera within a fraction of a degree of each other: up to the depth at which
-// the tile's footprint is a voxel or two wide they all cross the same empty space, and k_forward_line would make each of them
-// discover that for itself -- ~8 dependent probes per ray on the bench sweep, half of them far from any surface and therefore the
-// ones that miss L1 and L2.  Here ONE thread marches the tile's centre line Qc(k) on the distance bytes for all 16 rays:
-//   every sample k' of every ray of the tile lies within  rho(k') = A * z_k' + 3 * eps_q(view)  voxels (L-inf) of Qc(k'), where
-//   A = max_i |1/delta_i| * (|m_i0| * hw_x + |m_i1| * hw_y) and hw = half the tile's extent in (c-cx)/fx, (r-cy)/fy -- the rays'
-//   lines differ from the centre line by z * M * (ddx, ddy, 0) exactly, and each of {sample vs its line, its line in float, the
-//   centre line in float} is within eps_q(view) (k_view_start; the budget above k_forward_skip);
-//   a probe at k reads the byte d of the voxel V of Qc(k) (clamped into the grid; `disp` = how far it had to move): every grid
-//   voxel within d-1 of V is empty, and a point within R < d-1 of a point of V is in such a voxel.  Samples k .. k+n of all rays are
-//   within  disp + rho(k) + n * (max|QBc| + A * zdelta)  of Qc(k)'s clamped point, so they are misses (if they are in bounds at all)
-//   for  n = floor((d - 1 - 2^-8 - disp - rho(k)) / (max|QBc| + A * zdelta)), rounded down.
-// The march ends at the first probe that cannot advance; tile_k = that k: every IN-BOUNDS sample k' < tile_k of every ray of the
-// tile is a miss.  (Whether a sample is in bounds is still each ray's own business: k_forward_line only uses tile_k inside its slab
-// interval.)  It starts at the view's kstart (k_view_start: the probes before it are misses for every ray of the view); views
-// flagged kstart = -1 (eps_q > 0.1, non-finite poses) get tile_k = 0.  One thread per tile, 1/16 of the rays.
+// ---- per-tile prologue of the line march: k_tile_start ----------------------------------------------------------------
+// The 16 rays of a 4x4 tile of the lattice leave the camera within a fraction of a degree of each other.  What k_forward_line would
+// make each of them work out for itself is done here once per tile, by one thread (1/16 of the rays):
+//
+// (1) The sample intervals.  With the tile's centre line Qc(k) = QAc + k * QBc (voxel units), every ray's line differs from it by
+//     z_k * M * (ddx, ddy, 0) / delta exactly, |ddx| <= hw_x, |ddy| <= hw_y (half the tile's extent in (c-cx)/fx, (r-cy)/fy), so on
+//     axis i every ray's line point lies in Qc_i(k) +- (rho_i(k) + eps),  rho_i(k) = A_i * (z0 + k * zdelta),
+//     A_i = |1/delta_i| * (|m_i0| hw_x + |m_i1| hw_y), eps = 2 * eps_q(view) for the float evaluation of the two lines.
+//     "every ray's line is >= 0.25 voxel inside on axis i" and "some ray's line may be < 0.25 voxel outside" are then linear
+//     inequalities in k -- (QBc_i -+ A_i zdelta) k >= / <= const -- and intersecting them gives [kin, kout] (inner, a subset of
+//     every ray's own interval) and [k_begin, s_end) (outer, a superset), with the guard g(t) of k_forward_line.  Slopes too
+//     small to divide by make the inner interval empty and leave the outer one unconstrained.
+// (2) The cone pre-march.  Every sample k' of every ray of the tile lies within rho(k') = max_i rho_i(k') + 3 eps_q(view) of Qc(k')
+//     (sample vs its line, its line in float, the centre line in float: eps_q each).  A probe at k reads the byte d of the voxel V
+//     of Qc(k), clamped into the grid (`disp` = how far it had to move): every grid voxel within d-1 of V is empty, and a point
+//     within R < d-1 of a point of V is in such a voxel.  Samples k .. k+n of all 16 rays are within
+//     disp + rho(k) + n * (max|QBc| + A * zdelta) of the clamped point, so they are misses (if they are in bounds at all) for
+//     n = floor((d - 1 - 2^-8 - disp - rho(k)) / (max|QBc| + A * zdelta)).  The march ends at the first probe that cannot advance:
+//     every IN-BOUNDS sample k' < kt of every ray of the tile is a miss.  It starts at the view's kstart (k_view_start).
+//     Without it a ray spends ~7.3 dependent probes on the bench sweep, half of them far from any surface (the ones that miss L1
+//     and L2); with it 2.8.
+// Views flagged kstart = -1 (eps_q > 0.1, non-finite poses) get the record "evaluate every sample exactly".
 constexpr int TILE_RAYS = 4;
-__global__ void __launch_bounds__(128) k_tile_start(const FwdArgs a, int* __restrict__ tile_k) {
+__host__ __device__ __forceinline__ u64 tile_pack(int k_begin, int s_end, int kin, int kout, int kt) {      // all in [0, 4095]; kout stored + 1
+    return (u64)(unsigned)k_begin | ((u64)(unsigned)s_end << 12) | ((u64)(unsigned)kin << 24) | ((u64)(unsigned)(kout + 1) << 36) | ((u64)(unsigned)kt << 48);
+}
+// s * k >= r  folded into [lo, hi]; INNER: the interval must stay a subset (undecidable => empty), else a superset (=> unconstrained)
+template <bool INNER>
+__device__ __forceinline__ void tile_constrain(float& lo, float& hi, float s, float r) {
+    if (fabsf(s) > 1e-9f) {
+        const float t = __fdiv_rn(r, s);
+        if (s > 0.0f) lo = fmaxf(lo, t); else hi = fminf(hi, t);
+    } else if (INNER ? !(r < -1e-3f) : (r > 1e-3f)) lo = 3e30f;          // |s k| <= 1e-9 * 4096: the sign of r decides; in doubt, see above
+}
+__device__ __forceinline__ float tile_guard(float t) { return fmaf(fabsf(t), 3.814697265625e-06f, 0.015625f); }   // 2^-6 + |t| * 2^-18 samples
+
+__global__ void __launch_bounds__(128) k_tile_start(const FwdArgs a, u64* __restrict__ tile_rec) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (unsigned)a.tiles_per_view) return;
     const unsigned view = blockIdx.y;
@@ -684,27 +703,54 @@ __global__ void __launch_bounds__(128) k_tile_start(const FwdArgs a, int* __rest
     const float4* sp = a.viewrec + 4u * view;
     const float4 r0 = sp[0], r1 = sp[1], r2 = sp[2], r3 = sp[3];
     const int ks = __float_as_int(r3.y);
-    int kt = 0;
+    const int S = a.S;
+    u64 rec = tile_pack(0, S, S, -1, 0);                                             // every sample exactly
     if (ks >= 0) {
         const int tx = (int)(t % (unsigned)a.tiles_x), ty = (int)(t / (unsigned)a.tiles_x);
         const int c0 = tx * TILE_RAYS, c1 = min(c0 + TILE_RAYS - 1, a.Wc - 1), q0 = ty * TILE_RAYS, q1 = min(q0 + TILE_RAYS - 1, a.Hc - 1);
         const float xl = __ldg(a.dcx + c0), xh = __ldg(a.dcx + c1), yl = __ldg(a.dcy + q0), yh = __ldg(a.dcy + q1);
         const float xc = 0.5f * (xl + xh), yc = 0.5f * (yl + yh);
         const float hwx = fmaxf(fabsf(xl - xc), fabsf(xh - xc)) * 1.00001f, hwy = fmaxf(fabsf(yl - yc), fabsf(yh - yc)) * 1.00001f;
-        const float g0 = fmaf(r0.x, xc, fmaf(r0.y, yc, r0.z)), g1 = fmaf(r1.x, xc, fmaf(r1.y, yc, r1.z)), g2 = fmaf(r2.x, xc, fmaf(r2.y, yc, r2.z));
-        const float in0 = v.inv32[0], in1 = v.inv32[1], in2 = v.inv32[2];
-        const float qa0 = fmaf(fmaf(a.z0m, g0, r0.w), in0, v.c32[0]), qa1 = fmaf(fmaf(a.z0m, g1, r1.w), in1, v.c32[1]), qa2 = fmaf(fmaf(a.z0m, g2, r2.w), in2, v.c32[2]);
-        const float qb0 = a.zdm * g0 * in0, qb1 = a.zdm * g1 * in1, qb2 = a.zdm * g2 * in2;
-        const float A = fmaxf(fabsf(in0) * (fabsf(r0.x) * hwx + fabsf(r0.y) * hwy), fmaxf(fabsf(in1) * (fabsf(r1.x) * hwx + fabsf(r1.y) * hwy),
-                                                                                        fabsf(in2) * (fabsf(r2.x) * hwx + fabsf(r2.y) * hwy))) * 1.0001f;
-        const float grow = fmaxf(fabsf(qb0), fmaxf(fabsf(qb1), fabsf(qb2))) * 1.0001f + A * a.zdm * 1.0001f;     // growth of the bound per sample
+        const float m0[3] = {r0.x, r1.x, r2.x}, m1[3] = {r0.y, r1.y, r2.y}, m2[3] = {r0.z, r1.z, r2.z}, m3[3] = {r0.w, r1.w, r2.w};
+        float qa[3], qb[3], A3[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const float g = fmaf(m0[i], xc, fmaf(m1[i], yc, m2[i]));
+            qa[i] = fmaf(fmaf(a.z0m, g, m3[i]), v.inv32[i], v.c32[i]);
+            qb[i] = a.zdm * g * v.inv32[i];
+            A3[i] = fabsf(v.inv32[i]) * (fabsf(m0[i]) * hwx + fabsf(m1[i]) * hwy) * 1.0001f;
+        }
+        // ---- (1) sample intervals, conservative for the 16 rays ----
+        const float eps = 2.0f * r3.x;                                               // 2 * (eps_q(view) + 2^-10)
+        float ti0 = -1e30f, ti1 = 1e30f, to0 = -1e30f, to1 = 1e30f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const float as = A3[i] * a.zdm, bs = A3[i] * a.z0m + eps;                // rho_i(k) + eps = as * k + bs
+            tile_constrain<true>(ti0, ti1, qb[i] - as, 0.25f + bs - qa[i]);                       //  Qc - rho - eps >= 0.25
+            tile_constrain<true>(ti0, ti1, -(qb[i] + as), -(v.ext[i] - 0.25f - bs - qa[i]));      //  Qc + rho + eps <= ext - 0.25
+            tile_constrain<false>(to0, to1, qb[i] + as, -0.25f - bs - qa[i]);                     //  Qc + rho + eps >= -0.25
+            tile_constrain<false>(to0, to1, -(qb[i] - as), -(v.ext[i] + 0.25f + bs - qa[i]));     //  Qc - rho - eps <= ext + 0.25
+        }
+        const float Sf = a.Sf;
+        int k_begin = S, s_end = S, kin = S, kout = -1;
+        if (to0 <= to1) {
+            k_begin = (int)fminf(fmaxf(ceilf(to0 - tile_guard(to0)), 0.0f), Sf);
+            s_end = (int)fminf(fmaxf(floorf(to1 + tile_guard(to1)) + 1.0f, 0.0f), Sf);
+            if (ti0 <= ti1) {
+                kin = (int)fminf(fmaxf(ceilf(ti0 + tile_guard(ti0)), 0.0f), Sf);
+                kout = (int)fminf(fmaxf(floorf(ti1 - tile_guard(ti1)), -1.0f), Sf - 1.0f);
+            }
+        }
+        // ---- (2) cone pre-march ----
+        const float A = fmaxf(A3[0], fmaxf(A3[1], A3[2]));
+        const float grow = fmaxf(fabsf(qb[0]), fmaxf(fabsf(qb[1]), fabsf(qb[2]))) * 1.0001f + A * a.zdm * 1.0001f;     // growth of the bound per sample
         const float rgrow = 0.9999f / fmaxf(grow, 1e-3f);
         const float fixed = 1.0f + 0.00390625f + 3.0f * r3.x;                       // 1 + 2^-8 + 3 * (eps_q(view) + 2^-10)
         const float kM = 12582912.0f;
         const unsigned pnz = (unsigned)v.pdim[2];
-        float kf = (float)min(ks, a.S);
-        for (int it = 0; it < 64 && kf < a.Sf; it++) {
-            const float p0 = fmaf(kf, qb0, qa0), p1 = fmaf(kf, qb1, qa1), p2 = fmaf(kf, qb2, qa2);
+        float kf = (float)min(ks, S);
+        for (int it = 0; it < 64 && kf < Sf; it++) {
+            const float p0 = fmaf(kf, qb[0], qa[0]), p1 = fmaf(kf, qb[1], qa[1]), p2 = fmaf(kf, qb[2], qa[2]);
             const float l0 = fminf(fmaxf(p0, 0.0f), v.ext[0]), l1 = fminf(fmaxf(p1, 0.0f), v.ext[1]), l2 = fminf(fmaxf(p2, 0.0f), v.ext[2]);
             const float disp = fmaxf(fabsf(p0 - l0), fmaxf(fabsf(p1 - l1), fabsf(p2 - l2)));
             const unsigned bx = (unsigned)__float_as_int(__fadd_rd(l0, kM)), by = (unsigned)__float_as_int(__fadd_rd(l1, kM)), bz = (unsigned)__float_as_int(__fadd_rd(l2, kM));
@@ -715,9 +761,9 @@ __global__ void __launch_bounds__(128) k_tile_start(const FwdArgs a, int* __rest
             if (!(room >= 0.0f)) break;                                              // (NaN ends the march too)
             kf += floorf(room * rgrow) + 1.0f;
         }
-        kt = (int)fminf(kf, a.Sf);
+        rec = tile_pack(k_begin, s_end, kin, kout, (int)fminf(kf, Sf));
     }
-    tile_k[view * (unsigned)a.tiles_per_view + t] = kt;
+    tile_rec[view * (unsigned)a.tiles_per_view + t] = rec;
 }
 
 // ---- K1 on distance bytes, line-first: k_forward_line ------------------------------------------------------------
@@ -1032,19 +1078,17 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
     const VolDev& v = a.vol;
     const float kM = 12582912.0f;
     const int S = a.S;
-    // the tile's cone pre-march (k_tile_start): in-bounds samples before kt are misses for every ray of the 4x4 tile
-    int kt = 0;
-    if (a.tile_k) kt = __ldg(a.tile_k + ((unsigned)view * (unsigned)a.tiles_per_view + (unsigned)(ri / TILE_RAYS) * (unsigned)a.tiles_x + (unsigned)(ci / TILE_RAYS)));
-
-    // ---- per ray: the line and the sample intervals ----
+    // ---- per ray: the line; per tile (k_tile_start): the sample intervals and the first sample the cone pre-march could not prove a miss ----
+    const u64 rec = __ldg(a.tile_rec + ((unsigned)view * (unsigned)a.tiles_per_view + (unsigned)(ri / TILE_RAYS) * (unsigned)a.tiles_x + (unsigned)(ci / TILE_RAYS)));
     float qa0, qa1, qa2, qb0, qb1, qb2;
     float rq, c1;                                     // samples advanced after a probe with byte d >= 2: floor(d * rq + c1)
-    int k = 0, kin = 1, kout = 0, s_end = S;
-    int k_slab = 0;                                   // CARVE: first sample that can be in bounds (before the view-wide k0 skip)
+    int k = (int)((unsigned)rec & 0xFFFu), s_end = (int)(((unsigned)rec >> 12) & 0xFFFu), kin = (int)((unsigned)(rec >> 24) & 0xFFFu);
+    int kout = (int)((unsigned)(rec >> 36) & 0xFFFu) - 1;
+    const int kt = (int)((unsigned)(rec >> 48) & 0xFFFu);
+    const int k_slab = k;                             // CARVE: first sample that can be in bounds (before the view-wide k0 skip)
     unsigned n_inb = 0, n_exact = 0, n_f64 = 0, n_skip = 0;
     {
-        const float4 r0 = ldg_f4_volatile(sp), r1 = ldg_f4_volatile(sp + 1), r2 = ldg_f4_volatile(sp + 2), r3 = ldg_f4_volatile(sp + 3);
-        const int ks = __float_as_int(r3.y);          // -1: no skipping for this view; else leading probes no ray can hit
+        const float4 r0 = ldg_f4_volatile(sp), r1 = ldg_f4_volatile(sp + 1), r2 = ldg_f4_volatile(sp + 2);
         const float dcx = __ldg(a.dcx + ci), dcy = __ldg(a.dcy + ri);
         const float g0 = fmaf(r0.x, dcx, fmaf(r0.y, dcy, r0.z)), g1 = fmaf(r1.x, dcx, fmaf(r1.y, dcy, r1.z)), g2 = fmaf(r2.x, dcx, fmaf(r2.y, dcy, r2.z));
         const float z0m = a.z0m, zdm = a.zdm;
@@ -1053,36 +1097,8 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
         const float qbmax = fmaxf(fabsf(qb0), fmaxf(fabsf(qb1), fabsf(qb2)));
         rq = rcp_approx(fmaxf(qbmax, 1e-3f)) * 0.999999f;                           // <= 1000; rounded down: never over-skips
         c1 = fmaf(-1.25f, rq, 1.0f);
+        const int ks = __float_as_int(ldg_f4_volatile(sp + 3).y);                    // -1: no skipping for this view; else leading probes no ray can hit
         if (ks >= 0) {
-            // real-valued k intervals: [ti0, ti1] line >= 0.25 voxel inside on every axis; [to0, to1] line < 0.25 voxel outside.
-            // Per axis the outer interval is the inner one widened by 0.5 voxel = 0.5 * |1/qb| samples on each side.  An axis the
-            // ray is parallel to gets a huge finite "reciprocal": its interval becomes everything or nothing, as it should.
-            float ti0 = -1e30f, ti1 = 1e30f, to0 = -1e30f, to1 = 1e30f;
-            const float qa[3] = {qa0, qa1, qa2}, qb[3] = {qb0, qb1, qb2};
-#pragma unroll
-            for (int ax = 0; ax < 3; ax++) {
-                const float r = fabsf(qb[ax]) > 1e-12f ? rcp_approx(qb[ax]) : 1e30f;
-                const float ta = (0.25f - qa[ax]) * r, tb = (v.ext[ax] - 0.25f - qa[ax]) * r, w = 0.5f * fabsf(r);
-                const float lo = fminf(ta, tb), hi = fmaxf(ta, tb);
-                ti0 = fmaxf(ti0, lo); ti1 = fminf(ti1, hi);
-                to0 = fmaxf(to0, lo - w); to1 = fminf(to1, hi + w);
-            }
-            // The t's carry a relative error below 2^-21 (MUFU.RCP, one subtraction, one product), i.e. < 2^-9 sample for |t| <= 2^12 -- and
-            // S <= 1000, so larger |t| only meet the clamps.  Guard g(t) = 2^-6 + |t| * 2^-18 samples on each end: with the exact bounds t*,
-            // samples k < ceil(to0 - g) are < to0* (outside), k >= floor(to1 + g) + 1 are > to1* (outside), and ceil(ti0 + g) <= k <=
-            // floor(ti1 - g) are inside [ti0*, ti1*].  (Round 1 used a whole sample of guard per end: 4-5 exactly evaluated samples in the
-            // band where a ray leaves the volume instead of 1-2 -- a third of all exact evaluations of the bench sweep.)
-            const float Sf = a.Sf;
-            if (!(to0 <= to1)) { k = S; if (CARVE) k_slab = S; }                     // never inside: every sample fails validPoints
-            else {
-                k = (int)fminf(fmaxf(ceilf(to0 - fmaf(fabsf(to0), 3.814697265625e-06f, 0.015625f)), 0.0f), Sf);
-                if (CARVE) k_slab = k;
-                s_end = (int)fminf(fmaxf(floorf(to1 + fmaf(fabsf(to1), 3.814697265625e-06f, 0.015625f)) + 1.0f, 0.0f), Sf);
-                if (ti0 <= ti1) {
-                    kin = (int)fminf(fmaxf(ceilf(ti0 + fmaf(fabsf(ti0), 3.814697265625e-06f, 0.015625f)), 0.0f), Sf);
-                    kout = (int)fminf(fmaxf(floorf(ti1 - fmaf(fabsf(ti1), 3.814697265625e-06f, 0.015625f)), -1.0f), Sf - 1.0f);
-                }
-            }
             const int k0 = min(ks, S);
             k = max(k, k0);
             n_inb = n_skip = (unsigned)k0;                                            // k0 > 0 only when the camera sits inside the volume
