@@ -201,8 +201,6 @@ int set_volume_geometry(dmf_ctx* c, const double bounds[6], const double delta[3
 // already hold the volume ON THE DEVICE (uploaded by the host, produced by K0, or received from a peer GPU).
 // Out: bit grid, macro-cell bits + clearance, rank directory, rank -> ordinal table, centroid hashes, cleared marks.
 // One synchronisation at the end (the error words).  Timed with CUDA events: dmf_volume_prepare_ms.
-void drop_bytes_texture(dmf_ctx* c);
-
 int build_volume_device(dmf_ctx* c, size_t n_occ, size_t n_normals) {
     VolDev& v = c->vol;
     cudaStream_t st = c->stream;
@@ -222,7 +220,6 @@ int build_volume_device(dmf_ctx* c, size_t n_occ, size_t n_normals) {
     v.bits = c->d_bricks.as<unsigned>(); v.prefix = c->d_prefix.as<unsigned>(); v.rank2occ = c->d_rank2occ.as<unsigned>(); v.macro = c->d_macro.as<unsigned>();
     v.noff = c->d_noff.as<unsigned>(); v.normals = c->d_normals.as<float>(); v.occ_ids = c->d_occ_ids.as<u64>();
     v.bytes = nullptr; v.n_occ = (int)n_occ; v.n_cells = (unsigned)nbits;
-    drop_bytes_texture(c);
     c->n_occ = n_occ; c->n_normals = n_normals;
     c->bytes_built = false; c->auto_uses = 0; c->volume_epoch++;
     c->n_grid_words = nwords; c->observed_ready = false;     // a new volume starts unobserved
@@ -336,40 +333,6 @@ __global__ void k_observed_counts(const unsigned* __restrict__ obs, const unsign
     if ((threadIdx.x & 31) == 0) { if (n_obs) atomicAdd(out, n_obs); if (n_hit) atomicAdd(out + 1, n_hit); }
 }
 
-void drop_bytes_texture(dmf_ctx* c) {
-    if (c->bytes_texobj) { cudaDestroyTextureObject(c->bytes_texobj); c->bytes_texobj = 0; }
-    if (c->bytes_arr) { cudaFreeArray(c->bytes_arr); c->bytes_arr = nullptr; }
-    c->vol.bytes_tex = 0; alloc_generation()++;
-}
-
-// The distance bytes once more as a 3-D CUDA array (block-linear: a 32-byte sector holds a small brick of voxels, not 32 voxels
-// along z) behind a texture object: point sampling with unnormalised coordinates floors the line point and clamps it into the
-// grid in the texture unit, so a line probe is 3 FMAs + one TEX.  tex x = voxel z (the contiguous axis), tex z = voxel x.
-// Measured (profiles/r02_line_texture_ab.txt): 9 % SLOWER than the plain byte load -- fewer instructions, but the longer TEX
-// latency sits in the dependent chain of every probe -- so the array is only built in a -DDMF_LINE_TEX=1 build.
-int build_bytes_texture(dmf_ctx* c, cudaStream_t st) {
-    drop_bytes_texture(c);
-#if !DMF_LINE_TEX
-    (void)st;
-    return 0;
-#endif
-    const VolDev& v = c->vol;
-    cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
-    cudaExtent ext = make_cudaExtent((size_t)v.pdim[2], (size_t)v.pdim[1], (size_t)v.pdim[0]);
-    DMF_CUDA(cudaMalloc3DArray(&c->bytes_arr, &desc, ext));
-    cudaMemcpy3DParms cp; std::memset(&cp, 0, sizeof cp);
-    cp.srcPtr = make_cudaPitchedPtr(c->d_bytes.p, (size_t)v.pdim[2], (size_t)v.pdim[2], (size_t)v.pdim[1]);
-    cp.dstArray = c->bytes_arr; cp.extent = ext; cp.kind = cudaMemcpyDeviceToDevice;
-    DMF_CUDA(cudaMemcpy3DAsync(&cp, st));
-    cudaResourceDesc rd; std::memset(&rd, 0, sizeof rd); rd.resType = cudaResourceTypeArray; rd.res.array.array = c->bytes_arr;
-    cudaTextureDesc td; std::memset(&td, 0, sizeof td);
-    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
-    DMF_CUDA(cudaCreateTextureObject(&c->bytes_texobj, &rd, &td, nullptr));
-    c->vol.bytes_tex = (unsigned long long)c->bytes_texobj;
-    return 0;
-}
-
 // DMF_GRID_BYTE: the per-voxel Chebyshev distance bytes (dmf_distance.cuh), built on first use
 int ensure_bytes(dmf_ctx* c, cudaStream_t st) {
     if (c->bytes_built) return 0;
@@ -383,7 +346,6 @@ int ensure_bytes(dmf_ctx* c, cudaStream_t st) {
     k_dt_z<<<blocks_for(nlines, 8, 148 * 32), 256, 0, st>>>(v, bytes);
     k_dt_lines<1, false, false, EncodeNone><<<blocks_for((size_t)v.pdim[0] * v.pdim[2], 128, 148 * 32), 128, 0, st>>>(bytes, tmp, v.pdim[0], v.pdim[1], v.pdim[2], EncodeNone());
     k_dt_lines<0, false, true, EncodeNone><<<blocks_for((size_t)v.pdim[1] * v.pdim[2], 128, 148 * 32), 128, 0, st>>>(tmp, bytes, v.pdim[0], v.pdim[1], v.pdim[2], EncodeNone());
-    DMF_TRY(build_bytes_texture(c, st));
     DMF_CUDA(cudaEventRecord(c->ev_b1, st));
     c->launches += 3;
     cudaError_t e = cudaGetLastError();
@@ -651,7 +613,6 @@ void dmf_destroy(dmf_ctx* c) {
                       &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters,
                       &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err, &c->d_tile_rec};
     c->graph_fwd_ids.drop(); c->graph_rev_ids.drop();
-    drop_bytes_texture(c);
     for (auto* b : bufs) b->release();
     c->stage.release();
     for (int i = 0; i < 2; i++) for (int j = 0; j < 8; j++) c->d_out[i][j].release();

@@ -118,10 +118,6 @@ __device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn
 //            (DMF_GRID_BYTE, dmf_distance.cuh)
 //   macro    1 bit per 8x8x8-voxel macro cell: "contains an occupied voxel" (empty-space skipping)
 //   noff/normals  CSR of Voxel::normals in occupied order
-#ifndef DMF_LINE_TEX
-#define DMF_LINE_TEX 0     // 1: the line probes of k_forward_line read the distance bytes through vol.bytes_tex (a recorded experiment: slower)
-#endif
-
 struct VolDev {
     const unsigned* __restrict__ bits;
     const unsigned* __restrict__ prefix;
@@ -150,7 +146,6 @@ struct VolDev {
     float rev_eps[3]; // bound (voxel units) on |reverse-march sample - its line point|; > 0.1 disables skipping there
     float rev_esafe;  // a line point at least this far from every face of its voxel shares the voxel with the reference's sample
     float ext[3];    // >= (vmax-vmin)/delta: the volume's extent in voxel units (dim <= ext < dim+1, constructVolume truncates)
-    unsigned long long bytes_tex;   // cudaTextureObject_t over a 3-D array copy of `bytes` (point sampling, unnormalised, clamped); 0 = none
 };
 
 // The distance bytes hold the distance to the nearest OCCUPIED voxel only (dmf_distance.cuh).  A march that counts the samples it

@@ -86,6 +86,9 @@ __global__ void k_build_tables(float* xtab, float* ytab, float* ztab, float* dcx
     }
 }
 
+#ifndef DMF_VIS_READ_FIRST
+#define DMF_VIS_READ_FIRST 0                      // 1: read the visibility word before the atomicOr and skip it if the bit is set (measured 1.6 % slower:
+#endif                                            //    the read is one more dependent L2 round trip at the very end of the warp's life)
 // Per-ray epilogue shared by k_forward and k_forward_skip: outputs, visibility, marks, discovery keys, counters.
 template <int MODE>
 __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long long* s_cnt, int view, int ci, int ri, bool active, int hit_k,
@@ -149,7 +152,11 @@ __device__ __forceinline__ void forward_epilogue(const FwdArgs& a, unsigned long
             if (emit && (unsigned)(threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
                 unsigned* w = a.vis + ((size_t)(unsigned)view * a.vis_stride32 + ((unsigned)occ >> 5));
                 const unsigned m = 1u << (occ & 31);
+#if DMF_VIS_READ_FIRST
                 if (!(*w & m)) atomicOr(w, m);
+#else
+                atomicOr(w, m);
+#endif
             }
         }
         if (active && a.ray_key) {
@@ -673,29 +680,34 @@ __global__ void __launch_bounds__(SKIP_THREADS, 10) k_forward_dist(const FwdArgs
 //     small to divide by make the inner interval empty and leave the outer one unconstrained.
 // (2) The cone pre-march.  Every sample k' of every ray of the tile lies within rho(k') = max_i rho_i(k') + 3 eps_q(view) of Qc(k')
 //     (sample vs its line, its line in float, the centre line in float: eps_q each).  A probe at k reads the byte d of the voxel V
-//     of Qc(k), clamped into the grid (`disp` = how far it had to move): every grid voxel within d-1 of V is empty, and a point
-//     within R < d-1 of a point of V is in such a voxel.  Samples k .. k+n of all 16 rays are within
-//     disp + rho(k) + n * (max|QBc| + A * zdelta) of the clamped point, so they are misses (if they are in bounds at all) for
-//     n = floor((d - 1 - 2^-8 - disp - rho(k)) / (max|QBc| + A * zdelta)).  The march ends at the first probe that cannot advance:
-//     every IN-BOUNDS sample k' < kt of every ray of the tile is a miss.  It starts at the view's kstart (k_view_start).
+//     of Qc(k): every grid voxel within d-1 of V is empty, and a point within R < d-1 of a point of V is in such a voxel.  Samples
+//     k .. k+n of all 16 rays are within rho(k) + n * (max|QBc| + A * zdelta) of Qc(k), so they are misses for
+//     n = floor((d - 1 - 2^-8 - rho(k)) / (max|QBc| + A * zdelta)).  The march runs inside [kin, kout] (where Qc(k) is inside the grid),
+//     from max(kin, kstart of the view) to the first probe that cannot advance: every sample k' in [kin, kt) of every ray is a miss.
 //     Without it a ray spends ~7.3 dependent probes on the bench sweep, half of them far from any surface (the ones that miss L1
 //     and L2); with it 2.8.
 // Views flagged kstart = -1 (eps_q > 0.1, non-finite poses) get the record "evaluate every sample exactly".
 constexpr int TILE_RAYS = 4;
+#ifndef DMF_TILE_MIN_BLOCKS
+#define DMF_TILE_MIN_BLOCKS 16                    // k_tile_start is a chain of dependent far-field probes: occupancy is what hides them
+#endif
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __host__ __device__ __forceinline__ u64 tile_pack(int k_begin, int s_end, int kin, int kout, int kt) {      // all in [0, 4095]; kout stored + 1
     return (u64)(unsigned)k_begin | ((u64)(unsigned)s_end << 12) | ((u64)(unsigned)kin << 24) | ((u64)(unsigned)(kout + 1) << 36) | ((u64)(unsigned)kt << 48);
 }
 // s * k >= r  folded into [lo, hi]; INNER: the interval must stay a subset (undecidable => empty), else a superset (=> unconstrained)
 template <bool INNER>
-__device__ __forceinline__ void tile_constrain(float& lo, float& hi, float s, float r) {
-    if (fabsf(s) > 1e-9f) {
-        const float t = __fdiv_rn(r, s);
-        if (s > 0.0f) lo = fmaxf(lo, t); else hi = fminf(hi, t);
-    } else if (INNER ? !(r < -1e-3f) : (r > 1e-3f)) lo = 3e30f;          // |s k| <= 1e-9 * 4096: the sign of r decides; in doubt, see above
+__device__ __forceinline__ void tile_constrain(float& lo, float& hi, float s, float r) {      // branch-free: 12 of these per tile
+    const bool div = fabsf(s) > 1e-9f;
+    const float t = r * rcp_approx(div ? s : 1.0f);                        // relative error < 2^-21: inside tile_guard()
+    lo = (div && s > 0.0f) ? fmaxf(lo, t) : lo;
+    hi = (div && s < 0.0f) ? fminf(hi, t) : hi;
+    // |s k| <= 1e-9 * 4096: the sign of r decides; in doubt, see above
+    lo = (!div && (INNER ? !(r < -1e-3f) : (r > 1e-3f))) ? 3e30f : lo;
 }
 __device__ __forceinline__ float tile_guard(float t) { return fmaf(fabsf(t), 3.814697265625e-06f, 0.015625f); }   // 2^-6 + |t| * 2^-18 samples
 
-__global__ void __launch_bounds__(128) k_tile_start(const FwdArgs a, u64* __restrict__ tile_rec) {
+__global__ void __launch_bounds__(128, DMF_TILE_MIN_BLOCKS) k_tile_start(const FwdArgs a, u64* __restrict__ tile_rec) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (unsigned)a.tiles_per_view) return;
     const unsigned view = blockIdx.y;
@@ -741,25 +753,26 @@ __global__ void __launch_bounds__(128) k_tile_start(const FwdArgs a, u64* __rest
                 kout = (int)fminf(fmaxf(floorf(ti1 - tile_guard(ti1)), -1.0f), Sf - 1.0f);
             }
         }
-        // ---- (2) cone pre-march ----
+        // ---- (2) cone pre-march, inside [kin, kout] only: there every ray's line -- and so the centre line -- is >= 0.25 voxel inside the
+        // volume, the probed voxel needs no clamping, and k_forward_line uses the result nowhere else (the samples of [kin, kstart) are
+        // misses by k_view_start's proof) ----
         const float A = fmaxf(A3[0], fmaxf(A3[1], A3[2]));
         const float grow = fmaxf(fabsf(qb[0]), fmaxf(fabsf(qb[1]), fabsf(qb[2]))) * 1.0001f + A * a.zdm * 1.0001f;     // growth of the bound per sample
         const float rgrow = 0.9999f / fmaxf(grow, 1e-3f);
-        const float fixed = 1.0f + 0.00390625f + 3.0f * r3.x;                       // 1 + 2^-8 + 3 * (eps_q(view) + 2^-10)
-        const float kM = 12582912.0f;
+        const float rc0 = 1.0f + 0.00390625f + 3.0f * r3.x + A * a.z0m, c1n = -(A * a.zdm);   // room(k) = d - rc0 + c1n * k;  1 + 2^-8 + 3 * (eps_q(view) + 2^-10) + rho(0)
+        const float kM = 12582912.0f, koutf = (float)kout;
         const unsigned pnz = (unsigned)v.pdim[2];
-        float kf = (float)min(ks, S);
-        for (int it = 0; it < 64 && kf < Sf; it++) {
-            const float p0 = fmaf(kf, qb[0], qa[0]), p1 = fmaf(kf, qb[1], qa[1]), p2 = fmaf(kf, qb[2], qa[2]);
-            const float l0 = fminf(fmaxf(p0, 0.0f), v.ext[0]), l1 = fminf(fmaxf(p1, 0.0f), v.ext[1]), l2 = fminf(fmaxf(p2, 0.0f), v.ext[2]);
-            const float disp = fmaxf(fabsf(p0 - l0), fmaxf(fabsf(p1 - l1), fabsf(p2 - l2)));
-            const unsigned bx = (unsigned)__float_as_int(__fadd_rd(l0, kM)), by = (unsigned)__float_as_int(__fadd_rd(l1, kM)), bz = (unsigned)__float_as_int(__fadd_rd(l2, kM));
+        float kf = (float)max(min(ks, S), kin);
+        for (int it = 0; it < 64 && kf <= koutf; it++) {
+            const unsigned bx = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb[0], qa[0]), kM));
+            const unsigned by = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb[1], qa[1]), kM));
+            const unsigned bz = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb[2], qa[2]), kM));
             unsigned lidx = bx * a.pnyz + (by * pnz + (bz - a.bias));
             DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
-            const float d = (float)__ldg(v.bytes + min(lidx, a.last));
-            const float room = d - fixed - disp - A * fmaf(kf, a.zdm, a.z0m);
+            const unsigned d = __ldg(v.bytes + min(lidx, a.last));                   // (the clamp is a seat belt, never active)
+            const float room = fmaf(c1n, kf, (__int_as_float(0x4B000000 | (int)d) - 8388608.0f) - rc0);
             if (!(room >= 0.0f)) break;                                              // (NaN ends the march too)
-            kf += floorf(room * rgrow) + 1.0f;
+            kf += (__fadd_rd(room * rgrow, kM) - kM) + 1.0f;                         // floor(room / growth) more samples, and this one
         }
         rec = tile_pack(k_begin, s_end, kin, kout, (int)fminf(kf, Sf));
     }
@@ -787,7 +800,10 @@ __global__ void __launch_bounds__(128) k_tile_start(const FwdArgs a, u64* __rest
 //     block's largest |QB| (rays of a 16x8 pixel tile are within ~1 degree, so the common rate costs < 2 % of jump length);
 //     entries 0 and 1 hold 2^20, which ends the loop through the same comparison as running past kout;
 //   * reciprocals are MUFU approximations: they only steer conservative bounds that carry a whole sample of guard.
-constexpr int LINE_MIN_BLOCKS = 16;
+#ifndef DMF_LINE_MIN_BLOCKS
+#define DMF_LINE_MIN_BLOCKS 16
+#endif
+constexpr int LINE_MIN_BLOCKS = DMF_LINE_MIN_BLOCKS;
 constexpr float LINE_EXACT_FLAG = 1048576.0f;      // 2^20, far above any sample index or jump (<= 254 * 1000 + 1)
 
 // a 16-byte read of the per-view record at the point of use (volatile: the compiler must not keep the 12 pose floats live through the
@@ -797,7 +813,6 @@ __device__ __forceinline__ float4 ldg_f4_volatile(const float4* p) {
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // ---- carve mode on the line (DMF_FWD_CARVE) -----------------------------------------------------------------------
 // Every in-bounds sample a ray visits, up to and including its first hit, sets the bit of its voxel in a.observed.  Which
@@ -1133,30 +1148,6 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
                     const int cur = *((volatile int*)(a.min_depth + view));
                     if (a.z0 + (int)kf * a.zdelta > cur) { stop = true; break; }
                 }
-#if DMF_LINE_TEX
-                // the probe through the texture unit: point sampling floors the line point (to within 2^-8 voxel, which the 0.05 voxel of
-                // slack in the 1.25 absorbs: the sample is still in the fetched voxel or one next to it) -- 3 FMAs + TEX.  Bytes 0 and 1 are
-                // re-read from the linear grid at the exactly floored index, because what happens then depends on WHICH voxel it is.
-                const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
-                unsigned d = tex3D<unsigned char>((cudaTextureObject_t)v.bytes_tex, q2, q1, q0);
-#ifdef DMF_LINE_STATS
-                n_f64++;
-#endif
-                float adv;
-                if (d >= 2u) adv = __fadd_rd(fmaf(__int_as_float(0x4B000000 | (int)d) - 8388608.0f, rq, c1), kM) - kM;
-                else {
-                    const float s0 = __fadd_rd(q0, kM), s1 = __fadd_rd(q1, kM), s2 = __fadd_rd(q2, kM);
-                    unsigned lidx = (unsigned)__float_as_int(s0) * pnyz + ((unsigned)__float_as_int(s1) * pnz + ((unsigned)__float_as_int(s2) - bias));
-                    DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
-                    d = __ldg(gbytes + min(lidx, last));
-                    adv = d >= 2u ? __fadd_rd(fmaf(__int_as_float(0x4B000000 | (int)d) - 8388608.0f, rq, c1), kM) - kM : LINE_EXACT_FLAG;
-                    if (d == 1u) {
-                        const float f0 = q0 - (s0 - kM), f1 = q1 - (s1 - kM), f2 = q2 - (s2 - kM);
-                        const float e = ldg_f4_volatile(sp + 3).x;     // e_safe = eps_q of the view + 2^-10 voxel of slack
-                        if (fminf(f0, fminf(f1, f2)) >= e && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e) adv = 1.0f;
-                    }
-                }
-#else
                 const unsigned bx = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb0, qa0), kM));
                 const unsigned by = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb1, qa1), kM));
                 const unsigned bz = (unsigned)__float_as_int(__fadd_rd(fmaf(kf, qb2, qa2), kM));
@@ -1176,12 +1167,14 @@ __global__ void __launch_bounds__(SKIP_THREADS, CARVE ? CARVE_MIN_BLOCKS : LINE_
                     // Next to an occupied voxel, but this voxel itself is empty.  If the line point is
                     // at least e_safe (> eps_q) away from every face of its voxel, the reference's sample is in the same voxel:
                     // an in-bounds miss (the line is >= 0.25 voxel inside the volume here).  Otherwise evaluate exactly.
+                    // (Resolving d == 0 here as well -- "the sample is in this occupied voxel: a hit, work out its exact position after the
+                    // march" -- was measured 4 % SLOWER: ~1.2 % of the face tests fail, i.e. some lane of most warps still takes the exact
+                    // path, so the warp pays for both.)
                     const float q0 = fmaf(kf, qb0, qa0), q1 = fmaf(kf, qb1, qa1), q2 = fmaf(kf, qb2, qa2);
                     const float f0 = q0 - (__fadd_rd(q0, kM) - kM), f1 = q1 - (__fadd_rd(q1, kM) - kM), f2 = q2 - (__fadd_rd(q2, kM) - kM);
                     const float e = ldg_f4_volatile(sp + 3).x;     // e_safe = eps_q of the view + 2^-10 voxel of slack
                     if (fminf(f0, fminf(f1, f2)) >= e && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e) adv = 1.0f;
                 }
-#endif
                 kf += adv;
                 if (!(kf <= koutf)) break;
             }

@@ -175,8 +175,6 @@ struct dmf_ctx {
     dmf::DevBuf d_bricks /* bit grid words */, d_macro, d_prefix, d_rank2occ, d_bytes, d_noff, d_normals, d_occ_ids, d_centroid_hash;
     bool bytes_built = false;
     dmf::DevBuf d_tile_rec;                     // k_tile_start: [n_views][tiles] 64-bit records (sample intervals + cone pre-march) read by k_forward_line
-    cudaArray_t bytes_arr = nullptr;            // block-linear 3-D copy of d_bytes behind vol.bytes_tex (the line probes of the marches)
-    cudaTextureObject_t bytes_texobj = 0;
     int auto_uses = 0;                    // forward calls with DMF_GRID_AUTO since the volume was uploaded
     int reverse_format = DMF_GRID_BYTE;   // grid the reverse march probes (dmf_set_reverse_format)
     dmf::DevBuf d_view_mark, d_good_bits, d_first_view;
