@@ -448,18 +448,26 @@ int sweep_run(dmf_comm* g, const SweepSpec& spec, const float* host_poses, const
     for (size_t i = 0; i < g->m.size(); i++) {
         CommMember& mm = g->m[i];
         cudaStream_t st = streams && streams[i] ? (cudaStream_t)streams[i] : mm.ctx->stream;
-        if (g->exchange != 1) DMF_TRY(comm_wait(g, mm, kFlagGather, g->seq, st));
-        if (!out) continue;
         DMF_CUDA(cudaSetDevice(mm.ctx->device));
         const u64* rows = (const u64*)(mm.arena + off_gather(g, g->last_parity));
         // a single process sends every member's own rows over that member's own PCIe link; one process per GPU copies its own rows
         // or (DMF_SWEEP_ROWS_ALL) the whole gathered array
-        const bool all = !g->single_process && out->rows_to_host == DMF_SWEEP_ROWS_ALL;
-        const int r0 = all ? 0 : mm.rank, step = all ? 1 : g->world, cnt = all ? n_views : mm.n_my;
-        if (cnt > 0 && out->visibility && vw)
-            DMF_CUDA(cudaMemcpy2DAsync(out->visibility + (size_t)r0 * vw, (size_t)step * vw * 8, rows + (size_t)r0 * rw, (size_t)step * rw * 8, vw * 8, (size_t)cnt, cudaMemcpyDeviceToHost, st));
-        if (cnt > 0 && out->found_any)     // the low half of each row's extra word
-            DMF_CUDA(cudaMemcpy2DAsync(out->found_any + r0, (size_t)step * 4, rows + (size_t)r0 * rw + vw, (size_t)step * rw * 8, 4, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+        const bool all = out && !g->single_process && out->rows_to_host == DMF_SWEEP_ROWS_ALL;
+        auto rows_to_host = [&]() -> int {
+            const int r0 = all ? 0 : mm.rank, step = all ? 1 : g->world, cnt = all ? n_views : mm.n_my;
+            if (cnt > 0 && out->visibility && vw)
+                DMF_CUDA(cudaMemcpy2DAsync(out->visibility + (size_t)r0 * vw, (size_t)step * vw * 8, rows + (size_t)r0 * rw, (size_t)step * rw * 8, vw * 8, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+            if (cnt > 0 && out->found_any)     // the low half of each row's extra word
+                DMF_CUDA(cudaMemcpy2DAsync(out->found_any + r0, (size_t)step * 4, rows + (size_t)r0 * rw + vw, (size_t)step * rw * 8, 4, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+            return 0;
+        };
+        // A member's OWN rows are final as soon as its march (and push kernel) is: they go to the host before the stream waits for the
+        // peers' rows, so the copy overlaps that wait -- and the ranks' copies, which share the host's memory path, spread out in time.
+        // (The NCCL exchange interleaves the rows into view order after the all-gather: there the copy has to follow it.)
+        const bool early = out && !all && g->exchange != 1;
+        if (early) DMF_TRY(rows_to_host());
+        if (g->exchange != 1) DMF_TRY(comm_wait(g, mm, kFlagGather, g->seq, st));
+        if (out && !early) DMF_TRY(rows_to_host());
     }
     if (out) for (size_t i = 0; i < g->m.size(); i++) {
         cudaStream_t st = streams && streams[i] ? (cudaStream_t)streams[i] : g->m[i].ctx->stream;
