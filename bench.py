@@ -641,7 +641,8 @@ def run_config2(args):
                          "traffic": None if not traffic else traffic.get("dram_bytes_per_view", 0) * V,
                          "traffic_source": None if not traffic else traffic.get("source"),
                          "peak_source": peak_src, "kernel": "k_forward" if args.no_skip else (("k_forward_dist" if args.two_probe else "k_forward_line") if fmt == D.GRID_BYTE else "k_forward_skip"),
-                         "achieved_dram": None if not traffic else traffic.get("dram_bytes_per_view", 0) * V / (hot * 1e-3) / 1e9, "kernel_ms": hot, "algorithmic_bytes_per_launch": alg_bytes,
+                         "achieved_dram": None if not traffic else traffic.get("dram_bytes_per_view", 0) * V / (hot * 1e-3) / 1e9, "kernel_ms": hot, "kernel_ms_covers": "k_view_start + k_tile_start + the march kernel of one step (CUDA events inside the library around the three launches; the march kernel alone is ~90 % of it)",
+                         "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "algorithmic bytes are SURVEY 8(d)'s reference-equivalent ones (1 B per in-bounds sample of the reference + the per-ray and per-view outputs); the kernel proves ~98 % of those samples empty from one distance byte each without touching memory, so frac can exceed 1 and is not an HBM utilisation: achieved_dram (measured DRAM bytes / kernel time) is. The kernel is issue-bound, see DESIGN.md section 5"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": V * 48, "d2h_bytes_per_step": V * (vw * 8 + 4), "steps": e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "bytes_are": "per rank",

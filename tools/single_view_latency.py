@@ -5,7 +5,7 @@ import numpy as np, dmf_b200 as D
 sc = D.scenes.scene("S512"); ctx = D.Context.default(0)
 gv = D.VoxelVolume(ctx); gv.setDimensions(*sc.bounds); gv.setVolumeSize(*sc.dims); gv.constructVolume(); gv.integratePointCloud(sc.points, sc.normals)
 eng = D.RayTracingEngine(D.Camera(D.scenes.REFERENCE_K), ctx, D.GRID_BYTE)
-poses = D.scenes.bench_poses(1.0, 32)
+poses = np.ascontiguousarray(D.scenes.poses_sphere_lookat(1.0, 1024)[::8][:32]) if len(sys.argv) > 1 and sys.argv[1] == "spread" else D.scenes.bench_poses(1.0, 32)
 for want in (("ids",), ("visibility",), ("depth",), ()):
     for _ in range(3): eng.forward_views(gv, poses[:1], 0, 2, False, want=want)
     t = time.perf_counter()
