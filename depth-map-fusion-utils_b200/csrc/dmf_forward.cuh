@@ -790,16 +790,19 @@ __global__ void __launch_bounds__(128, DMF_TILE_MIN_BLOCKS) k_tile_start(const F
 //   d <= 1: next to an occupied voxel: the sample is evaluated exactly (tables, the reference's float expression, the
 //           exact voxel index), as k_forward does -- unless the line point is far enough from every face of its voxel.
 // The line is only consulted for k in [kin, kout], where it is >= 0.25 voxel inside the volume on every axis (slab test,
-// once per ray) so its voxel is addressable; samples that are provably outside (line > 0.25 voxel beyond a face) are
-// dropped without evaluation, and the thin bands in between are evaluated exactly.  Views whose eps_q exceeds 0.1 voxel
-// (or NaN/inf poses; k_view_start flags them with kstart = -1) evaluate every sample exactly.
-// The kernel is issue-bound (ncu: > 80 % issue-active), so the code below counts instructions:
-//   * the pose lives in shared memory and is re-read with vector loads where the (rare) exact path needs it, instead of
-//     pinning 12 registers through the line loop (16 blocks of 128 threads = all 64 warp slots of an SM; measured 9 % faster than 12 blocks / 40 registers);
-//   * "samples advanced after a probe with byte d" comes from a 256-entry shared table built once per block from the
-//     block's largest |QB| (rays of a 16x8 pixel tile are within ~1 degree, so the common rate costs < 2 % of jump length);
-//     entries 0 and 1 hold 2^20, which ends the loop through the same comparison as running past kout;
-//   * reciprocals are MUFU approximations: they only steer conservative bounds that carry a whole sample of guard.
+// once per 4x4-ray tile: k_tile_start) so its voxel is addressable; samples that are provably outside (line > 0.25 voxel
+// beyond a face) are dropped without evaluation, and the thin bands in between are evaluated exactly.  Views whose eps_q
+// exceeds 0.1 voxel (or NaN/inf poses; k_view_start flags them with kstart = -1) evaluate every sample exactly.
+// The first line probe of a ray goes to the tile's kt: the cone pre-march of k_tile_start has proven everything before it empty.
+// The kernel is issue- and latency-bound at once (ncu: > 80 % issue-active with all 64 warp slots of an SM in use, the top
+// stall on the consumer of the distance-byte load), so the code below counts instructions AND registers:
+//   * the pose is re-read from the view's 64-byte record with 16-byte loads where the (rare) exact path needs it, instead of
+//     pinning 12 registers through the line loop (16 blocks of 128 threads at 32 registers; 12 blocks at 40 registers without
+//     spills measured 8 % slower, 10 at 48: 18 %);
+//   * "samples advanced after a probe with byte d" is floor(d * rq + c1) from the ray's own slope: 5 FMA-pipe instructions,
+//     (float)d from the 0x4B000000 | d trick; d <= 1 yields 2^20, which ends the loop through the same comparison as running
+//     past kout;
+//   * reciprocals are MUFU approximations: they only steer conservative bounds.
 #ifndef DMF_LINE_MIN_BLOCKS
 #define DMF_LINE_MIN_BLOCKS 16
 #endif
