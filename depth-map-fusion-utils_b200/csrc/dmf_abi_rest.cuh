@@ -21,6 +21,8 @@ int fill_rev_args(dmf_ctx* c, RevArgs& a) {
     a.emit_list = nullptr; a.emit_count = nullptr; a.emit_cap = 0; a.zbuf = nullptr;
     a.counters = c->d_counters.as<u64>();
     a.step_cap = 1000000;
+    a.pnyz = (unsigned)c->vol.pdim[1] * (unsigned)c->vol.pdim[2];
+    a.bias = 0x4B400000u * (a.pnyz + (unsigned)c->vol.pdim[2] + 1u);
     return 0;
 }
 

@@ -108,6 +108,7 @@ struct RevArgs {
     int* zbuf;                             // [H*W] (z-buffer)
     u64* counters;
     int step_cap;
+    unsigned pnyz, bias;                   // pdim_y * pdim_z;  0x4B400000 * (pnyz + pdim_z + 1): the three shifter offsets of a line probe's index, folded on the host
 };
 
 __device__ __forceinline__ void camera_pixel(const RevArgs& a, float xx, float yy, float zz, int& r, int& c) {   // deProjectPoint, Camera.hpp:32-38
@@ -133,7 +134,7 @@ __device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float
     // the fast a/1000 is exact only for |a| >= 2^-100 (dmf_device.cuh); a = v_i * depth with depth >= 1
     const bool fast_div = fminf(fabsf(vx), fminf(fabsf(vy), fabsf(vz))) >= 7.888609052210118e-31f;
     const float step = fmaxf(fabsf(vx) * fabsf(in0), fmaxf(fabsf(vy) * fabsf(in1), fabsf(vz) * fabsf(in2))) * 0.001f;   // voxels per 1 mm step
-    const float rq = 1.0f / fmaxf(step, 1e-3f);
+    const float rq = 0.999999f / fmaxf(step, 1e-3f);                   // rounded down: a jump computed from it never over-skips
     const bool skip_ok = FMT == 1 && fmaxf(v.rev_eps[0], fmaxf(v.rev_eps[1], v.rev_eps[2])) <= 0.1f;
     const float kM = 12582912.0f;
     int depth = d0;
@@ -166,30 +167,29 @@ __device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float
     for (;;) {
         if (depth - d0 > a.step_cap) { n_runaway++; return false; }
         if (FMT == 1 && depth >= s_in && depth <= s_out) {
-            const float s_outf = (float)s_out, s_capf = (float)(d0 + a.step_cap);
+            // the line is followed up to s_out and never beyond the step cap (there the exact step below reports the runaway)
+            const float s_outf = (float)s_out, s_limf = fminf(s_outf, (float)(d0 + a.step_cap));
+            const float c1 = fmaf(-1.25f, rq, 1.0f);                                // this step + the skipped ones: floor(d * rq + c1)
             bool need_exact = false;
             for (;;) {
                 const float q0 = fmaf(s, qv0, qc0), q1 = fmaf(s, qv1, qc1), q2 = fmaf(s, qv2, qc2);
                 const float m0 = __fadd_rd(q0, kM), m1 = __fadd_rd(q1, kM), m2 = __fadd_rd(q2, kM);
-                const int ix = __float_as_int(m0) - 0x4B400000, iy = __float_as_int(m1) - 0x4B400000, iz = __float_as_int(m2) - 0x4B400000;
-                unsigned lidx = ((unsigned)ix * pny + (unsigned)iy) * pnz + (unsigned)iz;
+                unsigned lidx = (unsigned)__float_as_int(m0) * a.pnyz + ((unsigned)__float_as_int(m1) * pnz + ((unsigned)__float_as_int(m2) - a.bias));
                 DMF_CHECK_IDX(lidx, v.n_cells, a.counters);
                 const unsigned d = __ldg(v.bytes + lidx);
                 float adv = 1.0f;
-                if (d >= 2u) {
-                    const float df = __int_as_float(0x4B000000 | (int)d) - 8388608.0f;
-                    adv = fminf(__fadd_rd(fmaf(df - 1.25f, rq, 1.0f), kM) - kM, (float)a.step_cap + 1.0f);
-                } else {
+                if (d >= 2u) adv = __fadd_rd(fmaf(__int_as_float(0x4B000000 | (int)d) - 8388608.0f, rq, c1), kM) - kM;
+                else {
                     const float f0 = q0 - (m0 - kM), f1 = q1 - (m1 - kM), f2 = q2 - (m2 - kM);
                     if (!(fminf(f0, fminf(f1, f2)) >= e_safe && fmaxf(f0, fmaxf(f1, f2)) <= 1.0f - e_safe)) { need_exact = true; break; }
-                    if (d == 0u && hash_coords(ix, iy, iz) != chash) {       // an occupied voxel other than the origin: occluded
+                    if (d == 0u && hash_coords(__float_as_int(m0) - 0x4B400000, __float_as_int(m1) - 0x4B400000, __float_as_int(m2) - 0x4B400000) != chash) {   // an occupied voxel other than the origin: occluded
                         const unsigned n = (unsigned)((int)s - depth);
                         n_samples += n + 1u; n_inb += n + 1u; n_skip += n + 1u;
                         return true;
                     }
                 }
                 s += adv;
-                if (!(s <= s_outf) || s > s_capf) break;
+                if (!(s <= s_limf)) break;
             }
             s = fminf(s, s_outf + 1.0f);            // the bytes know nothing of the boundary: steps up to s_out are in bounds by the slab test, later ones are not proven
             const int nd = (int)s;
