@@ -8,6 +8,7 @@
 #include "dmf_integrate.cuh"
 #include "dmf_volume.cuh"
 #include "dmf_setcover.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -259,6 +260,20 @@ int build_volume_device(dmf_ctx* c, size_t n_occ, size_t n_normals) {
     if (n_occ) {
         k_centroid_hash<<<blocks_for(n_occ, 256), 256, 0, st>>>(c->vol, c->d_centroid_hash.as<u64>());
         c->launches++;
+    }
+    // work order of the fast reverse march: ordinals sorted by the Morton code of their voxels (dmf_volume.cuh)
+    v.rev_perm = nullptr;
+    if (n_occ >= 64) {
+        ScopedDevBuf keys_in, keys_out, vals_in, tmp;
+        DMF_TRY(keys_in.reserve(n_occ * 8)); DMF_TRY(keys_out.reserve(n_occ * 8)); DMF_TRY(vals_in.reserve(n_occ * 4)); DMF_TRY(c->d_rev_perm.reserve(n_occ * 4));
+        k_morton_keys<<<blocks_for(n_occ, 256), 256, 0, st>>>(v.occ_ids, (unsigned)n_occ, keys_in.as<u64>(), vals_in.as<unsigned>());
+        size_t tmp_bytes = 0;
+        DMF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.as<u64>(), keys_out.as<u64>(), vals_in.as<unsigned>(), c->d_rev_perm.as<unsigned>(), (int)n_occ, 0, 63, st));
+        DMF_TRY(tmp.reserve(std::max<size_t>(tmp_bytes, 16)));
+        DMF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.as<u64>(), keys_out.as<u64>(), vals_in.as<unsigned>(), c->d_rev_perm.as<unsigned>(), (int)n_occ, 0, 63, st));
+        DMF_CUDA(cudaStreamSynchronize(st));                                          // the temporaries go out of scope
+        c->launches += 2;
+        if (!std::getenv("DMF_REVERSE_NO_PERM")) v.rev_perm = c->d_rev_perm.as<unsigned>();
     }
     DMF_CUDA(cudaEventRecord(c->ev_p1, st));
     DMF_CUDA(cudaGetLastError());
@@ -611,7 +626,7 @@ void dmf_destroy(dmf_ctx* c) {
                       &c->d_view_mark, &c->d_good_bits, &c->d_first_view, &c->d_observed, &c->d_axis[0], &c->d_axis[1], &c->d_axis[2], &c->d_xtab, &c->d_ytab, &c->d_ztab, &c->d_kstart,
                       &c->d_poses[0], &c->d_poses[1], &c->d_inv_poses, &c->d_first_key, &c->d_ray_key, &c->d_ray_occ, &c->d_tmp_a, &c->d_tmp_b,
                       &c->d_out_occ, &c->d_n_ids, &c->d_offsets, &c->d_ids, &c->d_misc[0], &c->d_misc[1], &c->d_misc[2], &c->d_misc[3], &c->d_counters,
-                      &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err, &c->d_tile_rec};
+                      &c->d_scan, &c->d_dt_tmp, &c->d_macro_dist[0], &c->d_macro_dist[1], &c->d_err, &c->d_tile_rec, &c->d_rev_perm};
     c->graph_fwd_ids.drop(); c->graph_rev_ids.drop();
     for (auto* b : bufs) b->release();
     c->stage.release();

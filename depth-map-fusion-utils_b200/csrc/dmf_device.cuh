@@ -146,6 +146,7 @@ struct VolDev {
     float rev_eps[3]; // bound (voxel units) on |reverse-march sample - its line point|; > 0.1 disables skipping there
     float rev_esafe;  // a line point at least this far from every face of its voxel shares the voxel with the reference's sample
     float ext[3];    // >= (vmax-vmin)/delta: the volume's extent in voxel units (dim <= ext < dim+1, constructVolume truncates)
+    const unsigned* __restrict__ rev_perm;   // [n_occ] occupied ordinals in Morton order of their voxels: thread t of k_reverse<FAST> marches ordinal rev_perm[t] (null: t)
 };
 
 // The distance bytes hold the distance to the nearest OCCUPIED voxel only (dmf_distance.cuh).  A march that counts the samples it

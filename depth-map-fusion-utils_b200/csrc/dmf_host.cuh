@@ -47,6 +47,8 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+struct ScopedDevBuf : DevBuf { ~ScopedDevBuf() { release(); } };      // a temporary of one call
+
 // grow-only pinned host staging (small results leave the device through it: one asynchronous copy, one synchronisation)
 struct HostStage {
     void* p = nullptr; size_t cap = 0;
@@ -174,6 +176,7 @@ struct dmf_ctx {
     dmf::DevBuf d_scan, d_dt_tmp, d_macro_dist[2], d_err;   // scan scratch, distance-transform ping-pong, macro-cell distances, error words
     dmf::DevBuf d_bricks /* bit grid words */, d_macro, d_prefix, d_rank2occ, d_bytes, d_noff, d_normals, d_occ_ids, d_centroid_hash;
     bool bytes_built = false;
+    dmf::DevBuf d_rev_perm;                     // occupied ordinals in Morton order of their voxels (work order of k_reverse<FAST>)
     dmf::DevBuf d_tile_rec;                     // k_tile_start: [n_views][tiles] 64-bit records (sample intervals + cone pre-march) read by k_forward_line
     int auto_uses = 0;                    // forward calls with DMF_GRID_AUTO since the volume was uploaded
     int reverse_format = DMF_GRID_BYTE;   // grid the reverse march probes (dmf_set_reverse_format)

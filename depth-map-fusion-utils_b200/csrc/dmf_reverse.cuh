@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(128, REV_MIN_BLOCKS) k_reverse(const RevArgs a
         live = t < (size_t)v.n_occ;
         if (live) {
             int xid, yid, zid;
-            occ = (int)t;
+            occ = v.rev_perm ? (int)__ldg(v.rev_perm + t) : (int)t;               // Morton work order (dmf_volume.cuh)
             occ_centroid(v, occ, xid, yid, zid, cx, cy, cz);
             chash = __ldg(a.centroid_hash + occ);
         }
@@ -344,7 +344,18 @@ __global__ void __launch_bounds__(128, REV_MIN_BLOCKS) k_reverse(const RevArgs a
             }
         }
     }
-    if (FAST) {
+    if (FAST && v.rev_perm) {
+        // Morton work order: a warp's 32 voxels are neighbours in space, not in ordinal -- every unoccluded voxel sets its own bits
+        if (f_unocc) {
+            if (a.found_any) raise_flag(a.found_any + view);
+            const unsigned w = (unsigned)occ >> 5, m = 1u << (occ & 31);
+            if (a.unocc) atomicOr(a.unocc + (size_t)view * a.vis_words32 + w, m);
+            if (f_emit) {
+                if (a.viz) atomicOr(a.good_bits + w, m);                             // :112, :215
+                if (a.vis) atomicOr(a.vis + (size_t)view * a.vis_stride32 + w, m);
+            }
+        }
+    } else if (FAST) {
         // thread t <-> occupied ordinal t: the 32 lanes of a warp own exactly one word of every per-voxel bitset, so the warp
         // publishes its results with one atomic per bitset instead of one per voxel
         const unsigned mu = __ballot_sync(0xffffffffu, f_unocc), me = __ballot_sync(0xffffffffu, f_emit);

@@ -43,3 +43,26 @@ __global__ void k_vol_check_csr(const unsigned* __restrict__ noff, unsigned n_oc
         if (noff[i + 1] < noff[i]) atomicMin(err + 2, i);
     if (blockIdx.x == 0 && threadIdx.x == 0 && noff[0] != 0u) atomicMin(err + 2, 0u);
 }
+
+// ---- work order of the fast reverse march ---------------------------------------------------------------------------------
+// k_reverse<FAST> gives every occupied voxel a thread, and a warp waits for its longest march.  occupied_cells_ order is the order
+// points were integrated in -- for a scanned surface typically x-major, so that consecutive ordinals alternate between the near and
+// the far wall of whatever the object is (two voxels per (x, y) column of a shell): half the lanes of a warp are occluded at once,
+// the other half march to the end of the volume.  Marching the ordinals in MORTON order of their voxels puts 32 neighbours of one
+// surface patch into a warp: their rays are near-parallel and end alike.  Results are bit sets over ordinals -- order-free.
+__device__ __forceinline__ unsigned long long spread3_21(unsigned long long x) {      // 21 bits -> every third bit of 63
+    x &= 0x1FFFFFull;
+    x = (x | (x << 32)) & 0x1F00000000FFFFull;
+    x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+__global__ void k_morton_keys(const unsigned long long* __restrict__ occ_ids, unsigned n, unsigned long long* __restrict__ keys, unsigned* __restrict__ vals) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long id = occ_ids[i];
+    keys[i] = (spread3_21(id >> 40) << 2) | (spread3_21((id >> 20) & 0xFFFFFull) << 1) | spread3_21(id & 0xFFFFFull);
+    vals[i] = i;
+}
