@@ -264,14 +264,14 @@ int build_volume_device(dmf_ctx* c, size_t n_occ, size_t n_normals) {
     // work order of the fast reverse march: ordinals sorted by the Morton code of their voxels (dmf_volume.cuh)
     v.rev_perm = nullptr;
     if (n_occ >= 64) {
-        ScopedDevBuf keys_in, keys_out, vals_in, tmp;
+        // (the context's call scratch serves as temporaries: grow-only, stream-ordered, nothing to free or wait for)
+        DevBuf &keys_in = c->d_tmp_a, &keys_out = c->d_tmp_b, &vals_in = c->d_misc[0], &tmp = c->d_misc[1];
         DMF_TRY(keys_in.reserve(n_occ * 8)); DMF_TRY(keys_out.reserve(n_occ * 8)); DMF_TRY(vals_in.reserve(n_occ * 4)); DMF_TRY(c->d_rev_perm.reserve(n_occ * 4));
         k_morton_keys<<<blocks_for(n_occ, 256), 256, 0, st>>>(v.occ_ids, (unsigned)n_occ, keys_in.as<u64>(), vals_in.as<unsigned>());
         size_t tmp_bytes = 0;
         DMF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.as<u64>(), keys_out.as<u64>(), vals_in.as<unsigned>(), c->d_rev_perm.as<unsigned>(), (int)n_occ, 0, 63, st));
         DMF_TRY(tmp.reserve(std::max<size_t>(tmp_bytes, 16)));
         DMF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.as<u64>(), keys_out.as<u64>(), vals_in.as<unsigned>(), c->d_rev_perm.as<unsigned>(), (int)n_occ, 0, 63, st));
-        DMF_CUDA(cudaStreamSynchronize(st));                                          // the temporaries go out of scope
         c->launches += 2;
         if (!std::getenv("DMF_REVERSE_NO_PERM")) v.rev_perm = c->d_rev_perm.as<unsigned>();
     }

@@ -47,8 +47,6 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
-struct ScopedDevBuf : DevBuf { ~ScopedDevBuf() { release(); } };      // a temporary of one call
-
 // grow-only pinned host staging (small results leave the device through it: one asynchronous copy, one synchronisation)
 struct HostStage {
     void* p = nullptr; size_t cap = 0;
