@@ -268,10 +268,13 @@ int build_volume_device(dmf_ctx* c, size_t n_occ, size_t n_normals) {
         DevBuf &keys_in = c->d_tmp_a, &keys_out = c->d_tmp_b, &vals_in = c->d_misc[0], &tmp = c->d_misc[1];
         DMF_TRY(keys_in.reserve(n_occ * 8)); DMF_TRY(keys_out.reserve(n_occ * 8)); DMF_TRY(vals_in.reserve(n_occ * 4)); DMF_TRY(c->d_rev_perm.reserve(n_occ * 4));
         k_morton_keys<<<blocks_for(n_occ, 256), 256, 0, st>>>(v.occ_ids, (unsigned)n_occ, keys_in.as<u64>(), vals_in.as<unsigned>());
+        int axis_bits = 1;                                                            // the keys interleave three coordinates < dim: sort only the bits they use
+        while (axis_bits < 21 && (1 << axis_bits) < std::max(v.dim[0], std::max(v.dim[1], v.dim[2]))) axis_bits++;
+        const int end_bit = 3 * axis_bits;
         size_t tmp_bytes = 0;
-        DMF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.as<u64>(), keys_out.as<u64>(), vals_in.as<unsigned>(), c->d_rev_perm.as<unsigned>(), (int)n_occ, 0, 63, st));
+        DMF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.as<u64>(), keys_out.as<u64>(), vals_in.as<unsigned>(), c->d_rev_perm.as<unsigned>(), (int)n_occ, 0, end_bit, st));
         DMF_TRY(tmp.reserve(std::max<size_t>(tmp_bytes, 16)));
-        DMF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.as<u64>(), keys_out.as<u64>(), vals_in.as<unsigned>(), c->d_rev_perm.as<unsigned>(), (int)n_occ, 0, 63, st));
+        DMF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.as<u64>(), keys_out.as<u64>(), vals_in.as<unsigned>(), c->d_rev_perm.as<unsigned>(), (int)n_occ, 0, end_bit, st));
         c->launches += 2;
         if (!std::getenv("DMF_REVERSE_NO_PERM")) v.rev_perm = c->d_rev_perm.as<unsigned>();
     }
