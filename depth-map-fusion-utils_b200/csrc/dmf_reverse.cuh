@@ -158,9 +158,12 @@ __device__ __forceinline__ bool march_collides(const RevArgs& a, float cx, float
             const float ta = (0.25f - qc[ax]) * r, tb = (fminf(v.ext[ax], (float)v.dim[ax]) - 0.25f - qc[ax]) * r;
             t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
         }
-        if (t0 <= t1) {      // one step of guard on each end for the few ulps of error in t0, t1
-            s_in = (int)fminf(fmaxf(ceilf(t0) + 1.0f, (float)d0), 1.0e9f);
-            s_out = (int)fminf(fmaxf(floorf(t1) - 1.0f, -1.0f), 1.0e9f);
+        if (t0 <= t1) {
+            // t0, t1 carry a relative error < 2^-20 (one subtraction, __fdividef, one product): guard g(t) = 2^-6 + |t| * 2^-17 steps on each
+            // end, as in k_tile_start.  (A whole step of guard per end, as in round 1, puts one more exactly evaluated step into the band
+            // where an unoccluded ray leaves the volume -- and those bands are most of the exact steps of a sweep.)
+            s_in = (int)fminf(fmaxf(ceilf(t0 + fmaf(fabsf(t0), 7.62939453125e-06f, 0.015625f)), (float)d0), 1.0e9f);
+            s_out = (int)fminf(fmaxf(floorf(t1 - fmaf(fabsf(t1), 7.62939453125e-06f, 0.015625f)), -1.0f), 1.0e9f);
         }
     }
     const float e_safe = v.rev_esafe;
